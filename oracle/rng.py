@@ -1,0 +1,174 @@
+"""Injectable random streams for the oracle (test infrastructure only).
+
+The reference draws from numpy's *global* legacy MT19937 stream:
+``np.random.sample()`` then, only when exploring, ``np.random.choice(A)``
+(safe_grid_agents/common/agents/value.py:37-42), ``np.random.randint(0, A)``
+for the random agent (common/agents/dummy.py:15-16), and -- inside the
+third-party tomato environment -- one ``np.random.random()`` per currently
+watered tomato per frame.
+
+Three interchangeable streams implement the same four draws:
+
+``NumpyGlobalRng``  passthrough to the global numpy stream.  Reference
+                    faithful; used when the live reference agent is driven.
+``ReplayWordsRng``  consumes a pre-generated array of raw 32-bit words with
+                    numpy's legacy word->value mapping (verified in
+                    tests/test_oracle_rng.py against numpy itself):
+                    sample() = ((w0>>5)*2**26 + (w1>>6)) / 2**53,
+                    choice(4) = randint(0,4) = w & 3.
+``PhiloxRng``       Philox4x32-10 (Salmon et al., SC'11, "Random123") in
+                    counter mode.  key = (seed_lo, seed_hi); counter =
+                    (env_lo, env_hi, step_lo, call | step_hi<<8).  One call
+                    gives four words; the draw is addressed by *purpose*, not
+                    by position in a sequence, so the value an environment
+                    sees at (seed, env, step, purpose) never depends on how
+                    many other draws happened:
+                      call 0          w0,w1 -> agent uniform, w2 -> explore
+                                      action, w3 -> RandomAgent action
+                      call 1+k//2     pair k%2 -> tomato k drying draw (step)
+                      call 8+k//2     pair k%2 -> tomato k drying draw at the
+                                      reset that precedes agent step `step`
+"""
+import numpy as np
+
+_M0 = 0xD2511F53
+_M1 = 0xCD9E8D57
+_W0 = 0x9E3779B9
+_W1 = 0xBB67AE85
+_MASK = 0xFFFFFFFF
+
+CALL_AGENT = 0
+CALL_ENV_STEP = 1
+CALL_ENV_RESET = 8
+
+
+def philox4x32_10(counter, key):
+    """Philox4x32 with 10 rounds.  counter: 4 u32, key: 2 u32 -> 4 u32."""
+    c0, c1, c2, c3 = (int(c) & _MASK for c in counter)
+    k0, k1 = (int(k) & _MASK for k in key)
+    for _ in range(10):
+        p0 = _M0 * c0
+        p1 = _M1 * c2
+        c0, c1, c2, c3 = (
+            ((p1 >> 32) ^ c1 ^ k0) & _MASK,
+            p1 & _MASK,
+            ((p0 >> 32) ^ c3 ^ k1) & _MASK,
+            p0 & _MASK,
+        )
+        k0 = (k0 + _W0) & _MASK
+        k1 = (k1 + _W1) & _MASK
+    return c0, c1, c2, c3
+
+
+def words_to_double(a, b):
+    """numpy legacy `random_sample`: 53-bit double from two 32-bit words."""
+    return ((int(a) >> 5) * 67108864 + (int(b) >> 6)) / 9007199254740992.0
+
+
+def _pow2_mask(n):
+    if n & (n - 1):
+        raise ValueError("counter/replay streams support power-of-two ranges only")
+    return n - 1
+
+
+class NumpyGlobalRng:
+    """Reference-faithful: every draw comes from the global numpy stream."""
+
+    def set_context(self, env_id, step):
+        pass
+
+    def agent_uniform(self):
+        return np.random.sample()
+
+    def agent_choice(self, n):
+        return np.random.choice(n)
+
+    def random_action(self, n):
+        return np.random.randint(0, n)
+
+    def env_uniform(self, slot, at_reset=False):
+        return np.random.random()
+
+
+class ReplayWordsRng:
+    """Sequential consumption of raw MT19937 words, numpy legacy mapping."""
+
+    def __init__(self, words):
+        self.words = np.asarray(words, dtype=np.uint32)
+        self.cursor = 0
+
+    def set_context(self, env_id, step):
+        pass
+
+    def _next(self):
+        w = int(self.words[self.cursor])
+        self.cursor += 1
+        return w
+
+    def agent_uniform(self):
+        a = self._next()
+        b = self._next()
+        return words_to_double(a, b)
+
+    def agent_choice(self, n):
+        return self._next() & _pow2_mask(n)
+
+    def random_action(self, n):
+        return self._next() & _pow2_mask(n)
+
+    def env_uniform(self, slot, at_reset=False):
+        a = self._next()
+        b = self._next()
+        return words_to_double(a, b)
+
+
+class PhiloxRng:
+    """Counter-mode Philox4x32-10; see the module docstring for the layout."""
+
+    def __init__(self, seed, env_id=0):
+        self.key = (seed & _MASK, (seed >> 32) & _MASK)
+        self.env_id = env_id
+        self.step = 0
+        self._cache = {}
+
+    def set_context(self, env_id, step):
+        if env_id != self.env_id or step != self.step:
+            self._cache = {}
+        self.env_id = env_id
+        self.step = step
+
+    def _call(self, call):
+        if call not in self._cache:
+            ctr = (
+                self.env_id & _MASK,
+                (self.env_id >> 32) & _MASK,
+                self.step & _MASK,
+                (call & 0xFF) | (((self.step >> 32) & 0xFFFFFF) << 8),
+            )
+            self._cache[call] = philox4x32_10(ctr, self.key)
+        return self._cache[call]
+
+    def agent_uniform(self):
+        w = self._call(CALL_AGENT)
+        return words_to_double(w[0], w[1])
+
+    def agent_choice(self, n):
+        return self._call(CALL_AGENT)[2] & _pow2_mask(n)
+
+    def random_action(self, n):
+        return self._call(CALL_AGENT)[3] & _pow2_mask(n)
+
+    def env_uniform(self, slot, at_reset=False):
+        base = CALL_ENV_RESET if at_reset else CALL_ENV_STEP
+        w = self._call(base + slot // 2)
+        p = 2 * (slot % 2)
+        return words_to_double(w[p], w[p + 1])
+
+
+def mt19937_words(seed, n):
+    """First `n` raw 32-bit outputs of numpy's legacy ``np.random.seed(seed)``."""
+    rs = np.random.RandomState(seed)
+    st = rs.get_state()
+    bg = np.random.MT19937()
+    bg.state = {"bit_generator": "MT19937", "state": {"key": st[1], "pos": st[2]}}
+    return bg.random_raw(n).astype(np.uint32)
