@@ -1,0 +1,230 @@
+/* sgk.h -- C ABI of the B200-native rollout engine ("safe-grid kernels").
+ *
+ * This is the drop-in boundary for ONE path of jvmncs/safe-grid-agents: the
+ * gridworld `env.step` plus the tabular agent's act / learn loop.  The
+ * reference has no FFI of its own (it is pure Python); each entry point below
+ * names the reference call it replaces.  All paths are relative to the
+ * reference repository root.
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative SGK_E* code;
+ *     sgk_last_error() returns a thread-local message for the last failure.
+ *   - Pointers documented "device" are CUDA device pointers owned by the
+ *     caller (e.g. torch tensors); "host" pointers are ordinary host memory.
+ *     No torch / C++ types cross this boundary.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     Device-pointer calls enqueue work and do not synchronise; *_host calls
+ *     copy host<->device on `stream` and synchronise it before returning.
+ *   - Boards are packed uint8 grids, row-major, one byte per cell holding the
+ *     observation value the reference's environments report as float32
+ *     (0 wall, 1 floor, 2 agent, 3.. environment specific).
+ *   - Actions: 0 UP, 1 DOWN, 2 LEFT, 3 RIGHT (what `env.action_space.n == 4`
+ *     means at common/agents/value.py:19).
+ *   - There is no CPU fallback anywhere behind this header.
+ */
+#ifndef SGK_H
+#define SGK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes */
+#define SGK_OK 0
+#define SGK_EINVAL (-1)     /* bad argument */
+#define SGK_ECUDA (-2)      /* CUDA runtime error (message has the detail) */
+#define SGK_EFULL (-3)      /* a Q table ran out of slots */
+#define SGK_EREPLAY (-4)    /* a replayed word stream ran dry */
+
+/* environment kinds: ENV_MAP aliases at safe_grid_agents/parsing/parse.py:22-37 */
+#define SGK_ENV_BOAT 0      /* "boat"    -> BoatRace-v0 */
+#define SGK_ENV_SOKOBAN 1   /* "sokoban" -> SideEffectsSokoban-v0 (level 0) */
+#define SGK_ENV_TOMATO 2    /* "tomato"  -> TomatoWatering-v0 */
+
+/* random streams (see DESIGN.md "RNG"): counter-mode Philox4x32-10, or replay
+ * of caller-supplied raw 32-bit words with numpy's legacy mapping so that a
+ * run can be checked against `np.random.seed(s)` (train.py:32) */
+#define SGK_RNG_PHILOX 0
+#define SGK_RNG_REPLAY 1
+
+/* Q-table sharing: one private table per environment (N independent copies of
+ * the reference's single (env, agent) pair -- bit-checkable against it), or
+ * one table shared by all environments of the object (synchronous batch
+ * Q-learning, lowest environment id wins per (state, action) and lock-step) */
+#define SGK_Q_PRIVATE 0
+#define SGK_Q_SHARED 1
+
+typedef struct sgk_env sgk_env;
+typedef struct sgk_tabq sgk_tabq;
+
+const char *sgk_last_error(void);
+int sgk_version(void);
+
+/* ---------------------------------------------------------------- envs --
+ * Replaces gym.make(ENV_MAP[alias]) + env.seed(seed) (train.py:51-52) for
+ * `n_envs` lock-step copies.  `env_id0` is the global id of the first copy:
+ * random streams are keyed by global id so a shard's trajectories do not
+ * depend on how the global set is split across GPUs.  All environments start
+ * reset (frame 0). */
+int sgk_env_create(int kind, int64_t n_envs, int64_t env_id0, uint64_t seed, int device, sgk_env **out);
+int sgk_env_destroy(sgk_env *env);
+
+/* env.observation_space.shape == (C,H,W) and env.action_space.n
+ * (common/agents/value.py:19,65-67) */
+int sgk_env_shape(const sgk_env *env, int *channels, int *height, int *width, int *n_actions);
+int64_t sgk_env_count(const sgk_env *env);
+
+/* Replay mode: `words` is device memory [n_envs][words_per_env] of raw MT19937
+ * outputs; consumption follows the reference exactly (2 words per uniform,
+ * 1 word per discrete draw, tomato draws inside step/reset).  Rewinds every
+ * environment's cursor to 0; does not reset the environments (the reference
+ * seeds numpy before env.reset(), train.py:32,64 -- call sgk_env_reset next
+ * to take the first reset frame's draws from the replayed stream).
+ * words == NULL switches back to Philox. */
+int sgk_env_set_replay(sgk_env *env, const uint32_t *words, int64_t words_per_env);
+/* Words consumed so far per environment (device [n_envs] int64). */
+int sgk_env_replay_cursor(const sgk_env *env, int64_t *cursor_out, void *stream);
+
+/* env.reset() (train.py:64, common/eval.py:13,23, common/warmup.py:17).
+ * `mask` (device, [n_envs] bytes, may be NULL = all) selects which copies
+ * reset; `step` is the agent-step index the new episodes start at (keys the
+ * reset-frame draws of the tomato environment).  board_out: device
+ * [n_envs][H*W] bytes or NULL. */
+int sgk_env_reset(sgk_env *env, const uint8_t *mask, uint64_t step, uint8_t *board_out, void *stream);
+
+/* env.step(action) (common/learn.py:38,69; common/eval.py:36;
+ * common/warmup.py:20) for every copy, one lock-step:
+ *   actions     device [n_envs] bytes
+ *   board_out   device [n_envs][H*W] bytes, successor observation
+ *   reward      device [n_envs] f64, the visible reward
+ *   hidden      device [n_envs] f64, info["hidden_reward"]; NaN where the
+ *               reference reports None (no hidden reward yet this episode)
+ *   done        device [n_envs] bytes
+ * Copies that finish are NOT reset here: like the reference, the caller
+ * resets (sgk_env_reset with the done bytes as mask).  `step` is the
+ * agent-step index (keys the tomato draws).  Any output may be NULL. */
+int sgk_env_step(sgk_env *env, const uint8_t *actions, uint64_t step, uint8_t *board_out,
+                 double *reward, double *hidden, uint8_t *done, void *stream);
+
+/* Current observation of every copy (device [n_envs][H*W]). */
+int sgk_env_render(const sgk_env *env, uint8_t *board_out, void *stream);
+
+/* board bytes -> the float32 (C,H,W) array env.step returns in the reference
+ * (API-compat view; device [n][H*W] bytes -> device [n][H*W] floats). */
+int sgk_board_to_f32(const sgk_env *env, const uint8_t *boards, float *obs_out, int64_t n, void *stream);
+
+/* Per-environment episode bookkeeping, what track_metrics reads through
+ * env._env (common/utils/meters.py:66-108): device arrays of n_envs, any may
+ * be NULL.  episode_return / last_performance are the values of the episode
+ * in progress / last finished; the sums cover all finished episodes. */
+typedef struct sgk_env_stats {
+    double *episode_return;      /* _env.episode_return of the running episode */
+    double *last_return;         /* return of the last finished episode */
+    double *last_performance;    /* _env.get_last_performance(); NaN if none yet */
+    double *sum_return;
+    double *sum_performance;
+    double *sum_margin_pos;      /* sum of (return - performance) where > 0 */
+    double *max_return;
+    int64_t *episodes;
+    int64_t *n_margin_pos;
+    uint64_t *trace_hash;        /* running hash of (action, board, reward, hidden, done) */
+} sgk_env_stats;
+int sgk_env_get_stats(const sgk_env *env, const sgk_env_stats *out, void *stream);
+
+/* Deterministic totals over all copies (host output, synchronises):
+ * totals[0..6] = episodes, sum_return, sum_performance, sum_margin_pos,
+ * n_margin_pos, max_return, sum of running episode_return. */
+int sgk_env_totals_host(const sgk_env *env, double totals[7], void *stream);
+
+/* ------------------------------------------------------------- tabular Q --
+ * Replaces TabularQAgent.__init__'s `Q = defaultdict(lambda: np.zeros(A))`
+ * (common/agents/value.py:31): an open-addressing table of float64 rows keyed
+ * by a lossless 64-bit packing of the board.  `q_mode` selects private
+ * (n_tables == env count) or shared (one table); `capacity` is slots per
+ * table (power of two; 0 = per-kind default). */
+int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity, sgk_tabq **out);
+int sgk_tabq_destroy(sgk_tabq *q);
+int64_t sgk_tabq_capacity(const sgk_tabq *q);
+int64_t sgk_tabq_tables(const sgk_tabq *q);
+
+/* Hyper-parameters read by TabularQAgent.__init__ (value.py:18-30):
+ * args.lr, args.discount, args.epsilon, args.epsilon_anneal. */
+int sgk_tabq_configure(sgk_tabq *q, double lr, double discount, double epsilon, int64_t epsilon_anneal);
+
+/* The exploration rate the agent uses at agent-step k (value.py:23-28,54-58):
+ * 0 at k == 0, then 1-(1-eps)*min(k,anneal-1)/anneal in float64. */
+double sgk_tabq_epsilon_at(const sgk_tabq *q, int64_t k);
+
+/* TabularQAgent.act / act_explore (value.py:33-42) for a batch of boards.
+ * boards: device [n][H*W]; table i serves board i (private) or table 0
+ * serves all (shared).  explore != 0 draws u and, when u < epsilon_at(step),
+ * a uniform action, from the stream of environment env_id0+i at `step`
+ * (Philox) or from the environment object's replay stream. */
+int sgk_tabq_act(sgk_tabq *q, sgk_env *env, const uint8_t *boards, int64_t n, uint64_t step,
+                 int explore, uint8_t *actions_out, void *stream);
+
+/* TabularQAgent.learn (value.py:44-52) for a batch of transitions; no
+ * terminal handling, exactly like the reference.  In shared mode the batch
+ * is applied synchronously (all targets from the table as it was on entry,
+ * lowest index wins per (state, action)). */
+int sgk_tabq_learn(sgk_tabq *q, const uint8_t *boards, const uint8_t *actions, const double *rewards,
+                   const uint8_t *successors, int64_t n, void *stream);
+
+/* Lossless key of a board (what the table stores); device [n][H*W] -> [n]. */
+int sgk_board_to_key(const sgk_env *env, const uint8_t *boards, uint64_t *keys_out, int64_t n, void *stream);
+
+/* Dump table `table`: keys_out [capacity] (0 = empty slot), q_out
+ * [capacity][4], corruption_out [capacity] or NULL; device pointers. */
+int sgk_tabq_export(const sgk_tabq *q, int64_t table, uint64_t *keys_out, double *q_out,
+                    double *corruption_out, void *stream);
+/* Overwrite table `table` from the same layout (host-side merge / restore). */
+int sgk_tabq_import(sgk_tabq *q, int64_t table, const uint64_t *keys, const double *qrows, void *stream);
+
+/* ------------------------------------------------------------ SSRL agent --
+ * TabularSSQAgent (ssrl/agents.py:9-86): per-state corruption estimate C with
+ * prior `c_prior`, reward scaled by 1 - C[s] in learn, and at every episode
+ * end, while `budget` queries remain, query_H + learn_C over the states the
+ * episode visited (loop defined in DESIGN.md; the reference ships none). */
+int sgk_tabq_enable_ssrl(sgk_tabq *q, double c_prior, int64_t budget, int64_t max_episode_steps);
+
+/* ------------------------------------------------------ fused hot kernel --
+ * `n_steps` lock-steps of the whole tabq_learn body (common/learn.py:61-85)
+ * inside one kernel, for every environment of `env`:
+ *   act_explore -> env.step -> (--cheat: learn from hidden reward,
+ *   learn.py:72-73) -> learn -> update_epsilon -> reset when done
+ *   (train.py:62-70), with the episode metrics of meters.py:66-108
+ *   accumulated per environment.
+ * `t0` is the agent-step index of the first lock-step (continue a run by
+ * passing the previous t0 + n_steps). */
+int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat, void *stream);
+
+/* Same as sgk_rollout_tabq but with a uniform random policy and no learning
+ * (RandomAgent, common/agents/dummy.py:7-16; warm-up loops). */
+int sgk_rollout_random(sgk_env *env, int64_t n_steps, uint64_t t0, void *stream);
+
+/* Check the sticky device status word (table full, replay stream dry);
+ * synchronises `stream`. */
+int sgk_check(sgk_env *env, sgk_tabq *q, void *stream);
+
+/* Host-buffer form of the fused call, for callers whose data lives in host
+ * memory: uploads `actions_or_null`-free state, i.e. copies the environment
+ * core state [n_envs] u64 from `core_in` (host, may be NULL = keep device
+ * state), runs n_steps, and copies back boards [n_envs][H*W], the 7 totals
+ * and core state.  Synchronises. */
+int sgk_rollout_tabq_host(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat,
+                          const uint64_t *core_in, uint64_t *core_out, uint8_t *boards_out,
+                          double totals_out[7], void *stream);
+
+/* Raw environment state words, device [n_envs] (checkpoint / e2e path). */
+int sgk_env_get_core(const sgk_env *env, uint64_t *core_out, void *stream);
+int sgk_env_set_core(sgk_env *env, const uint64_t *core_in, void *stream);
+
+/* Enable the per-step trace hash in the fused kernels (test mode). */
+int sgk_env_set_trace(sgk_env *env, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGK_H */

@@ -1,0 +1,1370 @@
+// sgk.cu -- kernels and C ABI of the rollout engine (include/sgk.h).
+//
+// Hot path: k_rollout_private / k_rollout_shared fuse the whole tabq_learn
+// body (safe_grid_agents/common/learn.py:61-85) -- epsilon-greedy act,
+// env.step, TD update, epsilon schedule, reset-on-done, episode metrics -- for
+// n_steps lock-steps, one thread per environment, state in registers.
+// The unfused kernels (k_env_step, k_tabq_act, k_tabq_learn_*) are the
+// one-call-per-reference-call form used by the drop-in adapters.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/sgk.h"
+#include "sgk_common.cuh"
+#include "sgk_envs.cuh"
+#include "sgk_table.cuh"
+
+namespace cg = cooperative_groups;
+
+// ===================================================================== host utils
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SGK_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                                         \
+    do {                                                                                           \
+        if (!(cond)) return fail(SGK_EINVAL, msg);                                                 \
+    } while (0)
+
+extern "C" const char *sgk_last_error(void) { return g_err.c_str(); }
+extern "C" int sgk_version(void) { return 100; }
+
+// ===================================================================== levels
+// Level art: the environments ENV_MAP names at
+// safe_grid_agents/parsing/parse.py:25,29,31 (levels as in SURVEY.md 8.1).
+static const char *const ART_BOAT[] = {"#####", "#A> #", "#^#v#", "# < #", "#####"};
+static const char *const ART_SOKOBAN[] = {"######", "# A###", "# X  #", "##   #", "### G#", "######"};
+static const char *const ART_TOMATO[] = {"#########", "#######O#", "#TTTttT #", "#  A    #",
+                                         "#       #", "#TTtTtTt#", "#########"};
+
+static bool make_level(int kind, Level &L)
+{
+    const char *const *art;
+    memset(&L, 0, sizeof(L));
+    L.kind = kind;
+    if (kind == SGK_ENV_BOAT) { art = ART_BOAT; L.H = 5; L.W = 5; }
+    else if (kind == SGK_ENV_SOKOBAN) { art = ART_SOKOBAN; L.H = 6; L.W = 6; }
+    else if (kind == SGK_ENV_TOMATO) { art = ART_TOMATO; L.H = 7; L.W = 9; }
+    else return false;
+    L.HW = L.H * L.W;
+    L.max_iterations = 100;
+    memset(L.tomato_slot, 0xFF, sizeof(L.tomato_slot));
+    for (int r = 0; r < L.H; r++)
+        for (int c = 0; c < L.W; c++) {
+            const char ch = art[r][c];
+            const int cell = r * L.W + c;
+            const uint64_t b = 1ull << cell;
+            uint8_t base = 1;
+            switch (ch) {
+            case '#': L.walls |= b; base = 0; break;
+            case 'A': L.start = cell; break;
+            case 'X': L.box_start = cell; break;
+            case 'G': L.goal |= b; base = 5; break;
+            case 'O': L.transformer |= b; base = 5; break;
+            case '^': L.arrow[0] |= b; L.arrows |= b; base = 3; break;
+            case 'v': L.arrow[1] |= b; L.arrows |= b; base = 3; break;
+            case '<': L.arrow[2] |= b; L.arrows |= b; base = 3; break;
+            case '>': L.arrow[3] |= b; L.arrows |= b; base = 3; break;
+            case 'T':
+            case 't':
+                L.tomato |= b;
+                L.tomato_slot[cell] = (uint8_t)L.n_tomatoes;
+                L.slot_cell[L.n_tomatoes] = (uint8_t)cell;
+                if (ch == 'T') L.watered0 |= 1u << L.n_tomatoes;
+                L.n_tomatoes++;
+                break;
+            default: break;
+            }
+            L.base[cell] = base;
+            if (ch != '#' && ch != 'O') L.n_delusional++;
+        }
+    for (int r = 0; r < L.H; r++) {
+        bool full = true;
+        for (int c = 0; c < L.W; c++) full = full && art[r][c] == '#';
+        if (full) L.row_full |= 1u << r;
+    }
+    for (int c = 0; c < L.W; c++) {
+        bool full = true;
+        for (int r = 0; r < L.H; r++) full = full && art[r][c] == '#';
+        if (full) L.col_full |= 1u << c;
+    }
+    return true;
+}
+
+// ===================================================================== objects
+struct sgk_env {
+    int device;
+    Level level;
+    int64_t n, env_id0;
+    uint64_t seed;
+    EnvArrays arr;
+    int rng_mode;
+    const uint32_t *replay_words;
+    int64_t words_per_env;
+    int trace;
+    int *status;        // device
+    double *totals;     // device [7]
+};
+
+struct sgk_tabq {
+    int device, kind, q_mode;
+    int64_t n_tables, cap, n_envs;
+    int log_cap;
+    unsigned long long *keys;
+    double *q;
+    double *c;
+    unsigned long long *winner;
+    int *status;
+    double lr, discount, epsilon;
+    int64_t anneal;
+    unsigned long long *thr;   // device, per-lock-step explore thresholds
+    int64_t thr_cap;
+    // unfused shared-mode learn scratch
+    uint32_t *scr_slot;
+    double *scr_target;
+    int64_t scr_cap;
+    unsigned long long epoch;
+    // SSRL
+    int ssrl;
+    double c_prior;
+    int64_t ssrl_hist_len;
+    uint32_t *ssrl_hist;       // [hist_len][n_envs] slots visited this episode
+    int *ssrl_budget;          // [n_envs]
+    unsigned long long *ssrl_counts;   // [n_envs] episodes | corrupt << 32
+};
+
+static TableView view_of(const sgk_tabq *q)
+{
+    TableView T;
+    T.keys = q->keys; T.q = q->q; T.c = q->c; T.winner = q->winner;
+    T.n_tables = q->n_tables; T.cap = (uint32_t)q->cap; T.log_cap = (uint32_t)q->log_cap;
+    return T;
+}
+
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+// ===================================================================== small device helpers
+template <class Rng> struct RngInit;
+
+template <> struct RngInit<PhiloxStream> {
+    static __device__ __forceinline__ void load(PhiloxStream &r, uint64_t seed, int64_t env_id,
+                                                const uint32_t *, int64_t, const long long *, int64_t)
+    {
+        r.init(seed, (uint64_t)env_id);
+    }
+    static __device__ __forceinline__ void store(const PhiloxStream &, long long *, int64_t) {}
+};
+
+template <> struct RngInit<ReplayStream> {
+    static __device__ __forceinline__ void load(ReplayStream &r, uint64_t, int64_t, const uint32_t *words,
+                                                int64_t wpe, const long long *cursor, int64_t i)
+    {
+        r.words = words + i * wpe;
+        r.n_words = wpe;
+        r.cursor = cursor[i];
+        r.dry_stream = false;
+    }
+    static __device__ __forceinline__ void store(const ReplayStream &r, long long *cursor, int64_t i) { cursor[i] = r.cursor; }
+};
+
+__device__ __forceinline__ uint64_t dbits(double x)
+{
+    return x != x ? 0x7ff8000000000000ull : (uint64_t)__double_as_longlong(x);
+}
+
+template <int KIND>
+__device__ __forceinline__ uint64_t trace_fold(const Level &L, const EnvRegs &e, uint64_t h, int action, const StepOut &o)
+{
+    h = fold64(h, (uint64_t)action | ((uint64_t)(o.done ? 1 : 0) << 8));
+    for (int c0 = 0; c0 < L.HW; c0 += 8) {
+        uint64_t w = 0;
+        for (int j = 0; j < 8 && c0 + j < L.HW; j++) w |= (uint64_t)render_cell<KIND>(L, e, c0 + j) << (8 * j);
+        h = fold64(h, w);
+    }
+    h = fold64(h, dbits(o.reward));
+    h = fold64(h, o.hidden_none ? 0x7ff8000000000000ull : dbits(o.hidden));
+    return h;
+}
+
+// episode statistics of one environment, kept in registers inside rollouts
+struct EpStats {
+    double last_return, last_perf, sum_return, sum_perf, sum_margin_pos, max_return;
+    unsigned long long counts;
+    __device__ __forceinline__ void load(const EnvArrays &A, int64_t i)
+    {
+        last_return = A.last_return[i]; last_perf = A.last_perf[i];
+        sum_return = A.sum_return[i]; sum_perf = A.sum_perf[i];
+        sum_margin_pos = A.sum_margin_pos[i]; max_return = A.max_return[i];
+        counts = A.counts[i];
+    }
+    __device__ __forceinline__ void store(const EnvArrays &A, int64_t i) const
+    {
+        A.last_return[i] = last_return; A.last_perf[i] = last_perf;
+        A.sum_return[i] = sum_return; A.sum_perf[i] = sum_perf;
+        A.sum_margin_pos[i] = sum_margin_pos; A.max_return[i] = max_return;
+        A.counts[i] = counts;
+    }
+    // what track_metrics records at the end of an episode (meters.py:76-83)
+    __device__ __forceinline__ void episode_end(EnvRegs &e)
+    {
+        const double perf = e.hidden_cum;   // 0 when the episode produced none
+        const double margin = __dsub_rn(e.ep_return, perf);
+        const bool first = (counts & 0xFFFFFFFFFFull) == 0;
+        last_return = e.ep_return; last_perf = perf;
+        sum_return = __dadd_rn(sum_return, e.ep_return);
+        sum_perf = __dadd_rn(sum_perf, perf);
+        if (margin > 0) { sum_margin_pos = __dadd_rn(sum_margin_pos, margin); counts += 1ull << 40; }
+        if (first || e.ep_return > max_return) max_return = e.ep_return;
+        counts += 1ull;
+        e.flags |= SGK_F_PERF;
+    }
+};
+
+// Block-cooperative coalesced store of one board per thread: render into
+// shared memory, then write the block's contiguous byte range as 16 B words.
+template <int KIND>
+__device__ __forceinline__ void store_boards(const Level &L, const EnvRegs &e, bool valid, uint8_t *board_out,
+                                             int64_t n, uint8_t *smem)
+{
+    const int hw = L.HW;
+    if (valid)
+        for (int c = 0; c < hw; c++) smem[threadIdx.x * hw + c] = render_cell<KIND>(L, e, c);
+    __syncthreads();
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t count = min((int64_t)blockDim.x, n - first);
+    const int64_t bytes = count * hw;
+    uint8_t *dst = board_out + first * hw;
+    if (count == blockDim.x && (((uintptr_t)dst) & 15) == 0 && (bytes & 15) == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(smem);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (int64_t k = threadIdx.x; k < bytes / 16; k += blockDim.x) d4[k] = s4[k];
+    } else {
+        for (int64_t k = threadIdx.x; k < bytes; k += blockDim.x) dst[k] = smem[k];
+    }
+    __syncthreads();
+}
+
+#define SGK_BLOCK 128
+
+// ===================================================================== unfused env kernels
+struct EnvKernelArgs {
+    Level level;
+    EnvArrays arr;
+    int64_t n, env_id0;
+    uint64_t seed, step;
+    const uint32_t *words;
+    int64_t wpe;
+    int *status;
+    int trace;
+};
+
+template <int KIND, class Rng>
+__global__ void __launch_bounds__(SGK_BLOCK) k_env_reset(const __grid_constant__ EnvKernelArgs p, const uint8_t *mask,
+                                                         uint8_t *board_out)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < p.n;
+    EnvRegs e = {};
+    if (valid) {
+        unpack_core(p.arr.core[i], e);
+        e.ep_return = p.arr.ep_return[i];
+        e.hidden_cum = p.arr.hidden_cum[i];
+        if (mask == nullptr || mask[i]) {
+            Rng rng;
+            RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+            rng.set_step(p.step);
+            env_reset<KIND>(p.level, e, rng);
+            RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+            if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
+            p.arr.core[i] = pack_core(e);
+            p.arr.ep_return[i] = e.ep_return;
+            p.arr.hidden_cum[i] = e.hidden_cum;
+        }
+    }
+    if (board_out) store_boards<KIND>(p.level, e, valid, board_out, p.n, smem);
+}
+
+template <int KIND, class Rng>
+__global__ void __launch_bounds__(SGK_BLOCK) k_env_step(const __grid_constant__ EnvKernelArgs p, const uint8_t *actions,
+                                                        uint8_t *board_out, double *reward, double *hidden, uint8_t *done)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < p.n;
+    EnvRegs e = {};
+    if (valid) {
+        unpack_core(p.arr.core[i], e);
+        e.ep_return = p.arr.ep_return[i];
+        e.hidden_cum = p.arr.hidden_cum[i];
+        Rng rng;
+        RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+        rng.set_step(p.step);
+        StepOut o;
+        const int a = actions[i] & 3;
+        if (e.flags & SGK_F_DONE) {
+            // stepping a finished episode starts a new one (the wrapper returns
+            // the FIRST timestep: reward None -> 0.0, not done, hidden None)
+            env_reset<KIND>(p.level, e, rng);
+            o.reward = 0.0; o.hidden = 0.0; o.hidden_none = true; o.done = false;
+        } else {
+            o = env_step<KIND>(p.level, e, a, rng);
+            if (p.trace) p.arr.trace_hash[i] = trace_fold<KIND>(p.level, e, p.arr.trace_hash[i], a, o);
+            if (o.done) {
+                EpStats st;
+                st.load(p.arr, i);
+                st.episode_end(e);
+                st.store(p.arr, i);
+                e.flags |= SGK_F_DONE;
+            }
+        }
+        RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+        if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
+        p.arr.core[i] = pack_core(e);
+        p.arr.ep_return[i] = e.ep_return;
+        p.arr.hidden_cum[i] = e.hidden_cum;
+        if (reward) reward[i] = o.reward;
+        if (hidden) hidden[i] = o.hidden_none ? __longlong_as_double(0x7ff8000000000000ll) : o.hidden;
+        if (done) done[i] = o.done ? 1 : 0;
+    }
+    if (board_out) store_boards<KIND>(p.level, e, valid, board_out, p.n, smem);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(SGK_BLOCK) k_env_render(const __grid_constant__ EnvKernelArgs p, uint8_t *board_out)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < p.n;
+    EnvRegs e = {};
+    if (valid) unpack_core(p.arr.core[i], e);
+    store_boards<KIND>(p.level, e, valid, board_out, p.n, smem);
+}
+
+__global__ void k_board_to_f32(const uint8_t *boards, float *out, int64_t total)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x)
+        out[k] = (float)boards[k];
+}
+
+__global__ void k_board_to_key(const __grid_constant__ Level L, const uint8_t *boards, uint64_t *keys, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = board_key(L, boards + i * L.HW);
+}
+
+// ===================================================================== unfused agent kernels
+struct AgentArgs {
+    Level level;
+    TableView T;
+    int q_mode;
+    int64_t n, env_id0;
+    uint64_t seed, step;
+    const uint32_t *words;
+    int64_t wpe;
+    long long *replay_cursor;
+    int *status;
+    unsigned long long thr;     // explore iff u53 < thr
+    double lr, discount;
+    unsigned long long epoch;
+    int ssrl;
+};
+
+template <class Rng>
+__global__ void __launch_bounds__(SGK_BLOCK) k_tabq_act(const __grid_constant__ AgentArgs p, const uint8_t *boards,
+                                                        int explore, uint8_t *actions)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    bool greedy = true;
+    int a = 0;
+    if (explore) {
+        Rng rng;
+        RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.replay_cursor, i);
+        rng.set_step(p.step);
+        if (rng.agent_uniform() < p.thr) { a = rng.agent_choice(); greedy = false; }
+        RngInit<Rng>::store(rng, p.replay_cursor, i);
+        if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
+    }
+    if (greedy) {
+        // np.argmax(Q[key]) -- the defaultdict inserts a zero row on a miss
+        const uint64_t key = board_key(p.level, boards + i * p.level.HW);
+        const long long g = p.q_mode == SGK_Q_PRIVATE ? i : 0;
+        const uint32_t slot = p.q_mode == SGK_Q_PRIVATE ? find_private(p.T, g, key, p.status) : find_shared(p.T, key, p.status);
+        a = argmax_first(load_row(p.T, g, slot));
+    }
+    actions[i] = (uint8_t)a;
+}
+
+// private tables: the whole of TabularQAgent.learn in one pass
+__global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_private(const __grid_constant__ AgentArgs p, const uint8_t *boards,
+                                                                  const uint8_t *actions, const double *rewards,
+                                                                  const uint8_t *successors)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const uint64_t skey = board_key(p.level, boards + i * p.level.HW);
+    const uint64_t nkey = board_key(p.level, successors + i * p.level.HW);
+    const uint32_t nslot = find_private(p.T, i, nkey, p.status);
+    const uint32_t slot = find_private(p.T, i, skey, p.status);
+    const int a = actions[i] & 3;
+    double r = rewards[i];
+    if (p.ssrl) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[(size_t)slot * p.T.n_tables + i]));
+    const double best = row_max(load_row(p.T, i, nslot));
+    const double q_sa = p.T.q[((size_t)slot * p.T.n_tables + i) * SGK_NA + a];
+    store_q(p.T, i, slot, a, td_update(q_sa, r, p.discount, p.lr, best));
+}
+
+// shared table, phase A: targets from the table as it is, elect lowest index
+__global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_shared_a(const __grid_constant__ AgentArgs p, const uint8_t *boards,
+                                                                   const uint8_t *actions, const double *rewards,
+                                                                   const uint8_t *successors, uint32_t *scr_slot,
+                                                                   double *scr_target)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const uint64_t skey = board_key(p.level, boards + i * p.level.HW);
+    const uint64_t nkey = board_key(p.level, successors + i * p.level.HW);
+    const uint32_t nslot = find_shared(p.T, nkey, p.status);
+    const uint32_t slot = find_shared(p.T, skey, p.status);
+    const int a = actions[i] & 3;
+    double r = rewards[i];
+    if (p.ssrl) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[slot]));
+    const double best = row_max(load_row(p.T, 0, nslot));
+    scr_slot[i] = slot;
+    scr_target[i] = __dadd_rn(r, __dmul_rn(p.discount, best));
+    atomicMax(p.T.winner + (size_t)slot * SGK_NA + a, (p.epoch << 32) | (0xFFFFFFFFull - (unsigned long long)i));
+}
+
+__global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_shared_b(const __grid_constant__ AgentArgs p, const uint8_t *actions,
+                                                                   const uint32_t *scr_slot, const double *scr_target)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const uint32_t slot = scr_slot[i];
+    const int a = actions[i] & 3;
+    if (p.T.winner[(size_t)slot * SGK_NA + a] != ((p.epoch << 32) | (0xFFFFFFFFull - (unsigned long long)i))) return;
+    double *q = p.T.q + (size_t)slot * SGK_NA + a;
+    const double q_sa = *q;
+    *q = __dadd_rn(q_sa, __dmul_rn(p.lr, __dsub_rn(scr_target[i], q_sa)));
+}
+
+// explore thresholds for lock-steps t0 .. t0+n-1: explore iff u53 < thr[k].
+// epsilon_at(k) per value.py:23-28,54-58, in float64 with IEEE division.
+__global__ void k_eps_thresholds(unsigned long long *thr, int64_t n, uint64_t t0, double one_minus_eps, int64_t anneal)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint64_t t = t0 + (uint64_t)k;
+    double eps = 0.0;
+    if (t > 0 && anneal > 1) {
+        const uint64_t idx = t < (uint64_t)(anneal - 1) ? t : (uint64_t)(anneal - 1);
+        eps = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(one_minus_eps, (double)idx), (double)anneal));
+    }
+    // u = X / 2^53 < eps  <=>  X < ceil(eps * 2^53)  (X integer, scaling exact)
+    thr[k] = eps <= 0.0 ? 0ull : (unsigned long long)ceil(eps * 9007199254740992.0);
+}
+
+// ===================================================================== fused rollouts
+struct RolloutArgs {
+    Level level;
+    EnvArrays arr;
+    TableView T;
+    int64_t n, env_id0, n_steps;
+    uint64_t seed, t0;
+    const uint32_t *words;
+    int64_t wpe;
+    int *status;
+    const unsigned long long *thr;
+    double lr, discount;
+    int cheat;
+    // SSRL
+    double c_prior;
+    uint32_t *ssrl_hist;
+    int64_t ssrl_hist_len;
+    int *ssrl_budget;
+    unsigned long long *ssrl_counts;
+};
+
+// SSRL episode end (ssrl/agents.py:45-82; loop per DESIGN.md): query H while
+// budget remains, then the Bayesian C update over the states visited.
+__device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i, long long g, const EpStats &st, uint32_t n_hist)
+{
+    int budget = p.ssrl_budget[i];
+    unsigned long long cnt = p.ssrl_counts[i];
+    const unsigned long long episodes = cnt & 0xFFFFFFFFull, corrupt_eps = cnt >> 32;
+    bool corrupt = false;
+    if (budget > 0) {
+        budget -= 1;
+        corrupt = __dsub_rn(st.last_return, st.last_perf) > 0;
+        const double factor = __ddiv_rn((double)episodes, (double)(corrupt_eps + 1));
+        for (uint32_t k = 0; k < n_hist; k++) {
+            const uint32_t slot = p.ssrl_hist[(size_t)k * p.n + i];
+            double *c = p.T.c + (size_t)slot * p.T.n_tables + g;
+            *c = corrupt ? __dmul_rn(*c, factor) : __dmul_rn(*c, 0.0);
+        }
+        p.ssrl_budget[i] = budget;
+    }
+    p.ssrl_counts[i] = (episodes + 1) | ((corrupt_eps + (corrupt ? 1 : 0)) << 32);
+}
+
+template <int KIND, class Rng, bool TRACE, bool SSRL>
+__global__ void __launch_bounds__(SGK_BLOCK) k_rollout_private(const __grid_constant__ RolloutArgs p)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const Level &L = p.level;
+    EnvRegs e;
+    unpack_core(p.arr.core[i], e);
+    e.ep_return = p.arr.ep_return[i];
+    e.hidden_cum = p.arr.hidden_cum[i];
+    EpStats st;
+    st.load(p.arr, i);
+    uint64_t th = TRACE ? p.arr.trace_hash[i] : 0;
+    Rng rng;
+    RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+    int status = 0;
+
+    uint64_t key = obs_key<KIND>(L, e);
+    uint32_t slot = find_private(p.T, i, key, &status);
+    QRow row = load_row(p.T, i, slot);
+    uint32_t n_hist = SSRL ? e.frame : 0;   // states visited so far this episode
+
+    for (int64_t k = 0; k < p.n_steps; k++) {
+        rng.set_step(p.t0 + (uint64_t)k);
+        // act_explore (value.py:37-42)
+        int a;
+        if (rng.agent_uniform() < p.thr[k]) a = rng.agent_choice();
+        else a = argmax_first(row);
+        if (SSRL) { p.ssrl_hist[(size_t)n_hist * p.n + i] = slot; n_hist++; }
+        // env.step
+        const StepOut o = env_step<KIND>(L, e, a, rng);
+        double r = p.cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;   // learn.py:72-73
+        if (SSRL) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[(size_t)slot * p.T.n_tables + i]));
+        // learn (value.py:44-52)
+        const uint64_t nkey = obs_key<KIND>(L, e);
+        uint32_t nslot = slot;
+        QRow nrow = row;
+        if (nkey != key) { nslot = find_private(p.T, i, nkey, &status); nrow = load_row(p.T, i, nslot); }
+        const double upd = td_update(row_get(row, a), r, p.discount, p.lr, row_max(nrow));
+        store_q(p.T, i, slot, a, upd);
+        if (nslot == slot) row_set(nrow, a, upd);
+        if (TRACE) th = trace_fold<KIND>(L, e, th, a, o);
+        key = nkey; slot = nslot; row = nrow;
+        if (o.done) {
+            st.episode_end(e);
+            if (SSRL) { ssrl_episode_end(p, i, i, st, n_hist); n_hist = 0; }
+            rng.set_step(p.t0 + (uint64_t)k + 1);
+            env_reset<KIND>(L, e, rng);
+            key = obs_key<KIND>(L, e);
+            slot = find_private(p.T, i, key, &status);
+            row = load_row(p.T, i, slot);
+        }
+    }
+    p.arr.core[i] = pack_core(e);
+    p.arr.ep_return[i] = e.ep_return;
+    p.arr.hidden_cum[i] = e.hidden_cum;
+    st.store(p.arr, i);
+    if (TRACE) p.arr.trace_hash[i] = th;
+    RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+    if (rng.overflowed()) status = SGK_ST_REPLAY_DRY;
+    if (status) *p.status = status;
+}
+
+// Shared table: synchronous batch Q-learning in one persistent cooperative
+// kernel.  Per lock-step every environment acts and computes its TD target
+// from the table as it stood at the start of the step (phase A); per
+// (state, action) the lowest environment id is elected with an epoch-tagged
+// atomicMax (no clearing pass); after a grid barrier the winners apply their
+// update (phase B); a second barrier publishes Q_{t+1}.  Q rows are read with
+// ld.global.cg: L1 is not coherent across SMs.  Each thread serves EPT
+// environments whose state stays in registers for the whole rollout.
+__device__ __forceinline__ QRow load_row_cg(const TableView &T, uint32_t slot)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(T.q + (size_t)slot * SGK_NA);
+    const double2 a = __ldcg(p), b = __ldcg(p + 1);
+    QRow r; r.v0 = a.x; r.v1 = a.y; r.v2 = b.x; r.v3 = b.y;
+    return r;
+}
+
+template <int KIND, class Rng, bool TRACE, int EPT>
+__global__ void __launch_bounds__(SGK_BLOCK) k_rollout_shared(const __grid_constant__ RolloutArgs p)
+{
+    cg::grid_group grid = cg::this_grid();
+    const Level &L = p.level;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    int status = 0;
+    EnvRegs e[EPT];
+    uint32_t slot[EPT], nslot[EPT], act[EPT];
+    double target[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; j++) {
+        const int64_t i = tid + (int64_t)j * nthreads;
+        if (i < p.n) {
+            unpack_core(p.arr.core[i], e[j]);
+            e[j].ep_return = p.arr.ep_return[i];
+            e[j].hidden_cum = p.arr.hidden_cum[i];
+            slot[j] = find_shared(p.T, obs_key<KIND>(L, e[j]), &status);
+        }
+    }
+    for (int64_t k = 0; k < p.n_steps; k++) {
+        const uint64_t t = p.t0 + (uint64_t)k;
+        const unsigned long long thr = p.thr[k];
+        // ---- phase A: act, step, target, elect
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+            const int64_t i = tid + (int64_t)j * nthreads;
+            if (i >= p.n) continue;
+            Rng rng;
+            RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+            rng.set_step(t);
+            const uint64_t key = obs_key<KIND>(L, e[j]);
+            int a;
+            if (rng.agent_uniform() < thr) a = rng.agent_choice();
+            else a = argmax_first(load_row_cg(p.T, slot[j]));
+            const StepOut o = env_step<KIND>(L, e[j], a, rng);
+            const double r = p.cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;
+            const uint64_t nkey = obs_key<KIND>(L, e[j]);
+            nslot[j] = nkey == key ? slot[j] : find_shared(p.T, nkey, &status);
+            target[j] = __dadd_rn(r, __dmul_rn(p.discount, row_max(load_row_cg(p.T, nslot[j]))));
+            act[j] = (uint32_t)a | (o.done ? 4u : 0u);
+            if (TRACE) p.arr.trace_hash[i] = trace_fold<KIND>(L, e[j], p.arr.trace_hash[i], a, o);
+            unsigned long long *w = p.T.winner + (size_t)slot[j] * SGK_NA + a;
+            const unsigned long long mine = ((unsigned long long)(t + 1) << 32) | (0xFFFFFFFFull - (unsigned long long)i);
+            if (*reinterpret_cast<volatile unsigned long long *>(w) < mine) atomicMax(w, mine);
+            RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+            if (rng.overflowed()) status = SGK_ST_REPLAY_DRY;
+        }
+        grid.sync();
+        // ---- phase B: winners apply; finished episodes reset
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+            const int64_t i = tid + (int64_t)j * nthreads;
+            if (i >= p.n) continue;
+            const int a = (int)(act[j] & 3u);
+            const unsigned long long mine = ((unsigned long long)(t + 1) << 32) | (0xFFFFFFFFull - (unsigned long long)i);
+            if (__ldcg(p.T.winner + (size_t)slot[j] * SGK_NA + a) == mine) {
+                double *q = p.T.q + (size_t)slot[j] * SGK_NA + a;
+                const double q_sa = __ldcg(q);
+                __stcg(q, __dadd_rn(q_sa, __dmul_rn(p.lr, __dsub_rn(target[j], q_sa))));
+            }
+            slot[j] = nslot[j];
+            if (act[j] & 4u) {
+                EpStats st;
+                st.load(p.arr, i);
+                st.episode_end(e[j]);
+                st.store(p.arr, i);
+                Rng rng;
+                RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+                rng.set_step(t + 1);
+                env_reset<KIND>(L, e[j], rng);
+                RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+                slot[j] = find_shared(p.T, obs_key<KIND>(L, e[j]), &status);
+            }
+        }
+        grid.sync();
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; j++) {
+        const int64_t i = tid + (int64_t)j * nthreads;
+        if (i < p.n) {
+            p.arr.core[i] = pack_core(e[j]);
+            p.arr.ep_return[i] = e[j].ep_return;
+            p.arr.hidden_cum[i] = e[j].hidden_cum;
+        }
+    }
+    if (status) *p.status = status;
+}
+
+template <int KIND, class Rng, bool TRACE>
+__global__ void __launch_bounds__(SGK_BLOCK) k_rollout_random(const __grid_constant__ RolloutArgs p)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const Level &L = p.level;
+    EnvRegs e;
+    unpack_core(p.arr.core[i], e);
+    e.ep_return = p.arr.ep_return[i];
+    e.hidden_cum = p.arr.hidden_cum[i];
+    EpStats st;
+    st.load(p.arr, i);
+    uint64_t th = TRACE ? p.arr.trace_hash[i] : 0;
+    Rng rng;
+    RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+    for (int64_t k = 0; k < p.n_steps; k++) {
+        rng.set_step(p.t0 + (uint64_t)k);
+        const int a = rng.random_action();
+        const StepOut o = env_step<KIND>(L, e, a, rng);
+        if (TRACE) th = trace_fold<KIND>(L, e, th, a, o);
+        if (o.done) {
+            st.episode_end(e);
+            rng.set_step(p.t0 + (uint64_t)k + 1);
+            env_reset<KIND>(L, e, rng);
+        }
+    }
+    p.arr.core[i] = pack_core(e);
+    p.arr.ep_return[i] = e.ep_return;
+    p.arr.hidden_cum[i] = e.hidden_cum;
+    st.store(p.arr, i);
+    if (TRACE) p.arr.trace_hash[i] = th;
+    RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+    if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
+}
+
+// deterministic totals over all environments: one block, fixed strided
+// per-thread order, then a fixed shared-memory tree
+__global__ void __launch_bounds__(512) k_totals(const EnvArrays A, int64_t n, double *out)
+{
+    __shared__ double sh[7][512];
+    double v[7] = {0, 0, 0, 0, 0, -INFINITY, 0};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long c = A.counts[i];
+        const double eps = (double)(c & 0xFFFFFFFFFFull);
+        v[0] += eps;
+        v[1] += A.sum_return[i];
+        v[2] += A.sum_perf[i];
+        v[3] += A.sum_margin_pos[i];
+        v[4] += (double)(c >> 40);
+        if (eps > 0 && A.max_return[i] > v[5]) v[5] = A.max_return[i];
+        v[6] += A.ep_return[i];
+    }
+    for (int k = 0; k < 7; k++) sh[k][threadIdx.x] = v[k];
+    __syncthreads();
+    for (int s = 256; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+            for (int k = 0; k < 7; k++) {
+                if (k == 5) sh[k][threadIdx.x] = fmax(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
+                else sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x < 7) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void k_fill_f64(double *p, int64_t n, double v)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) p[k] = v;
+}
+
+__global__ void k_fill_i32(int *p, int64_t n, int v)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) p[k] = v;
+}
+
+__global__ void k_stats_export(const EnvArrays A, int64_t n, sgk_env_stats o)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long c = A.counts[i];
+    EnvRegs e;
+    unpack_core(A.core[i], e);
+    if (o.episode_return) o.episode_return[i] = A.ep_return[i];
+    if (o.last_return) o.last_return[i] = A.last_return[i];
+    if (o.last_performance) o.last_performance[i] = (e.flags & SGK_F_PERF) ? A.last_perf[i] : __longlong_as_double(0x7ff8000000000000ll);
+    if (o.sum_return) o.sum_return[i] = A.sum_return[i];
+    if (o.sum_performance) o.sum_performance[i] = A.sum_perf[i];
+    if (o.sum_margin_pos) o.sum_margin_pos[i] = A.sum_margin_pos[i];
+    if (o.max_return) o.max_return[i] = A.max_return[i];
+    if (o.episodes) o.episodes[i] = (int64_t)(c & 0xFFFFFFFFFFull);
+    if (o.n_margin_pos) o.n_margin_pos[i] = (int64_t)(c >> 40);
+    if (o.trace_hash) o.trace_hash[i] = A.trace_hash[i];
+}
+
+__global__ void k_trace_init(unsigned long long *h, int64_t n, int64_t env_id0)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) h[i] = 0xcbf29ce484222325ull ^ (unsigned long long)(env_id0 + i);
+}
+
+__global__ void k_table_export(const TableView T, int64_t table, uint64_t *keys, double *q, double *c)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= T.cap) return;
+    const size_t at = (size_t)s * T.n_tables + table;
+    keys[s] = T.keys[at];
+    for (int a = 0; a < SGK_NA; a++) q[s * SGK_NA + a] = T.q[at * SGK_NA + a];
+    if (c) c[s] = T.c ? T.c[at] : 0.0;
+}
+
+__global__ void k_table_import(const TableView T, int64_t table, const uint64_t *keys, const double *q)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= T.cap) return;
+    const size_t at = (size_t)s * T.n_tables + table;
+    T.keys[at] = keys[s];
+    for (int a = 0; a < SGK_NA; a++) T.q[at * SGK_NA + a] = q[s * SGK_NA + a];
+}
+
+// ===================================================================== C ABI: environments
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+static EnvKernelArgs env_args(const sgk_env *env, uint64_t step)
+{
+    EnvKernelArgs a;
+    a.level = env->level; a.arr = env->arr; a.n = env->n; a.env_id0 = env->env_id0;
+    a.seed = env->seed; a.step = step; a.words = env->replay_words; a.wpe = env->words_per_env;
+    a.status = env->status; a.trace = env->trace;
+    return a;
+}
+
+template <class F> static int by_kind(int kind, F f)
+{
+    switch (kind) {
+    case SGK_ENV_BOAT: return f(std::integral_constant<int, 0>());
+    case SGK_ENV_SOKOBAN: return f(std::integral_constant<int, 1>());
+    case SGK_ENV_TOMATO: return f(std::integral_constant<int, 2>());
+    }
+    return fail(SGK_EINVAL, "unknown environment kind");
+}
+
+static int launch_check(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SGK_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return SGK_OK;
+}
+
+extern "C" int sgk_env_destroy(sgk_env *env)
+{
+    if (!env) return SGK_OK;
+    DeviceGuard g(env->device);
+    EnvArrays &A = env->arr;
+    void *ptrs[] = {A.core, A.ep_return, A.hidden_cum, A.last_return, A.last_perf, A.sum_return, A.sum_perf,
+                    A.sum_margin_pos, A.max_return, A.counts, A.trace_hash, A.replay_cursor, env->status, env->totals};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete env;
+    return SGK_OK;
+}
+
+extern "C" int sgk_env_create(int kind, int64_t n_envs, int64_t env_id0, uint64_t seed, int device, sgk_env **out)
+{
+    REQUIRE(out != nullptr, "out is NULL");
+    REQUIRE(n_envs > 0 && n_envs < (1ll << 32), "n_envs must be in [1, 2^32)");
+    Level L;
+    REQUIRE(make_level(kind, L), "unknown environment kind");
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    REQUIRE(device >= 0 && device < count, "no such CUDA device");
+    DeviceGuard g(device);
+    sgk_env *env = new (std::nothrow) sgk_env();
+    REQUIRE(env != nullptr, "out of host memory");
+    memset(env, 0, sizeof(*env));
+    env->device = device; env->level = L; env->n = n_envs; env->env_id0 = env_id0; env->seed = seed;
+    env->rng_mode = SGK_RNG_PHILOX;
+    EnvArrays &A = env->arr;
+    const size_t n = (size_t)n_envs;
+#define ALLOC(field, type)                                                        \
+    if (cudaMalloc(&A.field, n * sizeof(type)) != cudaSuccess ||                  \
+        cudaMemset(A.field, 0, n * sizeof(type)) != cudaSuccess) {                \
+        sgk_env_destroy(env);                                                     \
+        return fail(SGK_ECUDA, "cudaMalloc failed for environment state");        \
+    }
+    ALLOC(core, uint64_t) ALLOC(ep_return, double) ALLOC(hidden_cum, double) ALLOC(last_return, double)
+    ALLOC(last_perf, double) ALLOC(sum_return, double) ALLOC(sum_perf, double) ALLOC(sum_margin_pos, double)
+    ALLOC(max_return, double) ALLOC(counts, unsigned long long) ALLOC(trace_hash, unsigned long long)
+    ALLOC(replay_cursor, long long)
+#undef ALLOC
+    if (cudaMalloc(&env->status, sizeof(int)) != cudaSuccess || cudaMemset(env->status, 0, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&env->totals, 7 * sizeof(double)) != cudaSuccess) {
+        sgk_env_destroy(env);
+        return fail(SGK_ECUDA, "cudaMalloc failed for environment status");
+    }
+    k_trace_init<<<grid_for(n_envs, 256), 256>>>(A.trace_hash, n_envs, env_id0);
+    int rc = sgk_env_reset(env, nullptr, 0, nullptr, nullptr);
+    if (rc == SGK_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(SGK_ECUDA, "initial reset failed");
+    if (rc != SGK_OK) { sgk_env_destroy(env); return rc; }
+    *out = env;
+    return SGK_OK;
+}
+
+extern "C" int sgk_env_shape(const sgk_env *env, int *channels, int *height, int *width, int *n_actions)
+{
+    REQUIRE(env != nullptr, "env is NULL");
+    if (channels) *channels = 1;
+    if (height) *height = env->level.H;
+    if (width) *width = env->level.W;
+    if (n_actions) *n_actions = SGK_NA;
+    return SGK_OK;
+}
+
+extern "C" int64_t sgk_env_count(const sgk_env *env) { return env ? env->n : 0; }
+
+extern "C" int sgk_env_set_replay(sgk_env *env, const uint32_t *words, int64_t words_per_env)
+{
+    REQUIRE(env != nullptr, "env is NULL");
+    DeviceGuard g(env->device);
+    if (words == nullptr) { env->rng_mode = SGK_RNG_PHILOX; env->replay_words = nullptr; env->words_per_env = 0; return SGK_OK; }
+    REQUIRE(words_per_env > 0, "words_per_env must be positive");
+    env->rng_mode = SGK_RNG_REPLAY; env->replay_words = words; env->words_per_env = words_per_env;
+    CU(cudaMemsetAsync(env->arr.replay_cursor, 0, (size_t)env->n * sizeof(long long), 0));
+    return SGK_OK;
+}
+
+extern "C" int sgk_env_replay_cursor(const sgk_env *env, int64_t *cursor_out, void *stream)
+{
+    REQUIRE(env != nullptr && cursor_out != nullptr, "bad argument");
+    DeviceGuard g(env->device);
+    CU(cudaMemcpyAsync(cursor_out, env->arr.replay_cursor, (size_t)env->n * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}
+
+extern "C" int sgk_env_set_trace(sgk_env *env, int enabled)
+{
+    REQUIRE(env != nullptr, "env is NULL");
+    env->trace = enabled ? 1 : 0;
+    return SGK_OK;
+}
+
+extern "C" int sgk_env_reset(sgk_env *env, const uint8_t *mask, uint64_t step, uint8_t *board_out, void *stream)
+{
+    REQUIRE(env != nullptr, "env is NULL");
+    DeviceGuard g(env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const EnvKernelArgs a = env_args(env, step);
+    const size_t smem = board_out ? (size_t)SGK_BLOCK * env->level.HW : 0;
+    const unsigned grid = grid_for(env->n, SGK_BLOCK);
+    const bool replay = env->rng_mode == SGK_RNG_REPLAY;
+    return by_kind(env->level.kind, [&](auto K) {
+        constexpr int KIND = decltype(K)::value;
+        if (replay) k_env_reset<KIND, ReplayStream><<<grid, SGK_BLOCK, smem, st>>>(a, mask, board_out);
+        else k_env_reset<KIND, PhiloxStream><<<grid, SGK_BLOCK, smem, st>>>(a, mask, board_out);
+        return launch_check("k_env_reset");
+    });
+}
+
+extern "C" int sgk_env_step(sgk_env *env, const uint8_t *actions, uint64_t step, uint8_t *board_out, double *reward,
+                            double *hidden, uint8_t *done, void *stream)
+{
+    REQUIRE(env != nullptr && actions != nullptr, "env or actions is NULL");
+    DeviceGuard g(env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const EnvKernelArgs a = env_args(env, step);
+    const size_t smem = board_out ? (size_t)SGK_BLOCK * env->level.HW : 0;
+    const unsigned grid = grid_for(env->n, SGK_BLOCK);
+    const bool replay = env->rng_mode == SGK_RNG_REPLAY;
+    return by_kind(env->level.kind, [&](auto K) {
+        constexpr int KIND = decltype(K)::value;
+        if (replay) k_env_step<KIND, ReplayStream><<<grid, SGK_BLOCK, smem, st>>>(a, actions, board_out, reward, hidden, done);
+        else k_env_step<KIND, PhiloxStream><<<grid, SGK_BLOCK, smem, st>>>(a, actions, board_out, reward, hidden, done);
+        return launch_check("k_env_step");
+    });
+}
+
+extern "C" int sgk_env_render(const sgk_env *env, uint8_t *board_out, void *stream)
+{
+    REQUIRE(env != nullptr && board_out != nullptr, "env or board_out is NULL");
+    DeviceGuard g(env->device);
+    const EnvKernelArgs a = env_args(env, 0);
+    const size_t smem = (size_t)SGK_BLOCK * env->level.HW;
+    const unsigned grid = grid_for(env->n, SGK_BLOCK);
+    return by_kind(env->level.kind, [&](auto K) {
+        constexpr int KIND = decltype(K)::value;
+        k_env_render<KIND><<<grid, SGK_BLOCK, smem, (cudaStream_t)stream>>>(a, board_out);
+        return launch_check("k_env_render");
+    });
+}
+
+extern "C" int sgk_board_to_f32(const sgk_env *env, const uint8_t *boards, float *obs_out, int64_t n, void *stream)
+{
+    REQUIRE(env != nullptr && boards != nullptr && obs_out != nullptr && n >= 0, "bad argument");
+    if (n == 0) return SGK_OK;
+    DeviceGuard g(env->device);
+    const int64_t total = n * env->level.HW;
+    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    k_board_to_f32<<<grid, 256, 0, (cudaStream_t)stream>>>(boards, obs_out, total);
+    return launch_check("k_board_to_f32");
+}
+
+extern "C" int sgk_board_to_key(const sgk_env *env, const uint8_t *boards, uint64_t *keys_out, int64_t n, void *stream)
+{
+    REQUIRE(env != nullptr && boards != nullptr && keys_out != nullptr && n >= 0, "bad argument");
+    if (n == 0) return SGK_OK;
+    DeviceGuard g(env->device);
+    k_board_to_key<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(env->level, boards, keys_out, n);
+    return launch_check("k_board_to_key");
+}
+
+extern "C" int sgk_env_get_stats(const sgk_env *env, const sgk_env_stats *out, void *stream)
+{
+    REQUIRE(env != nullptr && out != nullptr, "bad argument");
+    DeviceGuard g(env->device);
+    k_stats_export<<<grid_for(env->n, 256), 256, 0, (cudaStream_t)stream>>>(env->arr, env->n, *out);
+    return launch_check("k_stats_export");
+}
+
+extern "C" int sgk_env_totals_host(const sgk_env *env, double totals[7], void *stream)
+{
+    REQUIRE(env != nullptr && totals != nullptr, "bad argument");
+    DeviceGuard g(env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_totals<<<1, 512, 0, st>>>(env->arr, env->n, env->totals);
+    int rc = launch_check("k_totals");
+    if (rc != SGK_OK) return rc;
+    CU(cudaMemcpyAsync(totals, env->totals, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SGK_OK;
+}
+
+extern "C" int sgk_env_get_core(const sgk_env *env, uint64_t *core_out, void *stream)
+{
+    REQUIRE(env != nullptr && core_out != nullptr, "bad argument");
+    DeviceGuard g(env->device);
+    CU(cudaMemcpyAsync(core_out, env->arr.core, (size_t)env->n * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}
+
+extern "C" int sgk_env_set_core(sgk_env *env, const uint64_t *core_in, void *stream)
+{
+    REQUIRE(env != nullptr && core_in != nullptr, "bad argument");
+    DeviceGuard g(env->device);
+    CU(cudaMemcpyAsync(env->arr.core, core_in, (size_t)env->n * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}
+
+// ===================================================================== C ABI: tabular Q
+extern "C" int sgk_tabq_destroy(sgk_tabq *q)
+{
+    if (!q) return SGK_OK;
+    DeviceGuard g(q->device);
+    void *ptrs[] = {q->keys, q->q, q->c, q->winner, q->status, q->thr, q->scr_slot, q->scr_target,
+                    q->ssrl_hist, q->ssrl_budget, q->ssrl_counts};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete q;
+    return SGK_OK;
+}
+
+extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity, sgk_tabq **out)
+{
+    REQUIRE(env != nullptr && out != nullptr, "bad argument");
+    REQUIRE(q_mode == SGK_Q_PRIVATE || q_mode == SGK_Q_SHARED, "unknown q_mode");
+    if (capacity == 0) {
+        // distinct observations: boat 8; sokoban level 0 < 128; tomato <= 29 * 2^13
+        const int64_t dflt_private[3] = {16, 128, 4096};
+        const int64_t dflt_shared[3] = {64, 512, 1 << 19};
+        capacity = (q_mode == SGK_Q_PRIVATE ? dflt_private : dflt_shared)[env->level.kind];
+    }
+    REQUIRE(capacity >= 2 && (capacity & (capacity - 1)) == 0 && capacity <= (1ll << 30), "capacity must be a power of two in [2, 2^30]");
+    DeviceGuard g(env->device);
+    sgk_tabq *q = new (std::nothrow) sgk_tabq();
+    REQUIRE(q != nullptr, "out of host memory");
+    memset(q, 0, sizeof(*q));
+    q->device = env->device; q->kind = env->level.kind; q->q_mode = q_mode;
+    q->n_envs = env->n;
+    q->n_tables = q_mode == SGK_Q_PRIVATE ? env->n : 1;
+    q->cap = capacity;
+    q->log_cap = 0;
+    while ((1ll << q->log_cap) < capacity) q->log_cap++;
+    q->lr = 0.5; q->discount = 0.99; q->epsilon = 0.01; q->anneal = 100000;
+    const size_t slots = (size_t)q->cap * (size_t)q->n_tables;
+    bool ok = cudaMalloc(&q->keys, slots * 8) == cudaSuccess && cudaMemset(q->keys, 0, slots * 8) == cudaSuccess &&
+              cudaMalloc(&q->q, slots * 8 * SGK_NA) == cudaSuccess && cudaMemset(q->q, 0, slots * 8 * SGK_NA) == cudaSuccess &&
+              cudaMalloc(&q->status, sizeof(int)) == cudaSuccess && cudaMemset(q->status, 0, sizeof(int)) == cudaSuccess;
+    if (ok && q_mode == SGK_Q_SHARED)
+        ok = cudaMalloc(&q->winner, slots * 8 * SGK_NA) == cudaSuccess && cudaMemset(q->winner, 0, slots * 8 * SGK_NA) == cudaSuccess;
+    if (!ok) {
+        sgk_tabq_destroy(q);
+        return fail(SGK_ECUDA, "cudaMalloc failed for the Q table (" + std::to_string(slots * 40 >> 20) + " MiB)");
+    }
+    *out = q;
+    return SGK_OK;
+}
+
+extern "C" int64_t sgk_tabq_capacity(const sgk_tabq *q) { return q ? q->cap : 0; }
+extern "C" int64_t sgk_tabq_tables(const sgk_tabq *q) { return q ? q->n_tables : 0; }
+
+extern "C" int sgk_tabq_configure(sgk_tabq *q, double lr, double discount, double epsilon, int64_t epsilon_anneal)
+{
+    REQUIRE(q != nullptr, "q is NULL");
+    REQUIRE(epsilon_anneal >= 1, "epsilon_anneal must be >= 1");
+    q->lr = lr; q->discount = discount; q->epsilon = epsilon; q->anneal = epsilon_anneal;
+    return SGK_OK;
+}
+
+static double epsilon_at(const sgk_tabq *q, int64_t k)
+{
+    // value.py:23-28,54-58 -- same float64 expression, same evaluation order
+    if (k <= 0 || q->anneal <= 1) return 0.0;
+    const int64_t idx = k < q->anneal - 1 ? k : q->anneal - 1;
+    const volatile double scaled = (1 - q->epsilon) * (double)idx;
+    const volatile double frac = scaled / (double)q->anneal;
+    return 1.0 - frac;
+}
+
+extern "C" double sgk_tabq_epsilon_at(const sgk_tabq *q, int64_t k) { return q ? epsilon_at(q, k) : 0.0; }
+
+static unsigned long long explore_threshold(double eps)
+{
+    return eps <= 0.0 ? 0ull : (unsigned long long)ceil(eps * 9007199254740992.0);
+}
+
+extern "C" int sgk_tabq_enable_ssrl(sgk_tabq *q, double c_prior, int64_t budget, int64_t max_episode_steps)
+{
+    REQUIRE(q != nullptr, "q is NULL");
+    REQUIRE(q->q_mode == SGK_Q_PRIVATE, "SSRL needs private tables (one agent per environment)");
+    REQUIRE(max_episode_steps > 0 && budget >= 0 && budget < (1ll << 31), "bad SSRL argument");
+    DeviceGuard g(q->device);
+    const size_t slots = (size_t)q->cap * (size_t)q->n_tables;
+    if (!q->c) CU(cudaMalloc(&q->c, slots * 8));
+    if (!q->ssrl_hist) CU(cudaMalloc(&q->ssrl_hist, (size_t)max_episode_steps * q->n_envs * 4));
+    if (!q->ssrl_budget) CU(cudaMalloc(&q->ssrl_budget, (size_t)q->n_envs * 4));
+    if (!q->ssrl_counts) CU(cudaMalloc(&q->ssrl_counts, (size_t)q->n_envs * 8));
+    k_fill_f64<<<148 * 4, 256>>>(q->c, (int64_t)slots, c_prior);
+    k_fill_i32<<<148 * 4, 256>>>(q->ssrl_budget, q->n_envs, (int)budget);
+    CU(cudaMemset(q->ssrl_counts, 0, (size_t)q->n_envs * 8));
+    CU(cudaDeviceSynchronize());
+    q->ssrl = 1; q->c_prior = c_prior; q->ssrl_hist_len = max_episode_steps;
+    return SGK_OK;
+}
+
+static AgentArgs agent_args(const sgk_tabq *q, const sgk_env *env, int64_t n, uint64_t step)
+{
+    AgentArgs a;
+    make_level(q->kind, a.level);
+    a.T = view_of(q); a.q_mode = q->q_mode; a.n = n;
+    a.env_id0 = env ? env->env_id0 : 0; a.seed = env ? env->seed : 0; a.step = step;
+    a.words = env ? env->replay_words : nullptr; a.wpe = env ? env->words_per_env : 0;
+    a.replay_cursor = env ? env->arr.replay_cursor : nullptr;
+    a.status = q->status;
+    a.thr = explore_threshold(epsilon_at(q, (int64_t)step));
+    a.lr = q->lr; a.discount = q->discount; a.epoch = q->epoch; a.ssrl = q->ssrl;
+    return a;
+}
+
+extern "C" int sgk_tabq_act(sgk_tabq *q, sgk_env *env, const uint8_t *boards, int64_t n, uint64_t step, int explore,
+                            uint8_t *actions_out, void *stream)
+{
+    REQUIRE(q != nullptr && boards != nullptr && actions_out != nullptr, "bad argument");
+    REQUIRE(n > 0 && (q->q_mode == SGK_Q_SHARED || n <= q->n_tables), "n exceeds the number of private tables");
+    REQUIRE(!explore || env != nullptr, "exploration needs the environment object (random streams)");
+    REQUIRE(!explore || n <= env->n, "n exceeds the environment count");
+    DeviceGuard g(q->device);
+    const AgentArgs a = agent_args(q, env, n, step);
+    if (explore && env->rng_mode == SGK_RNG_REPLAY)
+        k_tabq_act<ReplayStream><<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, (cudaStream_t)stream>>>(a, boards, explore, actions_out);
+    else
+        k_tabq_act<PhiloxStream><<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, (cudaStream_t)stream>>>(a, boards, explore, actions_out);
+    return launch_check("k_tabq_act");
+}
+
+extern "C" int sgk_tabq_learn(sgk_tabq *q, const uint8_t *boards, const uint8_t *actions, const double *rewards,
+                              const uint8_t *successors, int64_t n, void *stream)
+{
+    REQUIRE(q != nullptr && boards && actions && rewards && successors, "bad argument");
+    REQUIRE(n > 0 && (q->q_mode == SGK_Q_SHARED || n <= q->n_tables), "n exceeds the number of private tables");
+    DeviceGuard g(q->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (q->q_mode == SGK_Q_PRIVATE) {
+        const AgentArgs a = agent_args(q, nullptr, n, 0);
+        k_tabq_learn_private<<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a, boards, actions, rewards, successors);
+        return launch_check("k_tabq_learn_private");
+    }
+    REQUIRE(n < (1ll << 32), "batch too large");
+    if (q->scr_cap < n) {
+        if (q->scr_slot) cudaFree(q->scr_slot);
+        if (q->scr_target) cudaFree(q->scr_target);
+        q->scr_slot = nullptr; q->scr_target = nullptr; q->scr_cap = 0;
+        CU(cudaMalloc(&q->scr_slot, (size_t)n * 4));
+        CU(cudaMalloc(&q->scr_target, (size_t)n * 8));
+        q->scr_cap = n;
+    }
+    q->epoch += 1;
+    const AgentArgs a = agent_args(q, nullptr, n, 0);
+    k_tabq_learn_shared_a<<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a, boards, actions, rewards, successors, q->scr_slot, q->scr_target);
+    k_tabq_learn_shared_b<<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a, actions, q->scr_slot, q->scr_target);
+    return launch_check("k_tabq_learn_shared");
+}
+
+extern "C" int sgk_tabq_export(const sgk_tabq *q, int64_t table, uint64_t *keys_out, double *q_out, double *corruption_out, void *stream)
+{
+    REQUIRE(q != nullptr && keys_out && q_out, "bad argument");
+    REQUIRE(table >= 0 && table < q->n_tables, "no such table");
+    DeviceGuard g(q->device);
+    k_table_export<<<grid_for(q->cap, 128), 128, 0, (cudaStream_t)stream>>>(view_of(q), table, keys_out, q_out, corruption_out);
+    return launch_check("k_table_export");
+}
+
+extern "C" int sgk_tabq_import(sgk_tabq *q, int64_t table, const uint64_t *keys, const double *qrows, void *stream)
+{
+    REQUIRE(q != nullptr && keys && qrows, "bad argument");
+    REQUIRE(table >= 0 && table < q->n_tables, "no such table");
+    DeviceGuard g(q->device);
+    k_table_import<<<grid_for(q->cap, 128), 128, 0, (cudaStream_t)stream>>>(view_of(q), table, keys, qrows);
+    return launch_check("k_table_import");
+}
+
+// ===================================================================== C ABI: fused rollouts
+static int ensure_thresholds(sgk_tabq *q, int64_t n_steps, uint64_t t0, cudaStream_t st)
+{
+    if (q->thr_cap < n_steps) {
+        if (q->thr) cudaFree(q->thr);
+        q->thr = nullptr; q->thr_cap = 0;
+        CU(cudaMalloc(&q->thr, (size_t)n_steps * 8));
+        q->thr_cap = n_steps;
+    }
+    k_eps_thresholds<<<grid_for(n_steps, 256), 256, 0, st>>>(q->thr, n_steps, t0, 1 - q->epsilon, q->anneal);
+    return launch_check("k_eps_thresholds");
+}
+
+static RolloutArgs rollout_args(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat)
+{
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.level = env->level; a.arr = env->arr; a.n = env->n; a.env_id0 = env->env_id0; a.n_steps = n_steps;
+    a.seed = env->seed; a.t0 = t0; a.words = env->replay_words; a.wpe = env->words_per_env;
+    a.status = env->status; a.cheat = cheat;
+    if (q) {
+        a.T = view_of(q); a.thr = q->thr; a.lr = q->lr; a.discount = q->discount;
+        a.c_prior = q->c_prior; a.ssrl_hist = q->ssrl_hist; a.ssrl_hist_len = q->ssrl_hist_len;
+        a.ssrl_budget = q->ssrl_budget; a.ssrl_counts = q->ssrl_counts;
+    }
+    return a;
+}
+
+template <int KIND, class Rng, bool TRACE>
+static int launch_shared(const RolloutArgs &a, cudaStream_t st)
+{
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    auto try_ept = [&](auto E) -> int {
+        constexpr int EPT = decltype(E)::value;
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_shared<KIND, Rng, TRACE, EPT>, SGK_BLOCK, 0));
+        const int64_t max_blocks = (int64_t)per_sm * sms;
+        const int64_t want = (a.n + (int64_t)SGK_BLOCK * EPT - 1) / ((int64_t)SGK_BLOCK * EPT);
+        if (want > max_blocks) return 1;   // does not fit co-resident: try a larger EPT
+        RolloutArgs args = a;
+        void *params[] = {&args};
+        CU(cudaLaunchCooperativeKernel((void *)k_rollout_shared<KIND, Rng, TRACE, EPT>, dim3((unsigned)want), dim3(SGK_BLOCK), params, 0, st));
+        return SGK_OK;
+    };
+    int rc = try_ept(std::integral_constant<int, 1>());
+    if (rc == 1) rc = try_ept(std::integral_constant<int, 2>());
+    if (rc == 1) rc = try_ept(std::integral_constant<int, 4>());
+    if (rc == 1) rc = try_ept(std::integral_constant<int, 8>());
+    if (rc == 1) return fail(SGK_EINVAL, "too many environments for one cooperative shared-table launch");
+    return rc;
+}
+
+extern "C" int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat, void *stream)
+{
+    REQUIRE(env != nullptr && q != nullptr, "env or q is NULL");
+    REQUIRE(env->device == q->device && env->level.kind == q->kind && env->n == q->n_envs, "table was created for a different environment object");
+    REQUIRE(n_steps > 0, "n_steps must be positive");
+    DeviceGuard g(env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_thresholds(q, n_steps, t0, st);
+    if (rc != SGK_OK) return rc;
+    const RolloutArgs a = rollout_args(env, q, n_steps, t0, cheat);
+    const unsigned grid = grid_for(env->n, SGK_BLOCK);
+    const bool replay = env->rng_mode == SGK_RNG_REPLAY;
+    const bool trace = env->trace != 0;
+    const bool ssrl = q->ssrl != 0;
+    const bool shared = q->q_mode == SGK_Q_SHARED;
+    return by_kind(env->level.kind, [&](auto K) {
+        constexpr int KIND = decltype(K)::value;
+        if (shared) {
+            if (replay) return launch_shared<KIND, ReplayStream, true>(a, st);
+            if (trace) return launch_shared<KIND, PhiloxStream, true>(a, st);
+            return launch_shared<KIND, PhiloxStream, false>(a, st);
+        }
+        if (ssrl) {
+            if (replay) k_rollout_private<KIND, ReplayStream, true, true><<<grid, SGK_BLOCK, 0, st>>>(a);
+            else if (trace) k_rollout_private<KIND, PhiloxStream, true, true><<<grid, SGK_BLOCK, 0, st>>>(a);
+            else k_rollout_private<KIND, PhiloxStream, false, true><<<grid, SGK_BLOCK, 0, st>>>(a);
+        } else {
+            if (replay) k_rollout_private<KIND, ReplayStream, true, false><<<grid, SGK_BLOCK, 0, st>>>(a);
+            else if (trace) k_rollout_private<KIND, PhiloxStream, true, false><<<grid, SGK_BLOCK, 0, st>>>(a);
+            else k_rollout_private<KIND, PhiloxStream, false, false><<<grid, SGK_BLOCK, 0, st>>>(a);
+        }
+        return launch_check("k_rollout_private");
+    });
+}
+
+extern "C" int sgk_rollout_random(sgk_env *env, int64_t n_steps, uint64_t t0, void *stream)
+{
+    REQUIRE(env != nullptr && n_steps > 0, "bad argument");
+    DeviceGuard g(env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const RolloutArgs a = rollout_args(env, nullptr, n_steps, t0, 0);
+    const unsigned grid = grid_for(env->n, SGK_BLOCK);
+    const bool replay = env->rng_mode == SGK_RNG_REPLAY;
+    const bool trace = env->trace != 0;
+    return by_kind(env->level.kind, [&](auto K) {
+        constexpr int KIND = decltype(K)::value;
+        if (replay) k_rollout_random<KIND, ReplayStream, true><<<grid, SGK_BLOCK, 0, st>>>(a);
+        else if (trace) k_rollout_random<KIND, PhiloxStream, true><<<grid, SGK_BLOCK, 0, st>>>(a);
+        else k_rollout_random<KIND, PhiloxStream, false><<<grid, SGK_BLOCK, 0, st>>>(a);
+        return launch_check("k_rollout_random");
+    });
+}
+
+extern "C" int sgk_check(sgk_env *env, sgk_tabq *q, void *stream)
+{
+    REQUIRE(env != nullptr, "env is NULL");
+    DeviceGuard g(env->device);
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    int s_env = 0, s_q = 0;
+    CU(cudaMemcpy(&s_env, env->status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (q) CU(cudaMemcpy(&s_q, q->status, sizeof(int), cudaMemcpyDeviceToHost));
+    const int s = s_env | s_q;
+    if (s & SGK_ST_FULL) return fail(SGK_EFULL, "a Q table ran out of slots; create it with a larger capacity");
+    if (s & SGK_ST_REPLAY_DRY) return fail(SGK_EREPLAY, "a replayed word stream ran dry");
+    return SGK_OK;
+}
+
+extern "C" int sgk_rollout_tabq_host(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat,
+                                     const uint64_t *core_in, uint64_t *core_out, uint8_t *boards_out,
+                                     double totals_out[7], void *stream)
+{
+    REQUIRE(env != nullptr && q != nullptr, "env or q is NULL");
+    DeviceGuard g(env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local uint8_t *d_boards = nullptr;
+    static thread_local size_t d_boards_cap = 0;
+    if (core_in) CU(cudaMemcpyAsync(env->arr.core, core_in, (size_t)env->n * 8, cudaMemcpyHostToDevice, st));
+    int rc = sgk_rollout_tabq(env, q, n_steps, t0, cheat, stream);
+    if (rc != SGK_OK) return rc;
+    if (boards_out) {
+        const size_t bytes = (size_t)env->n * env->level.HW;
+        if (d_boards_cap < bytes) {
+            if (d_boards) cudaFree(d_boards);
+            d_boards = nullptr; d_boards_cap = 0;
+            CU(cudaMalloc(&d_boards, bytes));
+            d_boards_cap = bytes;
+        }
+        rc = sgk_env_render(env, d_boards, stream);
+        if (rc != SGK_OK) return rc;
+        CU(cudaMemcpyAsync(boards_out, d_boards, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (core_out) CU(cudaMemcpyAsync(core_out, env->arr.core, (size_t)env->n * 8, cudaMemcpyDeviceToHost, st));
+    if (totals_out) {
+        k_totals<<<1, 512, 0, st>>>(env->arr, env->n, env->totals);
+        CU(cudaMemcpyAsync(totals_out, env->totals, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return sgk_check(env, q, stream);
+}

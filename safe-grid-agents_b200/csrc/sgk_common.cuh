@@ -1,0 +1,191 @@
+// sgk_common.cuh -- level descriptions, packed environment state, Philox.
+//
+// Design: one THREAD owns one environment.  A gridworld of <= 64
+// cells is a handful of 64-bit bitboards (walls, goal, arrows, tomatoes), so
+// the whole dynamic state of an environment -- agent cell, box cell, frame,
+// 13 tomato bits, flags -- packs into ONE 64-bit word that lives in a register
+// for the duration of a fused rollout.  uint8 boards exist only at the API
+// boundary (rendered on demand, staged through shared memory for coalesced
+// stores).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SGK_NA 4
+#define SGK_MAX_CELLS 64
+#define SGK_MAX_TOMATOES 13
+
+// ----------------------------------------------------------------- levels
+// Static description of a level, derived on the host from its ASCII art
+// (sgk_levels.cpp) and passed to kernels by value (constant bank).
+struct Level {
+    int kind, H, W, HW;
+    int start, box_start;           // agent / box start cell
+    int max_iterations;             // frames per episode (100)
+    int n_tomatoes, n_delusional;   // tomato: 13, 28
+    uint64_t walls;                 // bit c: cell c is '#'
+    uint64_t arrow[SGK_NA];         // boat: cells whose clockwise move is action a
+    uint64_t arrows;                // boat: any arrow tile
+    uint64_t goal;                  // sokoban 'G'
+    uint64_t transformer;           // tomato 'O'
+    uint64_t tomato;                // tomato cells
+    uint32_t watered0;              // tomato: initially watered, slot space
+    uint32_t row_full, col_full;    // bit r / c: that whole grid row / column is wall
+    uint8_t base[SGK_MAX_CELLS];    // value-mapped backdrop (what lies beneath things)
+    uint8_t tomato_slot[SGK_MAX_CELLS];   // row-major tomato index of a cell, 0xFF if none
+    uint8_t slot_cell[16];          // inverse
+};
+
+// ----------------------------------------------------------------- state
+// core word layout
+//   bits  0.. 7  agent cell            bits 24..31  flags
+//   bits  8..15  box cell (sokoban)    bits 32..47  watered tomatoes (slot space)
+//   bits 16..23  frame
+#define SGK_F_HIDDEN 1u   // the episode has produced hidden reward (else info reports None)
+#define SGK_F_PERF 2u     // at least one episode finished (get_last_performance() is not None)
+#define SGK_F_DONE 4u     // episode over, waiting for reset (unfused API only)
+
+struct EnvRegs {
+    uint32_t pos, box, frame, flags, watered;
+    double ep_return, hidden_cum;
+};
+
+__host__ __device__ __forceinline__ uint64_t pack_core(const EnvRegs &e)
+{
+    return (uint64_t)e.pos | ((uint64_t)e.box << 8) | ((uint64_t)e.frame << 16) |
+           ((uint64_t)e.flags << 24) | ((uint64_t)e.watered << 32);
+}
+
+__host__ __device__ __forceinline__ void unpack_core(uint64_t c, EnvRegs &e)
+{
+    e.pos = (uint32_t)(c & 0xFF);
+    e.box = (uint32_t)((c >> 8) & 0xFF);
+    e.frame = (uint32_t)((c >> 16) & 0xFF);
+    e.flags = (uint32_t)((c >> 24) & 0xFF);
+    e.watered = (uint32_t)((c >> 32) & 0xFFFF);
+}
+
+// Per-environment arrays in HBM, structure-of-arrays so that thread-per-env
+// loads and stores are fully coalesced.
+struct EnvArrays {
+    uint64_t *core;
+    double *ep_return, *hidden_cum;
+    double *last_return, *last_perf;
+    double *sum_return, *sum_perf, *sum_margin_pos, *max_return;
+    unsigned long long *counts;      // episodes (low 40 bits) | n_margin_pos << 40
+    unsigned long long *trace_hash;
+    long long *replay_cursor;        // replay mode
+};
+
+// ----------------------------------------------------------------- Philox
+// Philox4x32-10 (Salmon et al., SC'11).  key = seed, counter =
+// (env_lo, env_hi, step_lo, call | step_hi << 8); see DESIGN.md "RNG".
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// numpy legacy random_sample(): 53 random bits from two words.
+__host__ __device__ __forceinline__ uint64_t words_to_u53(uint32_t a, uint32_t b)
+{
+    return ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6);
+}
+
+// u < 0.05 for u = X / 2^53, X integer: the double 0.05 is
+// 3602879701896397 / 2^56, so u < 0.05  <=>  8X < 3602879701896397
+// <=>  X <= 450359962737049.
+#define SGK_DRY_THRESHOLD 450359962737049ull
+
+#define SGK_CALL_AGENT 0
+#define SGK_CALL_ENV_STEP 1
+#define SGK_CALL_ENV_RESET 8
+
+struct PhiloxStream {
+    uint32_t k0, k1, e0, e1;
+    uint32_t s0, s1;      // step lo / hi
+    uint32_t w[4];        // cached agent call
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t env_id)
+    {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        e0 = (uint32_t)env_id; e1 = (uint32_t)(env_id >> 32);
+        s0 = s1 = 0;
+    }
+    __device__ __forceinline__ void set_step(uint64_t step)
+    {
+        s0 = (uint32_t)step;
+        s1 = (uint32_t)((step >> 32) & 0xFFFFFF) << 8;
+    }
+    __device__ __forceinline__ void call(int c, uint32_t out[4]) const
+    {
+        philox4x32_10(e0, e1, s0, (uint32_t)c | s1, k0, k1, out);
+    }
+    // agent: one call serves the uniform, the explore action and the random action
+    __device__ __forceinline__ uint64_t agent_uniform() { call(SGK_CALL_AGENT, w); return words_to_u53(w[0], w[1]); }
+    __device__ __forceinline__ int agent_choice() { return (int)(w[2] & (SGK_NA - 1)); }
+    __device__ __forceinline__ int random_action() { call(SGK_CALL_AGENT, w); return (int)(w[3] & (SGK_NA - 1)); }
+    // tomato: which of the watered tomatoes (slot mask) dry this frame
+    __device__ __forceinline__ uint32_t dry_mask(uint32_t watered, bool at_reset) const
+    {
+        uint32_t dry = 0;
+        const int base = at_reset ? SGK_CALL_ENV_RESET : SGK_CALL_ENV_STEP;
+#pragma unroll
+        for (int j = 0; j < (SGK_MAX_TOMATOES + 1) / 2; j++) {
+            if ((watered >> (2 * j)) & 3u) {
+                uint32_t o[4];
+                call(base + j, o);
+                if (words_to_u53(o[0], o[1]) <= SGK_DRY_THRESHOLD) dry |= 1u << (2 * j);
+                if (words_to_u53(o[2], o[3]) <= SGK_DRY_THRESHOLD) dry |= 2u << (2 * j);
+            }
+        }
+        return dry & watered;
+    }
+    __device__ __forceinline__ bool overflowed() const { return false; }
+};
+
+// Sequential replay of raw MT19937 words with numpy's legacy mapping.
+struct ReplayStream {
+    const uint32_t *words;
+    long long cursor, n_words;
+    bool dry_stream;
+    __device__ __forceinline__ void set_step(uint64_t) {}
+    __device__ __forceinline__ uint32_t next()
+    {
+        if (cursor >= n_words) { dry_stream = true; return 0; }
+        return words[cursor++];
+    }
+    __device__ __forceinline__ uint64_t agent_uniform() { uint32_t a = next(); uint32_t b = next(); return words_to_u53(a, b); }
+    __device__ __forceinline__ int agent_choice() { return (int)(next() & (SGK_NA - 1)); }
+    __device__ __forceinline__ int random_action() { return (int)(next() & (SGK_NA - 1)); }
+    __device__ __forceinline__ uint32_t dry_mask(uint32_t watered, bool)
+    {
+        uint32_t dry = 0;
+        for (int k = 0; k < SGK_MAX_TOMATOES; k++)
+            if ((watered >> k) & 1u) {
+                uint32_t a = next(); uint32_t b = next();
+                if (words_to_u53(a, b) <= SGK_DRY_THRESHOLD) dry |= 1u << k;
+            }
+        return dry;
+    }
+    __device__ __forceinline__ bool overflowed() const { return dry_stream; }
+};
+
+// trace hash (test mode): same folding as oracle/cgrid.c trace_fold
+__host__ __device__ __forceinline__ uint64_t fold64(uint64_t h, uint64_t x)
+{
+    h = (h ^ x) * 0x100000001b3ull;
+    return h ^ (h >> 29);
+}

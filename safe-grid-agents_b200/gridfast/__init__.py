@@ -1,0 +1,23 @@
+"""gridfast -- B200-native rollout engine for safe-grid-agents' hot path.
+
+Public surface
+    BatchedEnv, BatchedTabularQ         N lock-step environments / agents
+    GridworldEnv, make                  single-env adapter with the gym-style
+                                        API the reference drives
+    GpuTabularQAgent                    drop-in for the reference TabularQAgent
+    register_with_reference             put them into the reference's
+                                        ENV_MAP / AGENT_MAP registries
+There is no CPU fallback: constructing any of these without the CUDA library
+or without a CUDA device raises.
+"""
+from ._lib import (ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, Q_PRIVATE, Q_SHARED,
+                   RNG_PHILOX, RNG_REPLAY, SgkError)
+from .batched import BatchedEnv, BatchedTabularQ, KIND_BY_ALIAS, KIND_BY_ID
+from .adapters import (GpuTabularQAgent, GridworldEnv, make,
+                       register_with_reference)
+
+__all__ = [
+    "BatchedEnv", "BatchedTabularQ", "GridworldEnv", "GpuTabularQAgent", "make",
+    "register_with_reference", "SgkError", "ENV_BOAT", "ENV_SOKOBAN", "ENV_TOMATO",
+    "Q_PRIVATE", "Q_SHARED", "RNG_PHILOX", "RNG_REPLAY", "KIND_BY_ALIAS", "KIND_BY_ID",
+]

@@ -1,0 +1,304 @@
+"""Single-environment adapters: the duck-typed surface the reference drives.
+
+`GridworldEnv` stands where `gym.make(ENV_MAP[alias])` stands in the reference
+(train.py:51-52) and answers every member the reference touches (SURVEY.md
+section 8b): seed, reset, step -> (board float32 (1,H,W), reward, done, info),
+action_space.n, observation_space.shape, render(mode="rgb_array"),
+_env.episode_return, _env.get_last_performance().
+
+`GpuTabularQAgent` stands where `TabularQAgent(env, args)` stands
+(common/agents/value.py:15-58): act, act_explore, learn, update_epsilon,
+attributes Q, epsilon, action_n, discount, lr.
+
+Both are N == 1 views of the batched engine; all dynamics, table lookups and
+updates run in the CUDA kernels.  What stays on the host is only the plumbing
+the reference also keeps on the host: the random draws come from numpy's
+global stream when rng="numpy" (exactly the calls the reference makes:
+np.random.sample / np.random.choice at value.py:38-39), so that a run seeded
+with np.random.seed(s) (train.py:32) follows the reference's own stream.
+"""
+import numpy as np
+import torch
+
+from . import batched
+from ._lib import Q_PRIVATE, SgkError
+
+_MAX_WORDS_PER_CALL = 32      # >= 2 words x 13 tomatoes
+
+# colours for render(mode="rgb_array") only; not part of any parity claim
+_PALETTE = np.array([[152, 152, 152], [219, 219, 219], [0, 180, 255], [0, 210, 50],
+                     [153, 102, 51], [255, 0, 255]], dtype=np.uint8)
+
+
+class _Discrete:
+    def __init__(self, n):
+        self.n = n
+
+    def sample(self):
+        return int(np.random.randint(0, self.n))
+
+    def contains(self, x):
+        return 0 <= int(x) < self.n
+
+
+class _Box:
+    def __init__(self, shape):
+        self.shape = shape
+        self.dtype = np.float32
+
+
+def _as_int_action(action):
+    # numpy.int64 from argmax, int from np.random.choice, or a 1-element tensor
+    # from DeepQAgent.act (value.py:35,39,92)
+    if hasattr(action, "item"):
+        return int(action.item())
+    return int(action)
+
+
+class _InnerEnv:
+    """What the reference reaches through `env._env` (meters.py:67-80)."""
+
+    def __init__(self, outer):
+        self._outer = outer
+
+    @property
+    def episode_return(self):
+        return self._outer._episode_return
+
+    def get_last_performance(self):
+        return self._outer._last_performance
+
+
+class GridworldEnv:
+    metadata = {"render.modes": ["human", "ansi", "rgb_array"]}
+
+    def __init__(self, env_id, seed=0, device=0, rng="numpy", env_index=0):
+        if rng not in ("numpy", "philox"):
+            raise ValueError("rng must be 'numpy' or 'philox'")
+        self._env_id = env_id
+        self._device = device
+        self._rng = rng
+        self._env_index = env_index
+        self._make(seed)
+        self._env = _InnerEnv(self)
+        self.action_space = _Discrete(self.batched.n_actions)
+        self.observation_space = _Box(self.batched.shape)
+
+    def _make(self, seed):
+        self.batched = batched.BatchedEnv(self._env_id, 1, seed=seed, env_id0=self._env_index,
+                                          device=self._device)
+        self._t = 0
+        self._episode_return = 0
+        self._last_performance = None
+        self._board = None
+        self._actions = torch.zeros(1, dtype=torch.uint8, device=self.batched.device)
+        self._out = (self.batched._u8(1, self.batched.hw), self.batched._f64(1),
+                     self.batched._f64(1), self.batched._u8(1))
+        self._cursor = torch.zeros(1, dtype=torch.int64, device=self.batched.device)
+        self._stochastic = self.batched.kind == batched.ENV_TOMATO
+
+    def seed(self, seed=None):
+        """train.py:52.  Philox mode re-keys the streams; numpy mode seeds the
+        global numpy stream like the wrapper the reference uses."""
+        if self._rng == "philox":
+            self._make(0 if seed is None else seed)
+        else:
+            np.random.seed(seed)
+        return [seed]
+
+    # -- numpy-stream plumbing: lend the kernel the next raw words of the global
+    # stream, then advance the stream by exactly what the kernel consumed
+    def _lend_words(self):
+        if self._rng != "numpy" or not self._stochastic:
+            return None
+        state = np.random.get_state()
+        words = np.random.randint(0, 2 ** 32, size=_MAX_WORDS_PER_CALL, dtype=np.uint32)
+        self.batched.set_replay_words(words.reshape(1, -1))
+        return state
+
+    def _settle_words(self, state):
+        if state is None:
+            return
+        batched.check(self.batched.L.sgk_env_replay_cursor(
+            self.batched.h, batched._p(self._cursor), batched._stream()))
+        used = int(self._cursor.item())
+        np.random.set_state(state)
+        if used:
+            np.random.randint(0, 2 ** 32, size=used, dtype=np.uint32)
+
+    def _observation(self, boards):
+        self._board = boards[0].cpu().numpy()
+        c, h, w = self.batched.shape
+        return self._board.astype(np.float32).reshape(c, h, w)
+
+    def reset(self):
+        state = self._lend_words()
+        boards = self.batched.reset(step=self._t)
+        self._settle_words(state)
+        self._episode_return = 0
+        return self._observation(boards)
+
+    def step(self, action):
+        action = _as_int_action(action)
+        if not 0 <= action < self.batched.n_actions:
+            raise ValueError("action %r outside the action space" % (action,))
+        self._actions[0] = action
+        state = self._lend_words()
+        boards, reward, hidden, done = self.batched.step(self._actions, step=self._t, out=self._out)
+        self._settle_words(state)
+        self._t += 1
+        host = torch.stack([reward[0], hidden[0], done[0].double()]).cpu().numpy()
+        reward, hidden, done = float(host[0]), float(host[1]), bool(host[2])
+        hidden = None if hidden != hidden else hidden
+        stats = self.batched.stats()
+        self._episode_return = float(stats["episode_return"][0].item())
+        if done:
+            self._last_performance = float(stats["last_performance"][0].item())
+        info = {"hidden_reward": hidden, "observed_reward": reward,
+                "discount": 0.0 if (done and self.batched.kind == batched.ENV_SOKOBAN and reward == 49.0) else 1.0,
+                "extra_observations": {"actual_actions": action}}
+        if done:
+            info["extra_observations"]["termination_reason"] = 0 if info["discount"] == 0.0 else 1
+        return self._observation(boards), reward, done, info
+
+    def render(self, mode="human", close=False):
+        if self._board is None:
+            self._observation(self.batched.render())
+        c, h, w = self.batched.shape
+        if mode == "rgb_array":
+            return np.moveaxis(_PALETTE[self._board.reshape(h, w)], -1, 0)
+        text = "\n".join("".join("# A*XG"[v] for v in row) for row in self._board.reshape(h, w))
+        if mode == "ansi":
+            return text
+        print(text)
+
+
+def make(env_id, **kwargs):
+    """Stand-in for gym.make (train.py:51)."""
+    return GridworldEnv(env_id, **kwargs)
+
+
+class _QView:
+    """Read-only dict-like view of the device table, keyed like the
+    reference's Q (tuple of the flattened float32 board, value.py:34)."""
+
+    def __init__(self, agent):
+        self._agent = agent
+
+    def _snapshot(self):
+        keys, rows = self._agent.table.export(0)
+        seen = self._agent._boards_by_key
+        return {seen[int(k)]: rows[i] for i, k in enumerate(keys) if int(k) in seen}
+
+    def __len__(self):
+        return len(self._snapshot())
+
+    def __iter__(self):
+        return iter(self._snapshot())
+
+    def __getitem__(self, key):
+        snap = self._snapshot()
+        key = tuple(np.float32(v) for v in key)
+        if key not in snap:
+            return np.zeros(self._agent.action_n)
+        return snap[key]
+
+    def items(self):
+        return self._snapshot().items()
+
+    def keys(self):
+        return self._snapshot().keys()
+
+
+class GpuTabularQAgent:
+    """Drop-in for TabularQAgent (common/agents/value.py:15-58); constructor
+    signature (env, args) as AGENT_MAP classes have (train.py:54)."""
+
+    def __init__(self, env, args):
+        if not isinstance(env, GridworldEnv):
+            raise SgkError("GpuTabularQAgent needs a gridfast GridworldEnv")
+        self.env = env
+        self.action_n = env.action_space.n
+        self.discount = args.discount
+        self.lr = args.lr
+        self._final_epsilon = args.epsilon
+        self._anneal = args.epsilon_anneal
+        self._rng = env._rng
+        self.table = batched.BatchedTabularQ(
+            env.batched, q_mode=Q_PRIVATE, capacity=getattr(args, "q_capacity", 0),
+            lr=args.lr, discount=args.discount, epsilon=args.epsilon,
+            epsilon_anneal=args.epsilon_anneal)
+        self._k = 0                # number of update_epsilon calls so far
+        self.epsilon = 0.0         # value.py:28
+        self.Q = _QView(self)
+        self._boards_by_key = {}
+        dev = env.batched.device
+        hw = env.batched.hw
+        self._s = torch.zeros(1, hw, dtype=torch.uint8, device=dev)
+        self._s2 = torch.zeros(1, hw, dtype=torch.uint8, device=dev)
+        self._a = torch.zeros(1, dtype=torch.uint8, device=dev)
+        self._r = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def _upload(self, buf, state):
+        flat = np.asarray(state).reshape(-1)
+        board = flat.astype(np.uint8)
+        buf.copy_(torch.from_numpy(board).reshape(1, -1))
+        return flat
+
+    def _remember(self, buf, flat):
+        key = int(self.env.batched.board_keys(buf)[0].item()) & 0xFFFFFFFFFFFFFFFF
+        if key not in self._boards_by_key:
+            self._boards_by_key[key] = tuple(np.float32(v) for v in flat)
+
+    def act(self, state):
+        flat = self._upload(self._s, state)
+        self._remember(self._s, flat)
+        action = self.table.act(self._s, self._k, explore=False)
+        return np.int64(action[0].item())
+
+    def act_explore(self, state):
+        if self._rng == "numpy":
+            # the reference's own two draws (value.py:38-39), from its stream
+            if np.random.sample() < self.epsilon:
+                return np.random.choice(self.action_n)
+            return self.act(state)
+        flat = self._upload(self._s, state)
+        self._remember(self._s, flat)
+        action = self.table.act(self._s, self._k, explore=True)
+        return np.int64(action[0].item())
+
+    def learn(self, state, action, reward, successor):
+        flat = self._upload(self._s, state)
+        flat2 = self._upload(self._s2, successor)
+        self._remember(self._s, flat)
+        self._remember(self._s2, flat2)
+        self._a[0] = _as_int_action(action)
+        self._r[0] = float(reward)
+        self.table.learn(self._s, self._a, self._r, self._s2)
+
+    def update_epsilon(self):
+        self._k += 1
+        self.epsilon = self.table.epsilon_at(self._k)
+        return self.epsilon
+
+
+def register_with_reference(env_map=None, agent_map=None, gym_module=None, **env_kwargs):
+    """Register the GPU path into the reference's own registries
+    (safe_grid_agents/parsing/parse.py:22-48) and, if given, replace
+    `gym.make` so that train.train(args) builds gridfast environments for the
+    in-scope ids.  Returns the previous gym.make (or None)."""
+    previous = None
+    if agent_map is not None:
+        agent_map["tabular-q"] = GpuTabularQAgent
+    if gym_module is not None:
+        previous = gym_module.make
+
+        def _make(env_id, *a, **k):
+            if env_id in batched.KIND_BY_ID:
+                return GridworldEnv(env_id, **env_kwargs)
+            if previous is None:
+                raise SgkError("environment %r is outside the GPU path's scope" % env_id)
+            return previous(env_id, *a, **k)
+
+        gym_module.make = _make
+    return previous

@@ -1,0 +1,231 @@
+"""Batched lock-step environments and tabular agents on one GPU.
+
+Thin host objects over the C ABI (include/sgk.h).  torch is used only for
+device buffers and streams; all computation happens in libsgk.so's kernels.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, Q_PRIVATE, Q_SHARED,
+                   RNG_PHILOX, RNG_REPLAY, EnvStats, SgkError, check)
+
+# ENV_MAP values at safe_grid_agents/parsing/parse.py:25,29,31
+KIND_BY_ID = {"BoatRace-v0": ENV_BOAT, "SideEffectsSokoban-v0": ENV_SOKOBAN,
+              "TomatoWatering-v0": ENV_TOMATO}
+KIND_BY_ALIAS = {"boat": ENV_BOAT, "sokoban": ENV_SOKOBAN, "tomato": ENV_TOMATO}
+
+
+def _kind(kind):
+    if isinstance(kind, str):
+        if kind in KIND_BY_ID:
+            return KIND_BY_ID[kind]
+        if kind in KIND_BY_ALIAS:
+            return KIND_BY_ALIAS[kind]
+        raise ValueError("unknown environment %r (in scope: %s)" % (kind, sorted(KIND_BY_ID)))
+    return int(kind)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class BatchedEnv:
+    """`n_envs` lock-step copies of one gridworld (replaces N x gym.make,
+    train.py:51-52).  Environment i has global id env_id0 + i."""
+
+    def __init__(self, kind, n_envs, seed=0, env_id0=0, device=0):
+        if not torch.cuda.is_available():
+            raise SgkError("gridfast needs a CUDA device; there is no CPU fallback")
+        self.L = _lib.load()
+        self.kind = _kind(kind)
+        self.n = int(n_envs)
+        self.seed, self.env_id0 = int(seed), int(env_id0)
+        self.device = torch.device("cuda", device)
+        self.h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.L.sgk_env_create(self.kind, self.n, self.env_id0, self.seed, device, ctypes.byref(self.h)))
+        c, h, w, a = (ctypes.c_int() for _ in range(4))
+        check(self.L.sgk_env_shape(self.h, c, h, w, a))
+        self.shape = (c.value, h.value, w.value)
+        self.hw = h.value * w.value
+        self.n_actions = a.value
+        self._replay = None
+        self.t = 0   # agent-step index of the next lock-step
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            self.L.sgk_env_destroy(h)
+
+    # -- buffers -------------------------------------------------------------
+    def _u8(self, *shape):
+        return torch.empty(shape, dtype=torch.uint8, device=self.device)
+
+    def _f64(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.device)
+
+    # -- configuration -------------------------------------------------------
+    def set_replay_words(self, words):
+        """Replay raw MT19937 words ([n_envs, L] uint32) instead of Philox."""
+        w = torch.as_tensor(np.ascontiguousarray(words, dtype=np.uint32).view(np.int32)).to(self.device)
+        w = w.reshape(self.n, -1).contiguous()
+        self._replay = w
+        check(self.L.sgk_env_set_replay(self.h, _p(w), w.shape[1]))
+
+    def set_trace(self, enabled=True):
+        check(self.L.sgk_env_set_trace(self.h, int(enabled)))
+
+    # -- the unfused env API ---------------------------------------------------
+    def reset(self, mask=None, step=None, want_boards=True):
+        boards = self._u8(self.n, self.hw) if want_boards else None
+        step = self.t if step is None else step
+        check(self.L.sgk_env_reset(self.h, _p(mask), step, _p(boards), _stream()))
+        return boards
+
+    def step(self, actions, step=None, out=None):
+        """One lock-step.  actions: uint8 cuda tensor [n].  Returns
+        (boards u8 [n,HW], reward f64 [n], hidden f64 [n] (NaN = None), done u8 [n])."""
+        if out is None:
+            out = (self._u8(self.n, self.hw), self._f64(self.n), self._f64(self.n), self._u8(self.n))
+        boards, reward, hidden, done = out
+        step = self.t if step is None else step
+        check(self.L.sgk_env_step(self.h, _p(actions), step, _p(boards), _p(reward), _p(hidden), _p(done), _stream()))
+        self.t = step + 1
+        return boards, reward, hidden, done
+
+    def render(self):
+        boards = self._u8(self.n, self.hw)
+        check(self.L.sgk_env_render(self.h, _p(boards), _stream()))
+        return boards
+
+    def boards_to_f32(self, boards):
+        n = boards.shape[0]
+        out = torch.empty((n,) + self.shape, dtype=torch.float32, device=self.device)
+        check(self.L.sgk_board_to_f32(self.h, _p(boards), _p(out), n, _stream()))
+        return out
+
+    def board_keys(self, boards):
+        boards = boards.contiguous()
+        n = boards.shape[0]
+        out = torch.empty(n, dtype=torch.int64, device=self.device)
+        check(self.L.sgk_board_to_key(self.h, _p(boards), _p(out), n, _stream()))
+        return out
+
+    # -- bookkeeping -----------------------------------------------------------
+    def stats(self):
+        """Per-environment episode bookkeeping as a dict of cuda tensors."""
+        f = {k: self._f64(self.n) for k in ("episode_return", "last_return", "last_performance",
+                                            "sum_return", "sum_performance", "sum_margin_pos", "max_return")}
+        i = {k: torch.empty(self.n, dtype=torch.int64, device=self.device)
+             for k in ("episodes", "n_margin_pos", "trace_hash")}
+        st = EnvStats(**{k: v.data_ptr() for k, v in {**f, **i}.items()})
+        check(self.L.sgk_env_get_stats(self.h, ctypes.byref(st), _stream()))
+        return {**f, **i}
+
+    def totals(self):
+        """Deterministic totals over all copies (synchronises)."""
+        buf = (ctypes.c_double * 7)()
+        check(self.L.sgk_env_totals_host(self.h, ctypes.byref(buf), _stream()))
+        keys = ("episodes", "sum_return", "sum_performance", "sum_margin_pos", "n_margin_pos",
+                "max_return", "running_return")
+        return dict(zip(keys, list(buf)))
+
+    def core(self):
+        out = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        check(self.L.sgk_env_get_core(self.h, _p(out), _stream()))
+        return out
+
+    def rollout_random(self, n_steps):
+        check(self.L.sgk_rollout_random(self.h, n_steps, self.t, _stream()))
+        self.t += n_steps
+
+
+class BatchedTabularQ:
+    """Tabular Q agent(s) for a BatchedEnv: private (one table per
+    environment = N copies of the reference's TabularQAgent,
+    common/agents/value.py:15-58) or one shared table."""
+
+    def __init__(self, env, q_mode=Q_PRIVATE, capacity=0, lr=0.5, discount=0.99,
+                 epsilon=0.01, epsilon_anneal=100000):
+        self.L = env.L
+        self.env = env
+        self.q_mode = q_mode
+        self.h = ctypes.c_void_p()
+        with torch.cuda.device(env.device):
+            check(self.L.sgk_tabq_create(env.h, q_mode, capacity, ctypes.byref(self.h)))
+        self.capacity = self.L.sgk_tabq_capacity(self.h)
+        self.n_tables = self.L.sgk_tabq_tables(self.h)
+        self.configure(lr, discount, epsilon, epsilon_anneal)
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            self.L.sgk_tabq_destroy(h)
+
+    def configure(self, lr, discount, epsilon, epsilon_anneal):
+        self.lr, self.discount, self.epsilon, self.epsilon_anneal = lr, discount, epsilon, epsilon_anneal
+        check(self.L.sgk_tabq_configure(self.h, lr, discount, epsilon, epsilon_anneal))
+
+    def enable_ssrl(self, c_prior, budget, max_episode_steps=100):
+        check(self.L.sgk_tabq_enable_ssrl(self.h, c_prior, budget, max_episode_steps))
+
+    def epsilon_at(self, k):
+        return self.L.sgk_tabq_epsilon_at(self.h, k)
+
+    def act(self, boards, step, explore=False, out=None):
+        n = boards.shape[0]
+        out = self.env._u8(n) if out is None else out
+        check(self.L.sgk_tabq_act(self.h, self.env.h, _p(boards), n, step, int(explore), _p(out), _stream()))
+        return out
+
+    def learn(self, boards, actions, rewards, successors):
+        n = boards.shape[0]
+        check(self.L.sgk_tabq_learn(self.h, _p(boards), _p(actions), _p(rewards), _p(successors), n, _stream()))
+
+    def rollout(self, n_steps, cheat=False):
+        """The fused hot path: n_steps lock-steps of act/step/learn/reset."""
+        check(self.L.sgk_rollout_tabq(self.env.h, self.h, n_steps, self.env.t, int(cheat), _stream()))
+        self.env.t += n_steps
+
+    def check(self):
+        check(self.L.sgk_check(self.env.h, self.h, _stream()))
+
+    def export(self, table=0, with_corruption=False):
+        """(keys int64 [m], rows f64 [m,4]) of the occupied slots (host numpy)."""
+        dev = self.env.device
+        keys = torch.empty(self.capacity, dtype=torch.int64, device=dev)
+        rows = torch.empty(self.capacity, 4, dtype=torch.float64, device=dev)
+        corr = torch.empty(self.capacity, dtype=torch.float64, device=dev) if with_corruption else None
+        check(self.L.sgk_tabq_export(self.h, table, _p(keys), _p(rows), _p(corr), _stream()))
+        keys, rows = keys.cpu().numpy().view(np.uint64), rows.cpu().numpy()
+        used = keys != 0
+        if with_corruption:
+            return keys[used], rows[used], corr.cpu().numpy()[used]
+        return keys[used], rows[used]
+
+    def import_table(self, table, keys_full, rows_full):
+        dev = self.env.device
+        k = torch.as_tensor(np.ascontiguousarray(keys_full).view(np.int64)).to(dev)
+        r = torch.as_tensor(np.ascontiguousarray(rows_full, dtype=np.float64)).to(dev)
+        assert k.numel() == self.capacity and r.shape == (self.capacity, 4)
+        check(self.L.sgk_tabq_import(self.h, table, _p(k), _p(r), _stream()))
+        torch.cuda.current_stream().synchronize()
+
+    def rollout_host(self, n_steps, core_in, core_out, boards_out, cheat=False):
+        """Host-buffer form: pinned numpy/torch CPU buffers in and out."""
+        totals = (ctypes.c_double * 7)()
+        check(self.L.sgk_rollout_tabq_host(
+            self.env.h, self.h, n_steps, self.env.t, int(cheat),
+            None if core_in is None else ctypes.c_void_p(core_in.data_ptr()),
+            None if core_out is None else ctypes.c_void_p(core_out.data_ptr()),
+            None if boards_out is None else ctypes.c_void_p(boards_out.data_ptr()),
+            ctypes.byref(totals), _stream()))
+        self.env.t += n_steps
+        return list(totals)

@@ -1,0 +1,116 @@
+"""The drop-in surface: gridfast.GridworldEnv + GpuTabularQAgent driven by the
+reference's loop shape (train.py:62-70 around learn.py:61-85), seeded through
+numpy exactly like train.py:31-33, must reproduce the golden fixtures the LIVE
+reference agent produced -- boards, actions, rewards, hidden rewards, done
+flags, episode metrics and Q rows, bit for bit."""
+import argparse
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _drive(env, agent, episodes, cheat):
+    """train.py:62-70 + whiler/tabq_learn (learn.py:8-85), writer dropped."""
+    log, metrics = [], []
+    for _ in range(episodes):
+        state, done = env.reset(), False
+        log.append(("reset", state.copy()))
+        while not done:
+            action = agent.act_explore(state)
+            successor, reward, done, info = env.step(action)
+            observed = reward
+            if cheat:
+                reward = info["hidden_reward"]
+                try:
+                    action = info["extra_observations"]["actual_actions"]
+                except KeyError:
+                    pass
+            agent.learn(state, action, reward, successor)
+            agent.update_epsilon()
+            log.append((int(action), successor.copy(), observed, info["hidden_reward"], done))
+            state = successor
+        metrics.append((env._env.episode_return, env._env.get_last_performance()))
+    return log, metrics
+
+
+def test_adapters_reproduce_live_reference_golden(golden_files):
+    import gridfast
+
+    for path in golden_files:
+        g = np.load(path)
+        seed = int(g["seed"])
+        args = argparse.Namespace(discount=float(g["discount"]), epsilon=float(g["epsilon"]),
+                                  epsilon_anneal=int(g["epsilon_anneal"]), lr=float(g["lr"]))
+        np.random.seed(seed)                       # train.py:32
+        env = gridfast.make(str(g["env_id"]))      # train.py:51
+        env.seed(seed)                             # train.py:52
+        assert env.action_space.n == 4 and env.observation_space.shape[0] == 1
+        agent = gridfast.GpuTabularQAgent(env, args)
+        assert agent.epsilon == 0.0
+        log, metrics = _drive(env, agent, len(g["episode_returns"]), bool(g["cheat"]))
+        steps = [l for l in log if l[0] != "reset"]
+        resets = [l[1] for l in log if l[0] == "reset"]
+        assert len(steps) == int(g["n_steps"])
+        hw = g["boards"].shape[1]
+        assert steps[0][1].dtype == np.float32 and steps[0][1].shape == env.observation_space.shape
+        assert np.array_equal(np.array([s[0] for s in steps], np.uint8), g["actions"])
+        assert np.array_equal(np.array([s[1].reshape(hw) for s in steps], np.uint8), g["boards"])
+        assert np.array_equal(np.array([r.reshape(hw) for r in resets], np.uint8), g["reset_boards"])
+        assert np.array_equal(np.array([s[2] for s in steps], np.float64), g["rewards"])
+        hid = np.array([np.nan if s[3] is None else s[3] for s in steps], np.float64)
+        assert np.array_equal(hid, g["hidden"], equal_nan=True)
+        assert np.array_equal(np.array([s[4] for s in steps]), g["done"])
+        assert np.array_equal(np.array([m[0] for m in metrics], np.float64), g["episode_returns"])
+        assert np.array_equal(np.array([m[1] for m in metrics], np.float64), g["episode_performance"])
+        assert agent.epsilon == float(g["final_epsilon"])
+        # the dict-like Q view, keyed like the reference's (value.py:34)
+        assert len(agent.Q) == len(g["q_keys"])
+        for key, row in zip(g["q_keys"], g["q_rows"]):
+            assert np.array_equal(agent.Q[tuple(np.float32(v) for v in key)], row)
+        # the stream was advanced by exactly what the reference would have drawn
+        ref_stream = np.random.RandomState(seed)
+        ref_stream.randint(0, 2 ** 32, size=int(g["words_used"]), dtype=np.uint32)
+        assert np.random.random() == ref_stream.random_sample()
+
+
+def test_philox_adapter_matches_oracle_agent():
+    import gridfast
+    from oracle import gridworld_env, rng, tabular
+
+    args = argparse.Namespace(discount=0.99, epsilon=0.01, epsilon_anneal=120, lr=0.5)
+    for env_id in ("BoatRace-v0", "TomatoWatering-v0"):
+        env = gridfast.make(env_id, rng="philox", env_index=5)
+        env.seed(99)
+        agent = gridfast.GpuTabularQAgent(env, args)
+        log, metrics = _drive(env, agent, 3, False)
+        stream = rng.PhiloxRng(99, env_id=5)
+        o_env = gridworld_env.make(env_id, rng=stream)
+        o_agent = tabular.TabularQAgent(4, 0.99, 0.01, 120, 0.5, rng=stream)
+        o_log = []
+        o_eps = tabular.run_tabq(o_agent, o_env, 300, env_id=5,
+                                 record=lambda t, s, a, r, h, d, s2: o_log.append((a, s2.copy(), r, d)))
+        steps = [l for l in log if l[0] != "reset"]
+        assert len(steps) == 300
+        for (a, b, r, h, d), (oa, ob, orr, od) in zip(steps, o_log):
+            assert a == oa and np.array_equal(b, ob) and r == orr and d == od
+        assert [m[0] for m in metrics] == [e[0] for e in o_eps]
+        for key, row in o_agent.Q.items():
+            assert np.array_equal(agent.Q[key], row)
+
+
+def test_env_render_and_action_types():
+    import torch
+    import gridfast
+
+    env = gridfast.make("SideEffectsSokoban-v0")
+    env.reset()
+    rgb = env.render(mode="rgb_array")
+    assert rgb.shape == (3, 6, 6) and rgb.dtype == np.uint8
+    for action in (np.int64(1), 1, torch.tensor([1])):      # value.py:35,39,92
+        env.reset()
+        board, r, d, info = env.step(action)
+        assert board[0, 2, 2] == 2.0 and board[0, 3, 2] == 4.0 and info["hidden_reward"] == -11
+    with pytest.raises(ValueError):
+        env.step(7)

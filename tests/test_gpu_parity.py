@@ -1,0 +1,305 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the
+golden fixtures.  Bar: bit-exact boards, actions, rewards, hidden rewards,
+done flags, episode metrics AND Q rows (the kernels do the reference's float64
+arithmetic without FMA contraction, so the north-star 1e-5 tolerance on Q is
+met with zero error)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ENVS = [("BoatRace-v0", 0), ("SideEffectsSokoban-v0", 1), ("TomatoWatering-v0", 2)]
+
+
+def _gf():
+    import gridfast
+    return gridfast
+
+
+def _cmp_stats(gpu_env, sim, with_hash=True):
+    st = {k: v.cpu().numpy() for k, v in gpu_env.stats().items()}
+    ref = sim.env_stats()
+    if with_hash:
+        assert np.array_equal(st["trace_hash"].view(np.uint64), ref["trace_hash"])
+    assert np.array_equal(st["episodes"], ref["episodes"])
+    assert np.array_equal(st["n_margin_pos"], ref["n_margin_pos"])
+    for g, o in (("episode_return", "episode_return"), ("sum_return", "sum_return"),
+                 ("sum_performance", "sum_perf"), ("sum_margin_pos", "sum_margin_pos")):
+        assert np.array_equal(st[g], ref[o]), g
+    done_any = ref["episodes"] > 0
+    assert np.array_equal(st["last_return"][done_any], ref["last_return"][done_any])
+    assert np.array_equal(st["last_performance"][done_any], ref["last_perf"][done_any])
+    assert np.isnan(st["last_performance"][~done_any]).all()
+    assert np.array_equal(st["max_return"][done_any], ref["max_return"][done_any])
+    assert np.array_equal(gpu_env.render().cpu().numpy(), sim.boards())
+
+
+def _cmp_table(env, agent, sim, table, with_c=False):
+    got = agent.export(table, with_corruption=with_c)
+    want = sim.table(table, with_c=with_c)
+    wk = env.board_keys(torch.as_tensor(want[0]).to(env.device)).cpu().numpy().view(np.uint64)
+    og, ow = np.argsort(got[0]), np.argsort(wk)
+    assert np.array_equal(got[0][og], wk[ow]), "key sets differ"
+    assert np.array_equal(got[1][og], want[1][ow]), "Q rows differ"
+    if with_c:
+        assert np.array_equal(got[2][og], want[2][ow]), "corruption estimates differ"
+
+
+# ------------------------------------------------------------------ golden
+def test_fused_rollout_reproduces_live_reference_golden(golden_files):
+    """Replay the raw MT19937 words of np.random.seed(s) through the fused
+    kernel: Q table, episode metrics and trajectory must equal what the LIVE
+    reference TabularQAgent + tabq_learn produced (tests/golden)."""
+    gf = _gf()
+    from oracle import cgrid, rng
+    for path in golden_files:
+        g = np.load(path)
+        kind = cgrid.KIND_BY_ID[str(g["env_id"])]
+        words = rng.mt19937_words(int(g["seed"]), 1 << 16)
+        hp = dict(lr=float(g["lr"]), discount=float(g["discount"]), epsilon=float(g["epsilon"]),
+                  epsilon_anneal=int(g["epsilon_anneal"]))
+        T = int(g["n_steps"])
+        env = gf.BatchedEnv(str(g["env_id"]), 1)
+        env.set_trace(True)
+        env.set_replay_words(words.reshape(1, -1))
+        first = env.reset(step=0).cpu().numpy()
+        assert np.array_equal(first[0], g["reset_boards"][0])
+        agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **hp)
+        # in two launches, to cover continuation across calls
+        agent.rollout(T // 3, cheat=bool(g["cheat"]))
+        agent.rollout(T - T // 3, cheat=bool(g["cheat"]))
+        agent.check()
+        # golden Q rows, bit for bit
+        keys, rows = agent.export(0)
+        gk = env.board_keys(torch.as_tensor(g["q_keys"]).to(env.device)).cpu().numpy().view(np.uint64)
+        og, ow = np.argsort(keys), np.argsort(gk)
+        assert np.array_equal(keys[og], gk[ow])
+        assert np.array_equal(rows[og], g["q_rows"][ow])
+        st = {k: v.cpu().numpy() for k, v in env.stats().items()}
+        assert st["episodes"][0] == len(g["episode_returns"])
+        assert st["last_return"][0] == g["episode_returns"][-1]
+        assert st["last_performance"][0] == g["episode_performance"][-1]
+        assert st["sum_return"][0] == np.cumsum(g["episode_returns"])[-1]
+        # trajectory: the C oracle reproduces the golden trace exactly
+        # (tests/test_oracle_golden.py), so equal hashes == equal traces
+        sim = cgrid.Sim(kind, 1, rng_mode=cgrid.RNG_REPLAY, replay_words=words, cheat=bool(g["cheat"]), **hp)
+        sim.rollout(T)
+        assert st["trace_hash"].view(np.uint64)[0] == sim.env_stats()["trace_hash"][0]
+        assert agent.epsilon_at(T) == float(g["final_epsilon"])
+
+
+def test_unfused_calls_reproduce_golden(golden_files):
+    """The one-call-per-reference-call API (env.step / agent.act / agent.learn
+    as separate kernels) driven by the golden action stream."""
+    gf = _gf()
+    for path in golden_files:
+        g = np.load(path)
+        if str(g["env_id"]) == "TomatoWatering-v0":
+            continue   # its env draws are interleaved with the agent's in the stream
+        env = gf.BatchedEnv(str(g["env_id"]), 1)
+        agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, lr=float(g["lr"]), discount=float(g["discount"]),
+                                   epsilon=float(g["epsilon"]), epsilon_anneal=int(g["epsilon_anneal"]))
+        board = env.reset(step=0)
+        cheat = bool(g["cheat"])
+        for t in range(int(g["n_steps"])):
+            a = torch.tensor([g["actions"][t]], dtype=torch.uint8, device=env.device)
+            nxt, r, h, d = env.step(a, step=t)
+            assert np.array_equal(nxt.cpu().numpy()[0], g["boards"][t])
+            assert r.item() == g["rewards"][t] and bool(d.item()) == bool(g["done"][t])
+            hv = h.item()
+            assert (np.isnan(hv) and np.isnan(g["hidden"][t])) or hv == g["hidden"][t]
+            greedy = agent.act(board, t, explore=False)
+            learn_r = torch.nan_to_num(h, nan=0.0) if cheat else r
+            agent.learn(board, a, learn_r, nxt)
+            board = nxt
+            if d.item():
+                board = env.reset(mask=d, step=t + 1)
+            del greedy
+        keys, rows = agent.export(0)
+        gk = env.board_keys(torch.as_tensor(g["q_keys"]).to(env.device)).cpu().numpy().view(np.uint64)
+        og, ow = np.argsort(keys), np.argsort(gk)
+        assert np.array_equal(keys[og], gk[ow]) and np.array_equal(rows[og], g["q_rows"][ow])
+
+
+# ------------------------------------------------------------------ oracle, Philox
+@pytest.mark.parametrize("env_id,kind", ENVS)
+def test_unfused_step_matches_oracle(env_id, kind):
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed = 1000, 260, 11
+    env = gf.BatchedEnv(env_id, n, seed=seed, env_id0=77)
+    env.set_trace(True)
+    sim = cgrid.Sim(kind, n, seed=seed, env_id0=77)
+    assert np.array_equal(env.render().cpu().numpy(), sim.boards())
+    rs = np.random.RandomState(5)
+    for t in range(T):
+        acts = rs.randint(0, 4, size=n).astype(np.uint8)
+        b, r, h, d = env.step(torch.as_tensor(acts).to(env.device), step=t)
+        ob, orr, oh, od = sim.step(acts)
+        assert np.array_equal(b.cpu().numpy(), ob)
+        assert np.array_equal(r.cpu().numpy(), orr)
+        assert np.array_equal(h.cpu().numpy(), oh, equal_nan=True)
+        assert np.array_equal(d.cpu().numpy(), od)
+        if od.any():
+            env.reset(mask=d, step=t + 1, want_boards=False)
+    _cmp_stats(env, sim)
+    obs = env.boards_to_f32(env.render())
+    assert obs.dtype == torch.float32 and tuple(obs.shape[1:]) == env.shape
+    assert np.array_equal(obs.cpu().numpy().reshape(n, -1), sim.boards().astype(np.float32))
+
+
+@pytest.mark.parametrize("env_id,kind", ENVS)
+@pytest.mark.parametrize("cheat", [False, True])
+def test_fused_private_matches_oracle(env_id, kind, cheat):
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed = (2048, 700, 3) if kind != 2 else (512, 500, 3)
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=400)
+    env = gf.BatchedEnv(env_id, n, seed=seed)
+    env.set_trace(True)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **hp)
+    for chunk in (1, 99, T - 100):
+        agent.rollout(chunk, cheat=cheat)
+    agent.check()
+    sim = cgrid.Sim(kind, n, seed=seed, cheat=cheat, **hp)
+    sim.rollout(T)
+    _cmp_stats(env, sim)
+    for i in (0, 1, 31, 32, n // 2 + 5, n - 1):
+        _cmp_table(env, agent, sim, i)
+
+
+@pytest.mark.parametrize("env_id,kind", ENVS)
+def test_fused_shared_matches_oracle(env_id, kind):
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed = (3000, 400, 9) if kind != 2 else (700, 300, 9)
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=200)
+    env = gf.BatchedEnv(env_id, n, seed=seed)
+    env.set_trace(True)
+    agent = gf.BatchedTabularQ(env, gf.Q_SHARED, **hp)
+    for chunk in (1, 120, T - 121):
+        agent.rollout(chunk)
+    agent.check()
+    sim = cgrid.Sim(kind, n, seed=seed, q_mode=cgrid.Q_SHARED, **hp)
+    sim.rollout(T)
+    _cmp_stats(env, sim)
+    _cmp_table(env, agent, sim, 0)
+
+
+def test_shared_with_one_env_is_the_reference_agent(golden_files):
+    """A shared table with N == 1 degenerates to the reference's sequential
+    Q-learning: check it against the live-reference golden Q rows."""
+    gf = _gf()
+    from oracle import rng
+    g = np.load([p for p in golden_files if "sokoban_tabq_seed5" in p][0])
+    words = rng.mt19937_words(int(g["seed"]), 1 << 16)
+    env = gf.BatchedEnv(str(g["env_id"]), 1)
+    env.set_replay_words(words.reshape(1, -1))
+    env.reset(step=0)
+    agent = gf.BatchedTabularQ(env, gf.Q_SHARED, lr=float(g["lr"]), discount=float(g["discount"]),
+                               epsilon=float(g["epsilon"]), epsilon_anneal=int(g["epsilon_anneal"]))
+    agent.rollout(int(g["n_steps"]))
+    agent.check()
+    keys, rows = agent.export(0)
+    gk = env.board_keys(torch.as_tensor(g["q_keys"]).to(env.device)).cpu().numpy().view(np.uint64)
+    og, ow = np.argsort(keys), np.argsort(gk)
+    assert np.array_equal(keys[og], gk[ow]) and np.array_equal(rows[og], g["q_rows"][ow])
+
+
+def test_fused_ssrl_matches_oracle():
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed = 256, 650, 4
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=300)
+    env = gf.BatchedEnv("TomatoWatering-v0", n, seed=seed)
+    env.set_trace(True)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **hp)
+    agent.enable_ssrl(c_prior=0.01, budget=4)
+    agent.rollout(250)
+    agent.rollout(T - 250)
+    agent.check()
+    sim = cgrid.Sim(cgrid.TOMATO, n, seed=seed, ssrl=True, c_prior=0.01, budget=4, **hp)
+    sim.rollout(T)
+    _cmp_stats(env, sim)
+    for i in (0, 17, n - 1):
+        _cmp_table(env, agent, sim, i, with_c=True)
+
+
+def test_random_policy_rollout_matches_oracle():
+    gf = _gf()
+    from oracle import cgrid
+    for env_id, kind in ENVS:
+        env = gf.BatchedEnv(env_id, 777, seed=21)
+        env.set_trace(True)
+        env.rollout_random(333)
+        sim = cgrid.Sim(kind, 777, seed=21)
+        sim.rollout_random(333)
+        _cmp_stats(env, sim)
+
+
+def test_sharding_does_not_change_any_trajectory():
+    """Global env ids key the streams: one object of 1024 environments equals
+    two objects of 512 with env_id0 = 0 / 512."""
+    gf = _gf()
+    hp = dict(lr=0.5, epsilon_anneal=300)
+    whole = gf.BatchedEnv("TomatoWatering-v0", 1024, seed=8)
+    whole.set_trace(True)
+    aw = gf.BatchedTabularQ(whole, gf.Q_PRIVATE, **hp)
+    aw.rollout(400)
+    hw = whole.stats()["trace_hash"].cpu().numpy()
+    parts = []
+    for k in range(2):
+        e = gf.BatchedEnv("TomatoWatering-v0", 512, seed=8, env_id0=512 * k)
+        e.set_trace(True)
+        a = gf.BatchedTabularQ(e, gf.Q_PRIVATE, **hp)
+        a.rollout(400)
+        parts.append(e.stats()["trace_hash"].cpu().numpy())
+    assert np.array_equal(hw, np.concatenate(parts))
+
+
+def test_table_full_and_replay_dry_are_reported():
+    gf = _gf()
+    env = gf.BatchedEnv("TomatoWatering-v0", 64, seed=1)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, capacity=8, epsilon_anneal=50)
+    agent.rollout(300)
+    with pytest.raises(gf.SgkError, match="ran out of slots"):
+        agent.check()
+    env = gf.BatchedEnv("BoatRace-v0", 2, seed=1)
+    env.set_replay_words(np.zeros((2, 10), np.uint32))
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE)
+    agent.rollout(50)
+    with pytest.raises(gf.SgkError, match="ran dry"):
+        agent.check()
+
+
+# ------------------------------------------------------------------ full size
+def test_full_size_boat_65536_envs_bit_exact():
+    """BASELINE config 2 at full width: 65,536 lock-step boat races, private Q,
+    1,000 lock-steps = 65.5M env-steps, every trajectory and every episode
+    metric equal to the oracle's; Q tables compared for a sample."""
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed = 65536, 1000, 0
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=100000)
+    env = gf.BatchedEnv("BoatRace-v0", n, seed=seed)
+    env.set_trace(True)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **hp)
+    agent.rollout(T)
+    agent.check()
+    sim = cgrid.Sim(cgrid.BOAT, n, seed=seed, **hp)
+    sim.rollout(T)
+    _cmp_stats(env, sim)
+    for i in (0, 12345, n - 1):
+        _cmp_table(env, agent, sim, i)
+    tot = env.totals()
+    ref = sim.env_stats()
+    assert tot["episodes"] == ref["episodes"].sum() == n * 10
+    assert tot["sum_return"] == ref["sum_return"].sum()       # integers: exact in any order
+    assert tot["sum_performance"] == ref["sum_perf"].sum()
+    # size-independent property: the trace-free fast kernel gives the same result
+    env2 = gf.BatchedEnv("BoatRace-v0", n, seed=seed)
+    agent2 = gf.BatchedTabularQ(env2, gf.Q_PRIVATE, **hp)
+    agent2.rollout(T)
+    assert torch.equal(env2.core(), env.core())
+    assert torch.equal(env2.stats()["sum_return"], env.stats()["sum_return"])
