@@ -137,6 +137,9 @@ int sgk_env_get_stats(const sgk_env *env, const sgk_env_stats *out, void *stream
  * totals[0..6] = episodes, sum_return, sum_performance, sum_margin_pos,
  * n_margin_pos, max_return, sum of running episode_return. */
 int sgk_env_totals_host(const sgk_env *env, double totals[7], void *stream);
+/* Same totals into device memory [7] without synchronising (the buffer that
+ * multi-GPU runs all-reduce at sync intervals). */
+int sgk_env_totals(const sgk_env *env, double *totals_out, void *stream);
 
 /* ------------------------------------------------------------- tabular Q --
  * Replaces TabularQAgent.__init__'s `Q = defaultdict(lambda: np.zeros(A))`

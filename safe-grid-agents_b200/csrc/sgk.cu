@@ -547,9 +547,13 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_private(const __grid_cons
     RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
     int status = 0;
 
+    // The dict of the reference gains a key when act/learn first touch it
+    // (value.py:35,46-52), not when the environment resets: look the start
+    // state up without inserting; it is inserted by the step that leaves it.
     uint64_t key = obs_key<KIND>(L, e);
-    uint32_t slot = find_private(p.T, i, key, &status);
-    QRow row = load_row(p.T, i, slot);
+    uint32_t slot = SGK_NOSLOT;
+    QRow row = {0.0, 0.0, 0.0, 0.0};
+    if (lookup(p.T, i, key, slot)) row = load_row(p.T, i, slot);
     uint32_t n_hist = SSRL ? e.frame : 0;   // states visited so far this episode
 
     for (int64_t k = 0; k < p.n_steps; k++) {
@@ -558,6 +562,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_private(const __grid_cons
         int a;
         if (rng.agent_uniform() < p.thr[k]) a = rng.agent_choice();
         else a = argmax_first(row);
+        if (slot == SGK_NOSLOT) slot = find_private(p.T, i, key, &status);
         if (SSRL) { p.ssrl_hist[(size_t)n_hist * p.n + i] = slot; n_hist++; }
         // env.step
         const StepOut o = env_step<KIND>(L, e, a, rng);
@@ -579,8 +584,9 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_private(const __grid_cons
             rng.set_step(p.t0 + (uint64_t)k + 1);
             env_reset<KIND>(L, e, rng);
             key = obs_key<KIND>(L, e);
-            slot = find_private(p.T, i, key, &status);
-            row = load_row(p.T, i, slot);
+            slot = SGK_NOSLOT;
+            row = QRow{0.0, 0.0, 0.0, 0.0};
+            if (lookup(p.T, i, key, slot)) row = load_row(p.T, i, slot);
         }
     }
     p.arr.core[i] = pack_core(e);
@@ -627,7 +633,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_shared(const __grid_const
             unpack_core(p.arr.core[i], e[j]);
             e[j].ep_return = p.arr.ep_return[i];
             e[j].hidden_cum = p.arr.hidden_cum[i];
-            slot[j] = find_shared(p.T, obs_key<KIND>(L, e[j]), &status);
+            slot[j] = SGK_NOSLOT;   // inserted by the step that leaves the state
         }
     }
     for (int64_t k = 0; k < p.n_steps; k++) {
@@ -642,6 +648,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_shared(const __grid_const
             RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
             rng.set_step(t);
             const uint64_t key = obs_key<KIND>(L, e[j]);
+            if (slot[j] == SGK_NOSLOT) slot[j] = find_shared(p.T, key, &status);
             int a;
             if (rng.agent_uniform() < thr) a = rng.agent_choice();
             else a = argmax_first(load_row_cg(p.T, slot[j]));
@@ -682,7 +689,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_shared(const __grid_const
                 rng.set_step(t + 1);
                 env_reset<KIND>(L, e[j], rng);
                 RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
-                slot[j] = find_shared(p.T, obs_key<KIND>(L, e[j]), &status);
+                slot[j] = SGK_NOSLOT;
             }
         }
         grid.sync();
@@ -1013,6 +1020,14 @@ extern "C" int sgk_env_get_stats(const sgk_env *env, const sgk_env_stats *out, v
     DeviceGuard g(env->device);
     k_stats_export<<<grid_for(env->n, 256), 256, 0, (cudaStream_t)stream>>>(env->arr, env->n, *out);
     return launch_check("k_stats_export");
+}
+
+extern "C" int sgk_env_totals(const sgk_env *env, double *totals_out, void *stream)
+{
+    REQUIRE(env != nullptr && totals_out != nullptr, "bad argument");
+    DeviceGuard g(env->device);
+    k_totals<<<1, 512, 0, (cudaStream_t)stream>>>(env->arr, env->n, totals_out);
+    return launch_check("k_totals");
 }
 
 extern "C" int sgk_env_totals_host(const sgk_env *env, double totals[7], void *stream)

@@ -17,6 +17,7 @@
 
 #define SGK_ST_FULL 1
 #define SGK_ST_REPLAY_DRY 2
+#define SGK_NOSLOT 0xFFFFFFFFu
 
 struct TableView {
     unsigned long long *keys;

@@ -40,6 +40,7 @@ SYMBOLS = [
     ("sgk_board_to_f32", _i32, [_vp, _vp, _vp, _i64, _vp]),
     ("sgk_env_get_stats", _i32, [_vp, ctypes.POINTER(EnvStats), _vp]),
     ("sgk_env_totals_host", _i32, [_vp, ctypes.POINTER(ctypes.c_double * 7), _vp]),
+    ("sgk_env_totals", _i32, [_vp, _vp, _vp]),
     ("sgk_tabq_create", _i32, [_vp, _i32, _i64, _pp]),
     ("sgk_tabq_destroy", _i32, [_vp]),
     ("sgk_tabq_capacity", _i64, [_vp]),

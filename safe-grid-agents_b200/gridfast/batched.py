@@ -137,6 +137,12 @@ class BatchedEnv:
                 "max_return", "running_return")
         return dict(zip(keys, list(buf)))
 
+    def totals_device(self, out=None):
+        """The same 7 totals as a cuda float64 tensor, no synchronisation."""
+        out = self._f64(7) if out is None else out
+        check(self.L.sgk_env_totals(self.h, _p(out), _stream()))
+        return out
+
     def core(self):
         out = torch.empty(self.n, dtype=torch.int64, device=self.device)
         check(self.L.sgk_env_get_core(self.h, _p(out), _stream()))
