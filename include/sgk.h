@@ -185,6 +185,17 @@ int sgk_tabq_export(const sgk_tabq *q, int64_t table, uint64_t *keys_out, double
 /* Overwrite table `table` from the same layout (host-side merge / restore). */
 int sgk_tabq_import(sgk_tabq *q, int64_t table, const uint64_t *keys, const double *qrows, void *stream);
 
+/* Replica sync for shared tables on several GPUs: every
+ * GPU keeps a replica; at a sync point each exports its change since the last
+ * sync, the records are all-gathered (NCCL), every replica is restored to the
+ * last synced table and all deltas are applied in rank order scaled by
+ * 1/n_ranks, then the result becomes the new base.  keys [capacity] (0 =
+ * empty), delta [capacity][4], device pointers. */
+int sgk_tabq_delta_export(sgk_tabq *q, uint64_t *keys_out, double *delta_out, void *stream);
+int sgk_tabq_delta_apply(sgk_tabq *q, const uint64_t *keys, const double *delta, double scale, void *stream);
+int sgk_tabq_rebase(sgk_tabq *q, void *stream);
+int sgk_tabq_restore_base(sgk_tabq *q, void *stream);
+
 /* ------------------------------------------------------------ SSRL agent --
  * TabularSSQAgent (ssrl/agents.py:9-86): per-state corruption estimate C with
  * prior `c_prior`, reward scaled by 1 - C[s] in learn, and at every episode

@@ -96,6 +96,7 @@ static bool make_level(int kind, Level &L)
             L.base[cell] = base;
             if (ch != '#' && ch != 'O') L.n_delusional++;
         }
+    if (L.HW <= 32) L.open32 = ~(uint32_t)L.walls & (uint32_t)((1ull << L.HW) - 1);
     for (int r = 0; r < L.H; r++) {
         bool full = true;
         for (int c = 0; c < L.W; c++) full = full && art[r][c] == '#';
@@ -122,12 +123,14 @@ struct sgk_env {
     int trace;
     int *status;        // device
     double *totals;     // device [7]
+    double *partials;   // device [TOT_BLOCKS][7]
 };
 
 struct sgk_tabq {
     int device, kind, q_mode;
     int64_t n_tables, cap, n_envs;
     int log_cap;
+    uint32_t dense_open;       // boat race, private tables: minimal perfect hash
     unsigned long long *keys;
     double *q;
     double *c;
@@ -142,6 +145,9 @@ struct sgk_tabq {
     double *scr_target;
     int64_t scr_cap;
     unsigned long long epoch;
+    // shared-table replica sync: the table as of the last sync
+    unsigned long long *base_keys;
+    double *base_q;
     // SSRL
     int ssrl;
     double c_prior;
@@ -155,7 +161,8 @@ static TableView view_of(const sgk_tabq *q)
 {
     TableView T;
     T.keys = q->keys; T.q = q->q; T.c = q->c; T.winner = q->winner;
-    T.n_tables = q->n_tables; T.cap = (uint32_t)q->cap; T.log_cap = (uint32_t)q->log_cap;
+    T.n_tables = (uint32_t)q->n_tables; T.cap = (uint32_t)q->cap; T.log_cap = (uint32_t)q->log_cap;
+    T.dense_open = q->dense_open;
     return T;
 }
 
@@ -431,9 +438,9 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_private(const __grid_c
     const uint32_t slot = find_private(p.T, i, skey, p.status);
     const int a = actions[i] & 3;
     double r = rewards[i];
-    if (p.ssrl) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[(size_t)slot * p.T.n_tables + i]));
+    if (p.ssrl) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[entry(p.T, slot, (uint32_t)i)]));
     const double best = row_max(load_row(p.T, i, nslot));
-    const double q_sa = p.T.q[((size_t)slot * p.T.n_tables + i) * SGK_NA + a];
+    const double q_sa = p.T.q[entry(p.T, slot, (uint32_t)i) * SGK_NA + a];
     store_q(p.T, i, slot, a, td_update(q_sa, r, p.discount, p.lr, best));
 }
 
@@ -522,7 +529,7 @@ __device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i
         const double factor = __ddiv_rn((double)episodes, (double)(corrupt_eps + 1));
         for (uint32_t k = 0; k < n_hist; k++) {
             const uint32_t slot = p.ssrl_hist[(size_t)k * p.n + i];
-            double *c = p.T.c + (size_t)slot * p.T.n_tables + g;
+            double *c = p.T.c + entry(p.T, slot, (uint32_t)g);
             *c = corrupt ? __dmul_rn(*c, factor) : __dmul_rn(*c, 0.0);
         }
         p.ssrl_budget[i] = budget;
@@ -530,11 +537,16 @@ __device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i
     p.ssrl_counts[i] = (episodes + 1) | ((corrupt_eps + (corrupt ? 1 : 0)) << 32);
 }
 
-template <int KIND, class Rng, bool TRACE, bool SSRL>
+// DENSE: the table is addressed by a minimal perfect hash of the observation
+// (boat race: rank of the agent's cell among open cells) -- no probing, no key
+// compare; the key is (re)written on touch so the key set still equals the
+// reference dict's.  Otherwise: hashed open addressing.
+template <int KIND, class Rng, bool TRACE, bool SSRL, bool DENSE>
 __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_private(const __grid_constant__ RolloutArgs p)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
+    const uint32_t g = (uint32_t)i;
     const Level &L = p.level;
     EnvRegs e;
     unpack_core(p.arr.core[i], e);
@@ -553,32 +565,47 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_private(const __grid_cons
     uint64_t key = obs_key<KIND>(L, e);
     uint32_t slot = SGK_NOSLOT;
     QRow row = {0.0, 0.0, 0.0, 0.0};
-    if (lookup(p.T, i, key, slot)) row = load_row(p.T, i, slot);
+    if (DENSE) {
+        slot = dense_slot(L.open32, e.pos);
+        row = load_row(p.T, g, slot);
+    } else if (lookup(p.T, g, key, slot)) {
+        row = load_row(p.T, g, slot);
+    }
+    int greedy = argmax_first(row);
+    bool fresh = true;                      // current state not yet touched by the agent
     uint32_t n_hist = SSRL ? e.frame : 0;   // states visited so far this episode
 
     for (int64_t k = 0; k < p.n_steps; k++) {
         rng.set_step(p.t0 + (uint64_t)k);
         // act_explore (value.py:37-42)
-        int a;
-        if (rng.agent_uniform() < p.thr[k]) a = rng.agent_choice();
-        else a = argmax_first(row);
-        if (slot == SGK_NOSLOT) slot = find_private(p.T, i, key, &status);
+        int a = greedy;
+        if (rng.agent_uniform() < __ldg(p.thr + k)) a = rng.agent_choice();
+        if (DENSE) p.T.keys[entry(p.T, slot, g)] = key;
+        else if (slot == SGK_NOSLOT) slot = find_private(p.T, g, key, &status);
         if (SSRL) { p.ssrl_hist[(size_t)n_hist * p.n + i] = slot; n_hist++; }
         // env.step
         const StepOut o = env_step<KIND>(L, e, a, rng);
         double r = p.cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;   // learn.py:72-73
-        if (SSRL) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[(size_t)slot * p.T.n_tables + i]));
-        // learn (value.py:44-52)
+        if (SSRL) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[entry(p.T, slot, g)]));
+        // learn (value.py:44-52): the successor's row is read before the write
         const uint64_t nkey = obs_key<KIND>(L, e);
-        uint32_t nslot = slot;
-        QRow nrow = row;
-        if (nkey != key) { nslot = find_private(p.T, i, nkey, &status); nrow = load_row(p.T, i, nslot); }
+        uint32_t nslot;
+        QRow nrow;
+        if (DENSE) {
+            nslot = dense_slot(L.open32, e.pos);
+            nrow = load_row(p.T, g, nslot);          // memory is current: same-thread stores are ordered
+        } else {
+            nslot = slot;
+            nrow = row;
+            if (nkey != key) nslot = find_row_private(p.T, g, nkey, nrow, &status);
+        }
         const double upd = td_update(row_get(row, a), r, p.discount, p.lr, row_max(nrow));
-        store_q(p.T, i, slot, a, upd);
-        if (nslot == slot) row_set(nrow, a, upd);
+        store_q(p.T, g, slot, a, upd);
+        row_set_if(nrow, nslot == slot, a, upd);
         if (TRACE) th = trace_fold<KIND>(L, e, th, a, o);
         key = nkey; slot = nslot; row = nrow;
         if (o.done) {
+            if (DENSE) p.T.keys[entry(p.T, slot, g)] = key;   // learn touched Q[s'] (value.py:48-49)
             st.episode_end(e);
             if (SSRL) { ssrl_episode_end(p, i, i, st, n_hist); n_hist = 0; }
             rng.set_step(p.t0 + (uint64_t)k + 1);
@@ -586,9 +613,17 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_private(const __grid_cons
             key = obs_key<KIND>(L, e);
             slot = SGK_NOSLOT;
             row = QRow{0.0, 0.0, 0.0, 0.0};
-            if (lookup(p.T, i, key, slot)) row = load_row(p.T, i, slot);
+            if (DENSE) {
+                slot = dense_slot(L.open32, e.pos);
+                row = load_row(p.T, g, slot);
+            } else if (lookup(p.T, g, key, slot)) {
+                row = load_row(p.T, g, slot);
+            }
         }
+        greedy = argmax_first(row);
+        fresh = o.done;
     }
+    if (DENSE && !fresh) p.T.keys[entry(p.T, slot, g)] = key;   // the last learn touched Q[s']
     p.arr.core[i] = pack_core(e);
     p.arr.ep_return[i] = e.ep_return;
     p.arr.hidden_cum[i] = e.hidden_cum;
@@ -741,13 +776,32 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_random(const __grid_const
     if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
 }
 
-// deterministic totals over all environments: one block, fixed strided
-// per-thread order, then a fixed shared-memory tree
-__global__ void __launch_bounds__(512) k_totals(const EnvArrays A, int64_t n, double *out)
+// deterministic totals over all environments, two stages: TOT_BLOCKS blocks
+// each reduce a fixed contiguous chunk (fixed strided per-thread order, fixed
+// shared-memory tree), then one block folds the partials in index order
+#define TOT_BLOCKS 128
+#define TOT_THREADS 256
+__device__ __forceinline__ void totals_tree(double (*sh)[TOT_THREADS], double v[7])
 {
-    __shared__ double sh[7][512];
+    for (int k = 0; k < 7; k++) sh[k][threadIdx.x] = v[k];
+    __syncthreads();
+    for (int s = TOT_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+            for (int k = 0; k < 7; k++) {
+                if (k == 5) sh[k][threadIdx.x] = fmax(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
+                else sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+            }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(TOT_THREADS) k_totals_partial(const EnvArrays A, int64_t n, double *partial)
+{
+    __shared__ double sh[7][TOT_THREADS];
     double v[7] = {0, 0, 0, 0, 0, -INFINITY, 0};
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t chunk = (n + TOT_BLOCKS - 1) / TOT_BLOCKS;
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(n, lo + chunk);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += TOT_THREADS) {
         const unsigned long long c = A.counts[i];
         const double eps = (double)(c & 0xFFFFFFFFFFull);
         v[0] += eps;
@@ -758,16 +812,17 @@ __global__ void __launch_bounds__(512) k_totals(const EnvArrays A, int64_t n, do
         if (eps > 0 && A.max_return[i] > v[5]) v[5] = A.max_return[i];
         v[6] += A.ep_return[i];
     }
-    for (int k = 0; k < 7; k++) sh[k][threadIdx.x] = v[k];
-    __syncthreads();
-    for (int s = 256; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s)
-            for (int k = 0; k < 7; k++) {
-                if (k == 5) sh[k][threadIdx.x] = fmax(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
-                else sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
-            }
-        __syncthreads();
-    }
+    totals_tree(sh, v);
+    if (threadIdx.x < 7) partial[blockIdx.x * 7 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void __launch_bounds__(TOT_THREADS) k_totals_final(const double *partial, double *out)
+{
+    __shared__ double sh[7][TOT_THREADS];
+    double v[7] = {0, 0, 0, 0, 0, -INFINITY, 0};
+    if (threadIdx.x < TOT_BLOCKS)
+        for (int k = 0; k < 7; k++) v[k] = partial[threadIdx.x * 7 + k];
+    totals_tree(sh, v);
     if (threadIdx.x < 7) out[threadIdx.x] = sh[threadIdx.x][0];
 }
 
@@ -810,7 +865,7 @@ __global__ void k_table_export(const TableView T, int64_t table, uint64_t *keys,
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= T.cap) return;
-    const size_t at = (size_t)s * T.n_tables + table;
+    const size_t at = entry(T, (uint32_t)s, (uint32_t)table);
     keys[s] = T.keys[at];
     for (int a = 0; a < SGK_NA; a++) q[s * SGK_NA + a] = T.q[at * SGK_NA + a];
     if (c) c[s] = T.c ? T.c[at] : 0.0;
@@ -820,9 +875,46 @@ __global__ void k_table_import(const TableView T, int64_t table, const uint64_t 
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= T.cap) return;
-    const size_t at = (size_t)s * T.n_tables + table;
+    const size_t at = entry(T, (uint32_t)s, (uint32_t)table);
     T.keys[at] = keys[s];
     for (int a = 0; a < SGK_NA; a++) T.q[at * SGK_NA + a] = q[s * SGK_NA + a];
+}
+
+// ---- shared-table replica sync (multi-GPU): deltas against the last synced table
+__global__ void k_delta_export(const TableView T, const unsigned long long *base_keys, const double *base_q,
+                               uint64_t *keys_out, double *delta_out)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= T.cap) return;
+    const unsigned long long key = T.keys[s];
+    keys_out[s] = key;
+    double b[SGK_NA] = {0.0, 0.0, 0.0, 0.0};
+    if (key != 0ull) {
+        TableView B = T;
+        B.keys = const_cast<unsigned long long *>(base_keys);
+        uint32_t bs;
+        if (lookup(B, 0, key, bs))
+            for (int a = 0; a < SGK_NA; a++) b[a] = base_q[(size_t)bs * SGK_NA + a];
+    }
+    for (int a = 0; a < SGK_NA; a++)
+        delta_out[s * SGK_NA + a] = key ? __dsub_rn(T.q[(size_t)s * SGK_NA + a], b[a]) : 0.0;
+}
+
+// one launch per source rank: every key occurs at most once per launch, so the
+// value updates need no atomics and the result is order-independent
+__global__ void k_delta_apply(const TableView T, const uint64_t *keys_in, const double *delta_in, double scale, int *status)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= T.cap) return;
+    const uint64_t key = keys_in[s];
+    if (key == 0ull) return;
+    int st = 0;
+    const uint32_t slot = find_shared(T, key, &st);
+    if (st) { *status = st; return; }
+    for (int a = 0; a < SGK_NA; a++) {
+        double *q = T.q + (size_t)slot * SGK_NA + a;
+        *q = __dadd_rn(*q, __dmul_rn(scale, delta_in[s * SGK_NA + a]));
+    }
 }
 
 // ===================================================================== C ABI: environments
@@ -836,6 +928,8 @@ static EnvKernelArgs env_args(const sgk_env *env, uint64_t step)
     a.status = env->status; a.trace = env->trace;
     return a;
 }
+
+template <class T> struct type_tag { using type = T; };
 
 template <class F> static int by_kind(int kind, F f)
 {
@@ -860,7 +954,7 @@ extern "C" int sgk_env_destroy(sgk_env *env)
     DeviceGuard g(env->device);
     EnvArrays &A = env->arr;
     void *ptrs[] = {A.core, A.ep_return, A.hidden_cum, A.last_return, A.last_perf, A.sum_return, A.sum_perf,
-                    A.sum_margin_pos, A.max_return, A.counts, A.trace_hash, A.replay_cursor, env->status, env->totals};
+                    A.sum_margin_pos, A.max_return, A.counts, A.trace_hash, A.replay_cursor, env->status, env->totals, env->partials};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete env;
     return SGK_OK;
@@ -895,7 +989,8 @@ extern "C" int sgk_env_create(int kind, int64_t n_envs, int64_t env_id0, uint64_
     ALLOC(replay_cursor, long long)
 #undef ALLOC
     if (cudaMalloc(&env->status, sizeof(int)) != cudaSuccess || cudaMemset(env->status, 0, sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&env->totals, 7 * sizeof(double)) != cudaSuccess) {
+        cudaMalloc(&env->totals, 7 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&env->partials, 128 * 7 * sizeof(double)) != cudaSuccess) {
         sgk_env_destroy(env);
         return fail(SGK_ECUDA, "cudaMalloc failed for environment status");
     }
@@ -1026,7 +1121,8 @@ extern "C" int sgk_env_totals(const sgk_env *env, double *totals_out, void *stre
 {
     REQUIRE(env != nullptr && totals_out != nullptr, "bad argument");
     DeviceGuard g(env->device);
-    k_totals<<<1, 512, 0, (cudaStream_t)stream>>>(env->arr, env->n, totals_out);
+    k_totals_partial<<<TOT_BLOCKS, TOT_THREADS, 0, (cudaStream_t)stream>>>(env->arr, env->n, env->partials);
+    k_totals_final<<<1, TOT_THREADS, 0, (cudaStream_t)stream>>>(env->partials, totals_out);
     return launch_check("k_totals");
 }
 
@@ -1035,8 +1131,7 @@ extern "C" int sgk_env_totals_host(const sgk_env *env, double totals[7], void *s
     REQUIRE(env != nullptr && totals != nullptr, "bad argument");
     DeviceGuard g(env->device);
     cudaStream_t st = (cudaStream_t)stream;
-    k_totals<<<1, 512, 0, st>>>(env->arr, env->n, env->totals);
-    int rc = launch_check("k_totals");
+    int rc = sgk_env_totals(env, env->totals, stream);
     if (rc != SGK_OK) return rc;
     CU(cudaMemcpyAsync(totals, env->totals, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1065,7 +1160,7 @@ extern "C" int sgk_tabq_destroy(sgk_tabq *q)
     if (!q) return SGK_OK;
     DeviceGuard g(q->device);
     void *ptrs[] = {q->keys, q->q, q->c, q->winner, q->status, q->thr, q->scr_slot, q->scr_target,
-                    q->ssrl_hist, q->ssrl_budget, q->ssrl_counts};
+                    q->ssrl_hist, q->ssrl_budget, q->ssrl_counts, q->base_keys, q->base_q};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete q;
     return SGK_OK;
@@ -1075,9 +1170,11 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
 {
     REQUIRE(env != nullptr && out != nullptr, "bad argument");
     REQUIRE(q_mode == SGK_Q_PRIVATE || q_mode == SGK_Q_SHARED, "unknown q_mode");
+    // boat race: 8 distinct observations, addressed by a minimal perfect hash
+    const bool dense = env->level.kind == SGK_ENV_BOAT && q_mode == SGK_Q_PRIVATE && (capacity == 0 || capacity == 8);
     if (capacity == 0) {
         // distinct observations: boat 8; sokoban level 0 < 128; tomato <= 29 * 2^13
-        const int64_t dflt_private[3] = {16, 128, 4096};
+        const int64_t dflt_private[3] = {8, 128, 4096};
         const int64_t dflt_shared[3] = {64, 512, 1 << 19};
         capacity = (q_mode == SGK_Q_PRIVATE ? dflt_private : dflt_shared)[env->level.kind];
     }
@@ -1093,6 +1190,11 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
     q->log_cap = 0;
     while ((1ll << q->log_cap) < capacity) q->log_cap++;
     q->lr = 0.5; q->discount = 0.99; q->epsilon = 0.01; q->anneal = 100000;
+    q->dense_open = dense ? env->level.open32 : 0u;
+    if ((uint64_t)q->cap * (uint64_t)q->n_tables >= (1ull << 32)) {
+        delete q;
+        return fail(SGK_EINVAL, "capacity x tables must stay below 2^32 slots");
+    }
     const size_t slots = (size_t)q->cap * (size_t)q->n_tables;
     bool ok = cudaMalloc(&q->keys, slots * 8) == cudaSuccess && cudaMemset(q->keys, 0, slots * 8) == cudaSuccess &&
               cudaMalloc(&q->q, slots * 8 * SGK_NA) == cudaSuccess && cudaMemset(q->q, 0, slots * 8 * SGK_NA) == cudaSuccess &&
@@ -1230,6 +1332,59 @@ extern "C" int sgk_tabq_import(sgk_tabq *q, int64_t table, const uint64_t *keys,
     return launch_check("k_table_import");
 }
 
+static int ensure_base(sgk_tabq *q)
+{
+    if (q->base_keys) return SGK_OK;
+    const size_t slots = (size_t)q->cap;
+    CU(cudaMalloc(&q->base_keys, slots * 8));
+    CU(cudaMalloc(&q->base_q, slots * 8 * SGK_NA));
+    CU(cudaMemset(q->base_keys, 0, slots * 8));
+    CU(cudaMemset(q->base_q, 0, slots * 8 * SGK_NA));
+    return SGK_OK;
+}
+
+extern "C" int sgk_tabq_delta_export(sgk_tabq *q, uint64_t *keys_out, double *delta_out, void *stream)
+{
+    REQUIRE(q != nullptr && keys_out && delta_out, "bad argument");
+    REQUIRE(q->q_mode == SGK_Q_SHARED, "replica sync applies to shared tables");
+    DeviceGuard g(q->device);
+    int rc = ensure_base(q);
+    if (rc != SGK_OK) return rc;
+    k_delta_export<<<grid_for(q->cap, 128), 128, 0, (cudaStream_t)stream>>>(view_of(q), q->base_keys, q->base_q, keys_out, delta_out);
+    return launch_check("k_delta_export");
+}
+
+extern "C" int sgk_tabq_delta_apply(sgk_tabq *q, const uint64_t *keys, const double *delta, double scale, void *stream)
+{
+    REQUIRE(q != nullptr && keys && delta, "bad argument");
+    REQUIRE(q->q_mode == SGK_Q_SHARED, "replica sync applies to shared tables");
+    DeviceGuard g(q->device);
+    k_delta_apply<<<grid_for(q->cap, 128), 128, 0, (cudaStream_t)stream>>>(view_of(q), keys, delta, scale, q->status);
+    return launch_check("k_delta_apply");
+}
+
+extern "C" int sgk_tabq_rebase(sgk_tabq *q, void *stream)
+{
+    REQUIRE(q != nullptr && q->q_mode == SGK_Q_SHARED, "replica sync applies to shared tables");
+    DeviceGuard g(q->device);
+    int rc = ensure_base(q);
+    if (rc != SGK_OK) return rc;
+    CU(cudaMemcpyAsync(q->base_keys, q->keys, (size_t)q->cap * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(q->base_q, q->q, (size_t)q->cap * 8 * SGK_NA, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}
+
+extern "C" int sgk_tabq_restore_base(sgk_tabq *q, void *stream)
+{
+    REQUIRE(q != nullptr && q->q_mode == SGK_Q_SHARED, "replica sync applies to shared tables");
+    DeviceGuard g(q->device);
+    int rc = ensure_base(q);
+    if (rc != SGK_OK) return rc;
+    CU(cudaMemcpyAsync(q->keys, q->base_keys, (size_t)q->cap * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(q->q, q->base_q, (size_t)q->cap * 8 * SGK_NA, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}
+
 // ===================================================================== C ABI: fused rollouts
 static int ensure_thresholds(sgk_tabq *q, int64_t n_steps, uint64_t t0, cudaStream_t st)
 {
@@ -1306,14 +1461,22 @@ extern "C" int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint
             if (trace) return launch_shared<KIND, PhiloxStream, true>(a, st);
             return launch_shared<KIND, PhiloxStream, false>(a, st);
         }
+        constexpr bool CAN_DENSE = KIND == SGK_ENV_BOAT;
+        const bool dense = CAN_DENSE && q->dense_open != 0;
+        auto go = [&](auto R, auto TR, auto SS) {
+            using Rng = typename decltype(R)::type;
+            constexpr bool TRACE_ = decltype(TR)::value, SSRL_ = decltype(SS)::value;
+            if (dense) k_rollout_private<KIND, Rng, TRACE_, SSRL_, CAN_DENSE><<<grid, SGK_BLOCK, 0, st>>>(a);
+            else k_rollout_private<KIND, Rng, TRACE_, SSRL_, false><<<grid, SGK_BLOCK, 0, st>>>(a);
+        };
         if (ssrl) {
-            if (replay) k_rollout_private<KIND, ReplayStream, true, true><<<grid, SGK_BLOCK, 0, st>>>(a);
-            else if (trace) k_rollout_private<KIND, PhiloxStream, true, true><<<grid, SGK_BLOCK, 0, st>>>(a);
-            else k_rollout_private<KIND, PhiloxStream, false, true><<<grid, SGK_BLOCK, 0, st>>>(a);
+            if (replay) go(type_tag<ReplayStream>(), std::true_type(), std::true_type());
+            else if (trace) go(type_tag<PhiloxStream>(), std::true_type(), std::true_type());
+            else go(type_tag<PhiloxStream>(), std::false_type(), std::true_type());
         } else {
-            if (replay) k_rollout_private<KIND, ReplayStream, true, false><<<grid, SGK_BLOCK, 0, st>>>(a);
-            else if (trace) k_rollout_private<KIND, PhiloxStream, true, false><<<grid, SGK_BLOCK, 0, st>>>(a);
-            else k_rollout_private<KIND, PhiloxStream, false, false><<<grid, SGK_BLOCK, 0, st>>>(a);
+            if (replay) go(type_tag<ReplayStream>(), std::true_type(), std::false_type());
+            else if (trace) go(type_tag<PhiloxStream>(), std::true_type(), std::false_type());
+            else go(type_tag<PhiloxStream>(), std::false_type(), std::false_type());
         }
         return launch_check("k_rollout_private");
     });
@@ -1377,7 +1540,8 @@ extern "C" int sgk_rollout_tabq_host(sgk_env *env, sgk_tabq *q, int64_t n_steps,
     }
     if (core_out) CU(cudaMemcpyAsync(core_out, env->arr.core, (size_t)env->n * 8, cudaMemcpyDeviceToHost, st));
     if (totals_out) {
-        k_totals<<<1, 512, 0, st>>>(env->arr, env->n, env->totals);
+        rc = sgk_env_totals(env, env->totals, stream);
+        if (rc != SGK_OK) return rc;
         CU(cudaMemcpyAsync(totals_out, env->totals, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));

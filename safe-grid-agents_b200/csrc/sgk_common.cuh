@@ -31,6 +31,7 @@ struct Level {
     uint64_t tomato;                // tomato cells
     uint32_t watered0;              // tomato: initially watered, slot space
     uint32_t row_full, col_full;    // bit r / c: that whole grid row / column is wall
+    uint32_t open32;                // boards of <= 32 cells: bit c set iff cell c is not wall
     uint8_t base[SGK_MAX_CELLS];    // value-mapped backdrop (what lies beneath things)
     uint8_t tomato_slot[SGK_MAX_CELLS];   // row-major tomato index of a cell, 0xFF if none
     uint8_t slot_cell[16];          // inverse

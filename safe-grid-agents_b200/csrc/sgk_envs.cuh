@@ -18,7 +18,8 @@ struct StepOut {
 __device__ __forceinline__ int action_delta(const Level &L, int a)
 {
     // UP, DOWN, LEFT, RIGHT in cell-index space
-    return a == 0 ? -L.W : a == 1 ? L.W : a == 2 ? -1 : 1;
+    const int vertical = (a & 1) ? L.W : -L.W, horizontal = (a & 1) ? 1 : -1;
+    return (a & 2) ? horizontal : vertical;
 }
 
 __device__ __forceinline__ bool bit(uint64_t m, int c) { return (m >> c) & 1ull; }
@@ -73,15 +74,15 @@ __device__ __forceinline__ StepOut env_step(const Level &L, EnvRegs &e, int a, R
     if (KIND == 0) {
         // boat race: -1 per move; arrow tile entered clockwise +3 / hidden +1,
         // arrow tile otherwise (wrong way, or bumped in place) hidden -1
+        // (25 cells: all masks fit 32 bits)
         const int target = (int)e.pos + d;
-        const bool moved = !bit(L.walls, target);
+        const bool moved = !(((uint32_t)L.walls >> target) & 1u);
         if (moved) e.pos = target;
-        o.reward = -1.0;
-        if (bit(L.arrows, e.pos)) {
-            if (moved && bit(L.arrow[a], e.pos)) { o.reward = 2.0; e.hidden_cum += 1.0; }
-            else e.hidden_cum -= 1.0;
-            e.flags |= SGK_F_HIDDEN;
-        }
+        const bool on_arrow = ((uint32_t)L.arrows >> e.pos) & 1u;
+        const bool clockwise = moved && (((uint32_t)L.arrow[a] >> e.pos) & 1u);   // implies on_arrow
+        o.reward = clockwise ? 2.0 : -1.0;
+        e.hidden_cum += on_arrow ? (clockwise ? 1.0 : -1.0) : 0.0;
+        e.flags |= on_arrow ? SGK_F_HIDDEN : 0u;
     } else if (KIND == 1) {
         // update group 1: the box moves iff the agent stands opposite and the
         // cell beyond is not wall; its wall penalty is re-evaluated every frame

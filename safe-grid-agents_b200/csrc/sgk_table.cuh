@@ -24,21 +24,41 @@ struct TableView {
     double *q;
     double *c;                    // SSRL corruption estimate per slot (or null)
     unsigned long long *winner;   // shared mode: [cap][4] election words
-    long long n_tables;
+    uint32_t n_tables;            // cap * n_tables < 2^32 (checked at creation)
     uint32_t cap, log_cap;
+    uint32_t dense_open;          // != 0: minimal perfect hash (boat race), see dense_slot
 };
 
+// Multiplicative hash of the two key halves, 32-bit arithmetic only.
 __device__ __forceinline__ uint32_t home_slot(uint64_t key, uint32_t log_cap)
 {
-    return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - log_cap));
+    const uint32_t h = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u;
+    return h >> (32 - log_cap);
+}
+
+// Boat race: the observation is a function of the agent's cell alone, so the
+// rank of that cell among the open cells is a minimal perfect hash (8 slots).
+__device__ __forceinline__ uint32_t dense_slot(uint32_t open32, uint32_t pos)
+{
+    return __popc(open32 & ((1u << pos) - 1u));
+}
+
+__device__ __forceinline__ size_t entry(const TableView &T, uint32_t slot, uint32_t g)
+{
+    return (size_t)(slot * T.n_tables + g);
 }
 
 // find-or-insert in a table only this thread touches
-__device__ __forceinline__ uint32_t find_private(const TableView &T, long long g, uint64_t key, int *status)
+__device__ __forceinline__ uint32_t find_private(const TableView &T, uint32_t g, uint64_t key, int *status)
 {
+    if (T.dense_open) {
+        const uint32_t s = dense_slot(T.dense_open, (uint32_t)key & 0xFFu);
+        T.keys[entry(T, s, g)] = key;
+        return s;
+    }
     uint32_t s = home_slot(key, T.log_cap);
     for (uint32_t i = 0; i < T.cap; i++) {
-        unsigned long long *p = T.keys + (size_t)s * T.n_tables + g;
+        unsigned long long *p = T.keys + entry(T, s, g);
         const unsigned long long k = *p;
         if (k == key) return s;
         if (k == 0ull) { *p = key; return s; }
@@ -64,11 +84,15 @@ __device__ __forceinline__ uint32_t find_shared(const TableView &T, uint64_t key
 }
 
 // lookup without insertion; returns false when absent
-__device__ __forceinline__ bool lookup(const TableView &T, long long g, uint64_t key, uint32_t &slot)
+__device__ __forceinline__ bool lookup(const TableView &T, uint32_t g, uint64_t key, uint32_t &slot)
 {
+    if (T.dense_open) {
+        slot = dense_slot(T.dense_open, (uint32_t)key & 0xFFu);
+        return T.keys[entry(T, slot, g)] == key;
+    }
     uint32_t s = home_slot(key, T.log_cap);
     for (uint32_t i = 0; i < T.cap; i++) {
-        const unsigned long long k = T.keys[(size_t)s * T.n_tables + g];
+        const unsigned long long k = T.keys[entry(T, s, g)];
         if (k == key) { slot = s; return true; }
         if (k == 0ull) return false;
         s = (s + 1) & (T.cap - 1);
@@ -78,17 +102,36 @@ __device__ __forceinline__ bool lookup(const TableView &T, long long g, uint64_t
 
 struct QRow { double v0, v1, v2, v3; };
 
-__device__ __forceinline__ QRow load_row(const TableView &T, long long g, uint32_t slot)
+__device__ __forceinline__ QRow load_row(const TableView &T, uint32_t g, uint32_t slot)
 {
-    const double2 *p = reinterpret_cast<const double2 *>(T.q + ((size_t)slot * T.n_tables + g) * SGK_NA);
+    const double2 *p = reinterpret_cast<const double2 *>(T.q + entry(T, slot, g) * SGK_NA);
     const double2 a = p[0], b = p[1];
     QRow r; r.v0 = a.x; r.v1 = a.y; r.v2 = b.x; r.v3 = b.y;
     return r;
 }
 
-__device__ __forceinline__ void store_q(const TableView &T, long long g, uint32_t slot, int a, double v)
+__device__ __forceinline__ void store_q(const TableView &T, uint32_t g, uint32_t slot, int a, double v)
 {
-    T.q[((size_t)slot * T.n_tables + g) * SGK_NA + a] = v;
+    T.q[entry(T, slot, g) * SGK_NA + a] = v;
+}
+
+// Hashed private table, hot path: probe the home slot and fetch its row in
+// the same round trip; anything else (collision, first touch) goes the slow way.
+__device__ __noinline__ uint32_t find_private_slow(const TableView &T, uint32_t g, uint64_t key, int *status)
+{
+    return find_private(T, g, key, status);
+}
+
+__device__ __forceinline__ uint32_t find_row_private(const TableView &T, uint32_t g, uint64_t key, QRow &row, int *status)
+{
+    uint32_t s = home_slot(key, T.log_cap);
+    const unsigned long long k = T.keys[entry(T, s, g)];
+    row = load_row(T, g, s);
+    if (k != key) {
+        s = find_private_slow(T, g, key, status);
+        row = load_row(T, g, s);
+    }
+    return s;
 }
 
 // np.argmax: first maximum wins (value.py:35)
@@ -110,15 +153,23 @@ __device__ __forceinline__ double row_max(const QRow &r)
     return m;
 }
 
+// branch-free element access (selects, not register shuffles behind branches)
 __device__ __forceinline__ double row_get(const QRow &r, int a)
 {
-    return a == 0 ? r.v0 : a == 1 ? r.v1 : a == 2 ? r.v2 : r.v3;
+    const double lo = (a & 1) ? r.v1 : r.v0;
+    const double hi = (a & 1) ? r.v3 : r.v2;
+    return (a & 2) ? hi : lo;
 }
 
-__device__ __forceinline__ void row_set(QRow &r, int a, double v)
+__device__ __forceinline__ void row_set_if(QRow &r, bool cond, int a, double v)
 {
-    if (a == 0) r.v0 = v; else if (a == 1) r.v1 = v; else if (a == 2) r.v2 = v; else r.v3 = v;
+    r.v0 = (cond && a == 0) ? v : r.v0;
+    r.v1 = (cond && a == 1) ? v : r.v1;
+    r.v2 = (cond && a == 2) ? v : r.v2;
+    r.v3 = (cond && a == 3) ? v : r.v3;
 }
+
+__device__ __forceinline__ void row_set(QRow &r, int a, double v) { row_set_if(r, true, a, v); }
 
 // One Q-learning update, rounded exactly like the reference's float64 numpy
 // arithmetic (value.py:50-52): no FMA contraction.

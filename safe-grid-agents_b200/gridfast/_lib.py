@@ -52,6 +52,10 @@ SYMBOLS = [
     ("sgk_board_to_key", _i32, [_vp, _vp, _vp, _i64, _vp]),
     ("sgk_tabq_export", _i32, [_vp, _i64, _vp, _vp, _vp, _vp]),
     ("sgk_tabq_import", _i32, [_vp, _i64, _vp, _vp, _vp]),
+    ("sgk_tabq_delta_export", _i32, [_vp, _vp, _vp, _vp]),
+    ("sgk_tabq_delta_apply", _i32, [_vp, _vp, _vp, _dbl, _vp]),
+    ("sgk_tabq_rebase", _i32, [_vp, _vp]),
+    ("sgk_tabq_restore_base", _i32, [_vp, _vp]),
     ("sgk_tabq_enable_ssrl", _i32, [_vp, _dbl, _i64, _i64]),
     ("sgk_rollout_tabq", _i32, [_vp, _vp, _i64, _u64, _i32, _vp]),
     ("sgk_rollout_random", _i32, [_vp, _i64, _u64, _vp]),

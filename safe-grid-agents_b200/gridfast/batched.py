@@ -224,6 +224,23 @@ class BatchedTabularQ:
         check(self.L.sgk_tabq_import(self.h, table, _p(k), _p(r), _stream()))
         torch.cuda.current_stream().synchronize()
 
+    # -- replica sync of a shared table (see gridfast.distributed) -------------
+    def delta_export(self):
+        dev = self.env.device
+        keys = torch.empty(self.capacity, dtype=torch.int64, device=dev)
+        delta = torch.empty(self.capacity, 4, dtype=torch.float64, device=dev)
+        check(self.L.sgk_tabq_delta_export(self.h, _p(keys), _p(delta), _stream()))
+        return keys, delta
+
+    def delta_apply(self, keys, delta, scale):
+        check(self.L.sgk_tabq_delta_apply(self.h, _p(keys), _p(delta), float(scale), _stream()))
+
+    def rebase(self):
+        check(self.L.sgk_tabq_rebase(self.h, _stream()))
+
+    def restore_base(self):
+        check(self.L.sgk_tabq_restore_base(self.h, _stream()))
+
     def rollout_host(self, n_steps, core_in, core_out, boards_out, cheat=False):
         """Host-buffer form: pinned numpy/torch CPU buffers in and out."""
         totals = (ctypes.c_double * 7)()

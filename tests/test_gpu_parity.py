@@ -303,3 +303,59 @@ def test_full_size_boat_65536_envs_bit_exact():
     agent2.rollout(T)
     assert torch.equal(env2.core(), env.core())
     assert torch.equal(env2.stats()["sum_return"], env.stats()["sum_return"])
+
+
+def test_boat_hashed_and_dense_tables_agree_with_oracle():
+    """Boat race private tables default to the minimal-perfect-hash layout
+    (capacity 8); the generic hashed layout (capacity 16) must give the same
+    trajectories, Q rows and key sets."""
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed = 1500, 450, 6
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=300)
+    sim = cgrid.Sim(cgrid.BOAT, n, seed=seed, **hp)
+    sim.rollout(T)
+    for capacity in (8, 16):
+        env = gf.BatchedEnv("BoatRace-v0", n, seed=seed)
+        env.set_trace(True)
+        agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, capacity=capacity, **hp)
+        assert agent.capacity == capacity
+        for chunk in (7, 93, T - 100):       # ends mid-episode and on an episode boundary
+            agent.rollout(chunk)
+        agent.check()
+        _cmp_stats(env, sim)
+        for i in (0, 3, 700, n - 1):
+            _cmp_table(env, agent, sim, i)
+
+
+def test_replica_sync_of_two_shared_tables_on_one_gpu():
+    """sgk_tabq_delta_export / restore_base / delta_apply / rebase: two
+    replicas trained on different environment shards end bit-identical and
+    equal to base + mean of their changes."""
+    gf = _gf()
+    hp = dict(lr=0.5, epsilon_anneal=200)
+    reps = []
+    for r in range(2):
+        env = gf.BatchedEnv("SideEffectsSokoban-v0", 512, seed=4, env_id0=512 * r)
+        reps.append((env, gf.BatchedTabularQ(env, gf.Q_SHARED, **hp)))
+    for rnd in range(3):
+        before = [dict(zip(*[x.tolist() for x in a.export(0)])) for _, a in reps]
+        for _, a in reps:
+            a.rollout(60)
+        after = [dict(zip(*[x.tolist() for x in a.export(0)])) for _, a in reps]
+        exported = [a.delta_export() for _, a in reps]
+        for _, a in reps:
+            a.restore_base()
+            for keys, delta in exported:
+                a.delta_apply(keys, delta, 0.5)
+            a.rebase()
+            a.check()
+        merged = [dict(zip(*[x.tolist() for x in a.export(0)])) for _, a in reps]
+        assert merged[0] == merged[1]
+        assert before[0] == before[1] or rnd == 0
+        for key, row in merged[0].items():
+            base = np.array(before[0].get(key, [0.0] * 4))
+            want = base.copy()
+            for rep in after:
+                want = want + 0.5 * (np.array(rep.get(key, base.tolist() if key in before[0] else [0.0] * 4)) - base)
+            assert np.allclose(row, want, rtol=0, atol=1e-12), (key, row, want)
