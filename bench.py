@@ -202,7 +202,7 @@ def run_ours(args):
 
     env = gridfast.BatchedEnv(ENV_ID, n, seed=0, env_id0=rank * n, device=local)
     agent = gridfast.BatchedTabularQ(env, gridfast.Q_PRIVATE, **HP)
-    totals = torch.zeros(7, dtype=torch.float64, device=dev)
+    totals = torch.zeros(9, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # 2x the 126 MB L2
 
     def barrier():
@@ -267,7 +267,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * T * K / float(t[0])
     h2d = n * 8
-    d2h = n * env.hw + n * 8 + 7 * 8
+    d2h = n * env.hw + n * 8 + 9 * 8
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -127,6 +127,8 @@ typedef struct sgk_env_stats {
     double *sum_performance;
     double *sum_margin_pos;      /* sum of (return - performance) where > 0 */
     double *max_return;
+    double *max_performance;
+    double *max_margin;          /* max of (return - performance) */
     int64_t *episodes;
     int64_t *n_margin_pos;
     uint64_t *trace_hash;        /* running hash of (action, board, reward, hidden, done) */
@@ -134,11 +136,16 @@ typedef struct sgk_env_stats {
 int sgk_env_get_stats(const sgk_env *env, const sgk_env_stats *out, void *stream);
 
 /* Deterministic totals over all copies (host output, synchronises):
- * totals[0..6] = episodes, sum_return, sum_performance, sum_margin_pos,
- * n_margin_pos, max_return, sum of running episode_return. */
-int sgk_env_totals_host(const sgk_env *env, double totals[7], void *stream);
-/* Same totals into device memory [7] without synchronising (the buffer that
- * multi-GPU runs all-reduce at sync intervals). */
+ * totals[0..8] = episodes, sum_return, sum_performance, sum_margin_pos,
+ * n_margin_pos, max_return, sum of running episode_return, max_performance,
+ * max_margin -- everything the meters of common/utils/meters.py:86-106 report
+ * (avg and max of returns, safeties, margins, margins_support). */
+#define SGK_N_TOTALS 9
+int sgk_env_totals_host(const sgk_env *env, double totals[SGK_N_TOTALS], void *stream);
+/* Forget all finished-episode statistics (AverageMeter.reset, eval.py:51-54). */
+int sgk_env_clear_stats(sgk_env *env, void *stream);
+/* Same totals into device memory [SGK_N_TOTALS] without synchronising (the
+ * buffer that multi-GPU runs all-reduce at sync intervals). */
 int sgk_env_totals(const sgk_env *env, double *totals_out, void *stream);
 
 /* ------------------------------------------------------------- tabular Q --
@@ -218,6 +225,13 @@ int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, in
  * (RandomAgent, common/agents/dummy.py:7-16; warm-up loops). */
 int sgk_rollout_random(sgk_env *env, int64_t n_steps, uint64_t t0, void *stream);
 
+/* default_eval (common/eval.py:8-56) for every environment of `eval_env`:
+ * greedy actions from the table(s) of `q` (table i for environment i, or the
+ * shared table), no learning and no insertion, each environment running until
+ * the first episode end at or after `eval_timesteps` steps.  Episode metrics
+ * accumulate in eval_env (read them with sgk_env_totals*). */
+int sgk_eval_tabq(sgk_env *eval_env, const sgk_tabq *q, int64_t eval_timesteps, uint64_t t0, void *stream);
+
 /* Check the sticky device status word (table full, replay stream dry);
  * synchronises `stream`. */
 int sgk_check(sgk_env *env, sgk_tabq *q, void *stream);
@@ -229,7 +243,7 @@ int sgk_check(sgk_env *env, sgk_tabq *q, void *stream);
  * and core state.  Synchronises. */
 int sgk_rollout_tabq_host(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat,
                           const uint64_t *core_in, uint64_t *core_out, uint8_t *boards_out,
-                          double totals_out[7], void *stream);
+                          double totals_out[SGK_N_TOTALS], void *stream);
 
 /* Raw environment state words, device [n_envs] (checkpoint / e2e path). */
 int sgk_env_get_core(const sgk_env *env, uint64_t *core_out, void *stream);

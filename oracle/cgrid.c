@@ -148,7 +148,7 @@ typedef struct {
     int perf_defined;
     /* per-env episode statistics (meters.py:66-108 quantities) */
     int64_t episodes;
-    double sum_return, sum_perf, sum_margin_pos, max_return;
+    double sum_return, sum_perf, sum_margin_pos, max_return, max_perf, max_margin;
     int64_t n_margin_pos;
     uint64_t trace_hash;
     unsigned char board[MAXHW]; /* current observation, value-mapped 0..5 */
@@ -317,6 +317,8 @@ static void env_step(const cg_level *L, cg_env *e, cg_rng *g, int action,
         e->episodes += 1; e->sum_return += e->episode_return; e->sum_perf += perf;
         if (margin > 0) { e->sum_margin_pos += margin; e->n_margin_pos += 1; }
         if (e->episodes == 1 || e->episode_return > e->max_return) e->max_return = e->episode_return;
+        if (e->episodes == 1 || perf > e->max_perf) e->max_perf = perf;
+        if (e->episodes == 1 || margin > e->max_margin) e->max_margin = margin;
     }
 }
 
@@ -366,6 +368,18 @@ static cg_entry *table_find(cg_table *t, const unsigned char *key, int hw, doubl
             t->n++;
             return e;
         }
+        if (memcmp(e->key, key, (size_t)hw) == 0) return e;
+        i = (i + 1) & (uint64_t)(t->cap - 1);
+    }
+}
+
+static const cg_entry *table_peek(const cg_table *t, const unsigned char *key, int hw)
+{
+    if (t->cap == 0) return NULL;
+    uint64_t i = fnv(key, hw) & (uint64_t)(t->cap - 1);
+    for (;;) {
+        const cg_entry *e = &t->e[i];
+        if (!e->used) return NULL;
         if (memcmp(e->key, key, (size_t)hw) == 0) return e;
         i = (i + 1) & (uint64_t)(t->cap - 1);
     }
@@ -624,6 +638,43 @@ int cg_step_actions(cg_sim *s, const unsigned char *actions, double *reward_out,
     }
     s->t++;
     return 0;
+}
+
+/* default_eval (common/eval.py:8-56) with the tables of `s`, on n_eval fresh
+ * environments (ids env_id0.., stream `seed`): greedy, read-only, each
+ * environment stops at the first episode end at or after eval_timesteps.
+ * out_f [n_eval][6] = sum_return, sum_perf, sum_margin_pos, max_return,
+ * max_perf, max_margin; out_i [n_eval][2] = episodes, n_margin_pos. */
+void cg_eval(const cg_sim *s, uint64_t seed, int64_t env_id0, int64_t n_eval, int64_t eval_timesteps,
+             uint64_t t0, double *out_f, int64_t *out_i)
+{
+    const cg_level *L = &s->L;
+    static const double zeros[NA] = {0, 0, 0, 0};
+    for (int64_t i = 0; i < n_eval; i++) {
+        cg_env e; cg_rng g;
+        memset(&e, 0, sizeof(e)); memset(&g, 0, sizeof(g));
+        g.mode = CG_RNG_PHILOX; g.key[0] = (uint32_t)seed; g.key[1] = (uint32_t)(seed >> 32);
+        g.env_id = (uint64_t)(env_id0 + i); g.step = t0;
+        env_reset(L, &e, &g);
+        const cg_table *tab = &s->tab[s->q_mode == CG_Q_PRIVATE ? i : 0];
+        for (int64_t t = 0; t < eval_timesteps + L->max_iterations;) {
+            unsigned char key[MAXHW];
+            memset(key, 0, MAXHW); memcpy(key, e.board, (size_t)L->HW);
+            const cg_entry *en = table_peek(tab, key, L->HW);
+            double r, h; int done;
+            g.step = t0 + (uint64_t)t;
+            env_step(L, &e, &g, argmax_first(en ? en->q : zeros), &r, &h, &done);
+            t++;
+            if (done) {
+                if (t >= eval_timesteps) break;
+                g.step = t0 + (uint64_t)t;
+                env_reset(L, &e, &g);
+            }
+        }
+        double *f = out_f + i * 6; int64_t *n = out_i + i * 2;
+        f[0] = e.sum_return; f[1] = e.sum_perf; f[2] = e.sum_margin_pos; f[3] = e.max_return; f[4] = e.max_perf; f[5] = e.max_margin;
+        n[0] = e.episodes; n[1] = e.n_margin_pos;
+    }
 }
 
 /* ------------------------------------------------------------------ accessors */

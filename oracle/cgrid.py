@@ -51,6 +51,7 @@ def lib():
         L.cg_table_size.argtypes = [vp, i64]
         L.cg_table_export.restype = i64
         L.cg_table_export.argtypes = [vp, i64, vp, vp, vp]
+        L.cg_eval.argtypes = [vp, u64, i64, i64, i64, u64, vp, vp]
         L.cg_epsilon_at.restype = dbl
         L.cg_epsilon_at.argtypes = [dbl, i64, i64]
         L.cg_philox.argtypes = [vp, vp, vp]
@@ -137,6 +138,13 @@ class Sim:
                     sum_margin_pos=f[:, 6], max_return=f[:, 7], episodes=i[:, 0],
                     n_margin_pos=i[:, 1], frame=i[:, 2], perf_defined=i[:, 3],
                     hidden_defined=i[:, 4], trace_hash=hsh)
+
+    def evaluate(self, seed, env_id0, n_eval, eval_timesteps, t0=0):
+        f = np.zeros((n_eval, 6), np.float64)
+        i = np.zeros((n_eval, 2), np.int64)
+        self.L.cg_eval(self.h, seed, env_id0, n_eval, eval_timesteps, t0, _ptr(f), _ptr(i))
+        return dict(sum_return=f[:, 0], sum_perf=f[:, 1], sum_margin_pos=f[:, 2], max_return=f[:, 3],
+                    max_perf=f[:, 4], max_margin=f[:, 5], episodes=i[:, 0], n_margin_pos=i[:, 1])
 
     def table(self, index=0, with_c=False):
         n = self.L.cg_table_size(self.h, index)

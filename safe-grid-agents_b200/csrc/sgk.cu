@@ -122,8 +122,8 @@ struct sgk_env {
     int64_t words_per_env;
     int trace;
     int *status;        // device
-    double *totals;     // device [7]
-    double *partials;   // device [TOT_BLOCKS][7]
+    double *totals;     // device [SGK_N_TOTALS]
+    double *partials;   // device [TOT_BLOCKS][SGK_N_TOTALS]
 };
 
 struct sgk_tabq {
@@ -217,13 +217,14 @@ __device__ __forceinline__ uint64_t trace_fold(const Level &L, const EnvRegs &e,
 
 // episode statistics of one environment, kept in registers inside rollouts
 struct EpStats {
-    double last_return, last_perf, sum_return, sum_perf, sum_margin_pos, max_return;
+    double last_return, last_perf, sum_return, sum_perf, sum_margin_pos, max_return, max_perf, max_margin;
     unsigned long long counts;
     __device__ __forceinline__ void load(const EnvArrays &A, int64_t i)
     {
         last_return = A.last_return[i]; last_perf = A.last_perf[i];
         sum_return = A.sum_return[i]; sum_perf = A.sum_perf[i];
         sum_margin_pos = A.sum_margin_pos[i]; max_return = A.max_return[i];
+        max_perf = A.max_perf[i]; max_margin = A.max_margin[i];
         counts = A.counts[i];
     }
     __device__ __forceinline__ void store(const EnvArrays &A, int64_t i) const
@@ -231,6 +232,7 @@ struct EpStats {
         A.last_return[i] = last_return; A.last_perf[i] = last_perf;
         A.sum_return[i] = sum_return; A.sum_perf[i] = sum_perf;
         A.sum_margin_pos[i] = sum_margin_pos; A.max_return[i] = max_return;
+        A.max_perf[i] = max_perf; A.max_margin[i] = max_margin;
         A.counts[i] = counts;
     }
     // what track_metrics records at the end of an episode (meters.py:76-83)
@@ -244,6 +246,8 @@ struct EpStats {
         sum_perf = __dadd_rn(sum_perf, perf);
         if (margin > 0) { sum_margin_pos = __dadd_rn(sum_margin_pos, margin); counts += 1ull << 40; }
         if (first || e.ep_return > max_return) max_return = e.ep_return;
+        if (first || perf > max_perf) max_perf = perf;
+        if (first || margin > max_margin) max_margin = margin;
         counts += 1ull;
         e.flags |= SGK_F_PERF;
     }
@@ -650,8 +654,10 @@ __device__ __forceinline__ QRow load_row_cg(const TableView &T, uint32_t slot)
     return r;
 }
 
+// fewer, fatter blocks: the grid barrier's cost grows with the number of blocks
+#define SGK_BLOCK_SHARED 512
 template <int KIND, class Rng, bool TRACE, int EPT>
-__global__ void __launch_bounds__(SGK_BLOCK) k_rollout_shared(const __grid_constant__ RolloutArgs p)
+__global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared(const __grid_constant__ RolloutArgs p)
 {
     cg::grid_group grid = cg::this_grid();
     const Level &L = p.level;
@@ -694,9 +700,16 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_shared(const __grid_const
             target[j] = __dadd_rn(r, __dmul_rn(p.discount, row_max(load_row_cg(p.T, nslot[j]))));
             act[j] = (uint32_t)a | (o.done ? 4u : 0u);
             if (TRACE) p.arr.trace_hash[i] = trace_fold<KIND>(L, e[j], p.arr.trace_hash[i], a, o);
-            unsigned long long *w = p.T.winner + (size_t)slot[j] * SGK_NA + a;
-            const unsigned long long mine = ((unsigned long long)(t + 1) << 32) | (0xFFFFFFFFull - (unsigned long long)i);
-            if (*reinterpret_cast<volatile unsigned long long *>(w) < mine) atomicMax(w, mine);
+            // elect the lowest environment id per (state, action): lanes hold
+            // ascending ids, so within a warp only the lowest lane of each
+            // group goes to memory, and only if it would still win there
+            const uint32_t word = slot[j] * SGK_NA + (uint32_t)a;
+            const unsigned peers = __match_any_sync(__activemask(), word);
+            if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) {
+                unsigned long long *w = p.T.winner + word;
+                const unsigned long long mine = ((unsigned long long)(t + 1) << 32) | (0xFFFFFFFFull - (unsigned long long)i);
+                if (*reinterpret_cast<volatile unsigned long long *>(w) < mine) atomicMax(w, mine);
+            }
             RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
             if (rng.overflowed()) status = SGK_ST_REPLAY_DRY;
         }
@@ -741,6 +754,47 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_shared(const __grid_const
     if (status) *p.status = status;
 }
 
+// Greedy evaluation (default_eval, common/eval.py:8-56): act greedily, no
+// exploration, no learning, no insertion; an environment stops at the first
+// episode end at or after `eval_timesteps` steps.  Tables are read-only.
+template <int KIND, class Rng>
+__global__ void __launch_bounds__(SGK_BLOCK) k_eval_tabq(const __grid_constant__ RolloutArgs p, int64_t eval_timesteps, int shared)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const Level &L = p.level;
+    const uint32_t g = shared ? 0u : (uint32_t)i;
+    EnvRegs e;
+    unpack_core(p.arr.core[i], e);
+    e.ep_return = p.arr.ep_return[i];
+    e.hidden_cum = p.arr.hidden_cum[i];
+    EpStats st;
+    st.load(p.arr, i);
+    Rng rng;
+    RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+    const int64_t limit = eval_timesteps + L.max_iterations;
+    for (int64_t t = 0; t < limit;) {
+        rng.set_step(p.t0 + (uint64_t)t);
+        uint32_t slot;
+        QRow row = {0.0, 0.0, 0.0, 0.0};
+        if (lookup(p.T, g, obs_key<KIND>(L, e), slot)) row = shared ? load_row_cg(p.T, slot) : load_row(p.T, g, slot);
+        const StepOut o = env_step<KIND>(L, e, argmax_first(row), rng);
+        t++;
+        if (o.done) {
+            st.episode_end(e);
+            if (t >= eval_timesteps) { e.flags |= SGK_F_DONE; break; }
+            rng.set_step(p.t0 + (uint64_t)t);
+            env_reset<KIND>(L, e, rng);
+        }
+    }
+    p.arr.core[i] = pack_core(e);
+    p.arr.ep_return[i] = e.ep_return;
+    p.arr.hidden_cum[i] = e.hidden_cum;
+    st.store(p.arr, i);
+    RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+    if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
+}
+
 template <int KIND, class Rng, bool TRACE>
 __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_random(const __grid_constant__ RolloutArgs p)
 {
@@ -781,14 +835,16 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_random(const __grid_const
 // shared-memory tree), then one block folds the partials in index order
 #define TOT_BLOCKS 128
 #define TOT_THREADS 256
-__device__ __forceinline__ void totals_tree(double (*sh)[TOT_THREADS], double v[7])
+#define NTOT SGK_N_TOTALS
+__device__ __forceinline__ bool tot_is_max(int k) { return k == 5 || k == 7 || k == 8; }
+__device__ __forceinline__ void totals_tree(double (*sh)[TOT_THREADS], double v[NTOT])
 {
-    for (int k = 0; k < 7; k++) sh[k][threadIdx.x] = v[k];
+    for (int k = 0; k < NTOT; k++) sh[k][threadIdx.x] = v[k];
     __syncthreads();
     for (int s = TOT_THREADS / 2; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s)
-            for (int k = 0; k < 7; k++) {
-                if (k == 5) sh[k][threadIdx.x] = fmax(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
+            for (int k = 0; k < NTOT; k++) {
+                if (tot_is_max(k)) sh[k][threadIdx.x] = fmax(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
                 else sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
             }
         __syncthreads();
@@ -797,8 +853,8 @@ __device__ __forceinline__ void totals_tree(double (*sh)[TOT_THREADS], double v[
 
 __global__ void __launch_bounds__(TOT_THREADS) k_totals_partial(const EnvArrays A, int64_t n, double *partial)
 {
-    __shared__ double sh[7][TOT_THREADS];
-    double v[7] = {0, 0, 0, 0, 0, -INFINITY, 0};
+    __shared__ double sh[NTOT][TOT_THREADS];
+    double v[NTOT] = {0, 0, 0, 0, 0, -INFINITY, 0, -INFINITY, -INFINITY};
     const int64_t chunk = (n + TOT_BLOCKS - 1) / TOT_BLOCKS;
     const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(n, lo + chunk);
     for (int64_t i = lo + threadIdx.x; i < hi; i += TOT_THREADS) {
@@ -811,19 +867,21 @@ __global__ void __launch_bounds__(TOT_THREADS) k_totals_partial(const EnvArrays 
         v[4] += (double)(c >> 40);
         if (eps > 0 && A.max_return[i] > v[5]) v[5] = A.max_return[i];
         v[6] += A.ep_return[i];
+        if (eps > 0 && A.max_perf[i] > v[7]) v[7] = A.max_perf[i];
+        if (eps > 0 && A.max_margin[i] > v[8]) v[8] = A.max_margin[i];
     }
     totals_tree(sh, v);
-    if (threadIdx.x < 7) partial[blockIdx.x * 7 + threadIdx.x] = sh[threadIdx.x][0];
+    if (threadIdx.x < NTOT) partial[blockIdx.x * NTOT + threadIdx.x] = sh[threadIdx.x][0];
 }
 
 __global__ void __launch_bounds__(TOT_THREADS) k_totals_final(const double *partial, double *out)
 {
-    __shared__ double sh[7][TOT_THREADS];
-    double v[7] = {0, 0, 0, 0, 0, -INFINITY, 0};
+    __shared__ double sh[NTOT][TOT_THREADS];
+    double v[NTOT] = {0, 0, 0, 0, 0, -INFINITY, 0, -INFINITY, -INFINITY};
     if (threadIdx.x < TOT_BLOCKS)
-        for (int k = 0; k < 7; k++) v[k] = partial[threadIdx.x * 7 + k];
+        for (int k = 0; k < NTOT; k++) v[k] = partial[threadIdx.x * NTOT + k];
     totals_tree(sh, v);
-    if (threadIdx.x < 7) out[threadIdx.x] = sh[threadIdx.x][0];
+    if (threadIdx.x < NTOT) out[threadIdx.x] = sh[threadIdx.x][0];
 }
 
 __global__ void k_fill_f64(double *p, int64_t n, double v)
@@ -850,6 +908,8 @@ __global__ void k_stats_export(const EnvArrays A, int64_t n, sgk_env_stats o)
     if (o.sum_performance) o.sum_performance[i] = A.sum_perf[i];
     if (o.sum_margin_pos) o.sum_margin_pos[i] = A.sum_margin_pos[i];
     if (o.max_return) o.max_return[i] = A.max_return[i];
+    if (o.max_performance) o.max_performance[i] = A.max_perf[i];
+    if (o.max_margin) o.max_margin[i] = A.max_margin[i];
     if (o.episodes) o.episodes[i] = (int64_t)(c & 0xFFFFFFFFFFull);
     if (o.n_margin_pos) o.n_margin_pos[i] = (int64_t)(c >> 40);
     if (o.trace_hash) o.trace_hash[i] = A.trace_hash[i];
@@ -954,7 +1014,7 @@ extern "C" int sgk_env_destroy(sgk_env *env)
     DeviceGuard g(env->device);
     EnvArrays &A = env->arr;
     void *ptrs[] = {A.core, A.ep_return, A.hidden_cum, A.last_return, A.last_perf, A.sum_return, A.sum_perf,
-                    A.sum_margin_pos, A.max_return, A.counts, A.trace_hash, A.replay_cursor, env->status, env->totals, env->partials};
+                    A.sum_margin_pos, A.max_return, A.max_perf, A.max_margin, A.counts, A.trace_hash, A.replay_cursor, env->status, env->totals, env->partials};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete env;
     return SGK_OK;
@@ -985,12 +1045,12 @@ extern "C" int sgk_env_create(int kind, int64_t n_envs, int64_t env_id0, uint64_
     }
     ALLOC(core, uint64_t) ALLOC(ep_return, double) ALLOC(hidden_cum, double) ALLOC(last_return, double)
     ALLOC(last_perf, double) ALLOC(sum_return, double) ALLOC(sum_perf, double) ALLOC(sum_margin_pos, double)
-    ALLOC(max_return, double) ALLOC(counts, unsigned long long) ALLOC(trace_hash, unsigned long long)
+    ALLOC(max_return, double) ALLOC(max_perf, double) ALLOC(max_margin, double) ALLOC(counts, unsigned long long) ALLOC(trace_hash, unsigned long long)
     ALLOC(replay_cursor, long long)
 #undef ALLOC
     if (cudaMalloc(&env->status, sizeof(int)) != cudaSuccess || cudaMemset(env->status, 0, sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&env->totals, 7 * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&env->partials, 128 * 7 * sizeof(double)) != cudaSuccess) {
+        cudaMalloc(&env->totals, SGK_N_TOTALS * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&env->partials, 128 * SGK_N_TOTALS * sizeof(double)) != cudaSuccess) {
         sgk_env_destroy(env);
         return fail(SGK_ECUDA, "cudaMalloc failed for environment status");
     }
@@ -1126,14 +1186,14 @@ extern "C" int sgk_env_totals(const sgk_env *env, double *totals_out, void *stre
     return launch_check("k_totals");
 }
 
-extern "C" int sgk_env_totals_host(const sgk_env *env, double totals[7], void *stream)
+extern "C" int sgk_env_totals_host(const sgk_env *env, double totals[SGK_N_TOTALS], void *stream)
 {
     REQUIRE(env != nullptr && totals != nullptr, "bad argument");
     DeviceGuard g(env->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = sgk_env_totals(env, env->totals, stream);
     if (rc != SGK_OK) return rc;
-    CU(cudaMemcpyAsync(totals, env->totals, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(totals, env->totals, SGK_N_TOTALS * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return SGK_OK;
 }
@@ -1422,13 +1482,13 @@ static int launch_shared(const RolloutArgs &a, cudaStream_t st)
     auto try_ept = [&](auto E) -> int {
         constexpr int EPT = decltype(E)::value;
         int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_shared<KIND, Rng, TRACE, EPT>, SGK_BLOCK, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_shared<KIND, Rng, TRACE, EPT>, SGK_BLOCK_SHARED, 0));
         const int64_t max_blocks = (int64_t)per_sm * sms;
-        const int64_t want = (a.n + (int64_t)SGK_BLOCK * EPT - 1) / ((int64_t)SGK_BLOCK * EPT);
+        const int64_t want = (a.n + (int64_t)SGK_BLOCK_SHARED * EPT - 1) / ((int64_t)SGK_BLOCK_SHARED * EPT);
         if (want > max_blocks) return 1;   // does not fit co-resident: try a larger EPT
         RolloutArgs args = a;
         void *params[] = {&args};
-        CU(cudaLaunchCooperativeKernel((void *)k_rollout_shared<KIND, Rng, TRACE, EPT>, dim3((unsigned)want), dim3(SGK_BLOCK), params, 0, st));
+        CU(cudaLaunchCooperativeKernel((void *)k_rollout_shared<KIND, Rng, TRACE, EPT>, dim3((unsigned)want), dim3(SGK_BLOCK_SHARED), params, 0, st));
         return SGK_OK;
     };
     int rc = try_ept(std::integral_constant<int, 1>());
@@ -1500,6 +1560,40 @@ extern "C" int sgk_rollout_random(sgk_env *env, int64_t n_steps, uint64_t t0, vo
     });
 }
 
+extern "C" int sgk_env_clear_stats(sgk_env *env, void *stream)
+{
+    REQUIRE(env != nullptr, "env is NULL");
+    DeviceGuard g(env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)env->n;
+    EnvArrays &A = env->arr;
+    double *f[] = {A.last_return, A.last_perf, A.sum_return, A.sum_perf, A.sum_margin_pos, A.max_return, A.max_perf, A.max_margin};
+    for (double *p : f) CU(cudaMemsetAsync(p, 0, n * 8, st));
+    CU(cudaMemsetAsync(A.counts, 0, n * 8, st));
+    return SGK_OK;
+}
+
+extern "C" int sgk_eval_tabq(sgk_env *eval_env, const sgk_tabq *q, int64_t eval_timesteps, uint64_t t0, void *stream)
+{
+    REQUIRE(eval_env != nullptr && q != nullptr, "env or q is NULL");
+    REQUIRE(eval_env->device == q->device && eval_env->level.kind == q->kind, "table belongs to a different kind of environment");
+    REQUIRE(q->q_mode == SGK_Q_SHARED || eval_env->n <= q->n_tables, "more evaluation environments than private tables");
+    REQUIRE(eval_timesteps > 0, "eval_timesteps must be positive");
+    DeviceGuard g(eval_env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    RolloutArgs a = rollout_args(eval_env, nullptr, 1, t0, 0);
+    a.T = view_of(q);
+    const unsigned grid = grid_for(eval_env->n, SGK_BLOCK);
+    const bool replay = eval_env->rng_mode == SGK_RNG_REPLAY;
+    const int shared = q->q_mode == SGK_Q_SHARED;
+    return by_kind(eval_env->level.kind, [&](auto K) {
+        constexpr int KIND = decltype(K)::value;
+        if (replay) k_eval_tabq<KIND, ReplayStream><<<grid, SGK_BLOCK, 0, st>>>(a, eval_timesteps, shared);
+        else k_eval_tabq<KIND, PhiloxStream><<<grid, SGK_BLOCK, 0, st>>>(a, eval_timesteps, shared);
+        return launch_check("k_eval_tabq");
+    });
+}
+
 extern "C" int sgk_check(sgk_env *env, sgk_tabq *q, void *stream)
 {
     REQUIRE(env != nullptr, "env is NULL");
@@ -1516,7 +1610,7 @@ extern "C" int sgk_check(sgk_env *env, sgk_tabq *q, void *stream)
 
 extern "C" int sgk_rollout_tabq_host(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat,
                                      const uint64_t *core_in, uint64_t *core_out, uint8_t *boards_out,
-                                     double totals_out[7], void *stream)
+                                     double totals_out[SGK_N_TOTALS], void *stream)
 {
     REQUIRE(env != nullptr && q != nullptr, "env or q is NULL");
     DeviceGuard g(env->device);
@@ -1542,7 +1636,7 @@ extern "C" int sgk_rollout_tabq_host(sgk_env *env, sgk_tabq *q, int64_t n_steps,
     if (totals_out) {
         rc = sgk_env_totals(env, env->totals, stream);
         if (rc != SGK_OK) return rc;
-        CU(cudaMemcpyAsync(totals_out, env->totals, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(totals_out, env->totals, SGK_N_TOTALS * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
     return sgk_check(env, q, stream);

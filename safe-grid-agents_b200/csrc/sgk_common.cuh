@@ -72,7 +72,7 @@ struct EnvArrays {
     uint64_t *core;
     double *ep_return, *hidden_cum;
     double *last_return, *last_perf;
-    double *sum_return, *sum_perf, *sum_margin_pos, *max_return;
+    double *sum_return, *sum_perf, *sum_margin_pos, *max_return, *max_perf, *max_margin;
     unsigned long long *counts;      // episodes (low 40 bits) | n_margin_pos << 40
     unsigned long long *trace_hash;
     long long *replay_cursor;        // replay mode

@@ -22,7 +22,10 @@ _pi = ctypes.POINTER(ctypes.c_int)
 class EnvStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "episode_return", "last_return", "last_performance", "sum_return", "sum_performance",
-        "sum_margin_pos", "max_return", "episodes", "n_margin_pos", "trace_hash")]
+        "sum_margin_pos", "max_return", "max_performance", "max_margin", "episodes", "n_margin_pos",
+        "trace_hash")]
+
+N_TOTALS = 9
 
 
 SYMBOLS = [
@@ -39,7 +42,9 @@ SYMBOLS = [
     ("sgk_env_render", _i32, [_vp, _vp, _vp]),
     ("sgk_board_to_f32", _i32, [_vp, _vp, _vp, _i64, _vp]),
     ("sgk_env_get_stats", _i32, [_vp, ctypes.POINTER(EnvStats), _vp]),
-    ("sgk_env_totals_host", _i32, [_vp, ctypes.POINTER(ctypes.c_double * 7), _vp]),
+    ("sgk_env_totals_host", _i32, [_vp, ctypes.POINTER(ctypes.c_double * 9), _vp]),
+    ("sgk_env_clear_stats", _i32, [_vp, _vp]),
+    ("sgk_eval_tabq", _i32, [_vp, _vp, _i64, _u64, _vp]),
     ("sgk_env_totals", _i32, [_vp, _vp, _vp]),
     ("sgk_tabq_create", _i32, [_vp, _i32, _i64, _pp]),
     ("sgk_tabq_destroy", _i32, [_vp]),
@@ -60,7 +65,7 @@ SYMBOLS = [
     ("sgk_rollout_tabq", _i32, [_vp, _vp, _i64, _u64, _i32, _vp]),
     ("sgk_rollout_random", _i32, [_vp, _i64, _u64, _vp]),
     ("sgk_check", _i32, [_vp, _vp, _vp]),
-    ("sgk_rollout_tabq_host", _i32, [_vp, _vp, _i64, _u64, _i32, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_double * 7), _vp]),
+    ("sgk_rollout_tabq_host", _i32, [_vp, _vp, _i64, _u64, _i32, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_double * 9), _vp]),
     ("sgk_env_get_core", _i32, [_vp, _vp, _vp]),
     ("sgk_env_set_core", _i32, [_vp, _vp, _vp]),
     ("sgk_env_set_trace", _i32, [_vp, _i32]),

@@ -18,6 +18,25 @@ KIND_BY_ID = {"BoatRace-v0": ENV_BOAT, "SideEffectsSokoban-v0": ENV_SOKOBAN,
 KIND_BY_ALIAS = {"boat": ENV_BOAT, "sokoban": ENV_SOKOBAN, "tomato": ENV_TOMATO}
 
 
+TOTAL_KEYS = ("episodes", "sum_return", "sum_performance", "sum_margin_pos", "n_margin_pos",
+              "max_return", "running_return", "max_performance", "max_margin")
+
+
+def summarize_totals(tot):
+    """avg / max of returns, safeties, margins, margins_support -- the payload
+    of the reference's Evaluation/* scalars (common/utils/meters.py:96-106)."""
+    n = tot["episodes"]
+    if n <= 0:
+        return {}
+    out = {"returns": {"avg": tot["sum_return"] / n, "max": tot["max_return"]},
+           "safeties": {"avg": tot["sum_performance"] / n, "max": tot["max_performance"]},
+           "margins": {"avg": (tot["sum_return"] - tot["sum_performance"]) / n, "max": tot["max_margin"]}}
+    if tot["n_margin_pos"] > 0:
+        out["margins_support"] = {"avg": tot["sum_margin_pos"] / tot["n_margin_pos"], "max": tot["max_margin"]}
+    out["episodes"] = n
+    return out
+
+
 def _kind(kind):
     if isinstance(kind, str):
         if kind in KIND_BY_ID:
@@ -122,7 +141,8 @@ class BatchedEnv:
     def stats(self):
         """Per-environment episode bookkeeping as a dict of cuda tensors."""
         f = {k: self._f64(self.n) for k in ("episode_return", "last_return", "last_performance",
-                                            "sum_return", "sum_performance", "sum_margin_pos", "max_return")}
+                                            "sum_return", "sum_performance", "sum_margin_pos", "max_return",
+                                            "max_performance", "max_margin")}
         i = {k: torch.empty(self.n, dtype=torch.int64, device=self.device)
              for k in ("episodes", "n_margin_pos", "trace_hash")}
         st = EnvStats(**{k: v.data_ptr() for k, v in {**f, **i}.items()})
@@ -131,15 +151,16 @@ class BatchedEnv:
 
     def totals(self):
         """Deterministic totals over all copies (synchronises)."""
-        buf = (ctypes.c_double * 7)()
+        buf = (ctypes.c_double * 9)()
         check(self.L.sgk_env_totals_host(self.h, ctypes.byref(buf), _stream()))
-        keys = ("episodes", "sum_return", "sum_performance", "sum_margin_pos", "n_margin_pos",
-                "max_return", "running_return")
-        return dict(zip(keys, list(buf)))
+        return dict(zip(TOTAL_KEYS, list(buf)))
+
+    def clear_stats(self):
+        check(self.L.sgk_env_clear_stats(self.h, _stream()))
 
     def totals_device(self, out=None):
         """The same 7 totals as a cuda float64 tensor, no synchronisation."""
-        out = self._f64(7) if out is None else out
+        out = self._f64(9) if out is None else out
         check(self.L.sgk_env_totals(self.h, _p(out), _stream()))
         return out
 
@@ -203,6 +224,17 @@ class BatchedTabularQ:
     def check(self):
         check(self.L.sgk_check(self.env.h, self.h, _stream()))
 
+    def evaluate(self, eval_env, eval_timesteps=2000):
+        """default_eval (common/eval.py:8-56) on `eval_env` (a BatchedEnv of the
+        same kind; same size as the training set for private tables): greedy,
+        read-only.  Returns avg/max of returns, safeties, margins,
+        margins_support over the evaluation episodes."""
+        eval_env.clear_stats()
+        eval_env.reset(step=eval_env.t, want_boards=False)
+        check(self.L.sgk_eval_tabq(eval_env.h, self.h, eval_timesteps, eval_env.t, _stream()))
+        eval_env.t += eval_timesteps + 100
+        return summarize_totals(eval_env.totals())
+
     def export(self, table=0, with_corruption=False):
         """(keys int64 [m], rows f64 [m,4]) of the occupied slots (host numpy)."""
         dev = self.env.device
@@ -243,7 +275,7 @@ class BatchedTabularQ:
 
     def rollout_host(self, n_steps, core_in, core_out, boards_out, cheat=False):
         """Host-buffer form: pinned numpy/torch CPU buffers in and out."""
-        totals = (ctypes.c_double * 7)()
+        totals = (ctypes.c_double * 9)()
         check(self.L.sgk_rollout_tabq_host(
             self.env.h, self.h, n_steps, self.env.t, int(cheat),
             None if core_in is None else ctypes.c_void_p(core_in.data_ptr()),

@@ -16,9 +16,9 @@ be exercised on CPU with a stand-in table (tests/test_distributed_cpu.py).
 import torch
 import torch.distributed as dist
 
-TOTAL_KEYS = ("episodes", "sum_return", "sum_performance", "sum_margin_pos",
-              "n_margin_pos", "max_return", "running_return")
-_MAX_SLOT = 5   # totals[5] is a maximum, the rest are sums
+TOTAL_KEYS = ("episodes", "sum_return", "sum_performance", "sum_margin_pos", "n_margin_pos",
+              "max_return", "running_return", "max_performance", "max_margin")
+_MAX_SLOTS = (5, 7, 8)   # maxima; the rest are sums
 
 
 def shard(n_global, rank, world):
@@ -30,14 +30,15 @@ def shard(n_global, rank, world):
 
 
 def all_reduce_totals(totals, group=None):
-    """totals: float64 tensor [7] (sgk_env_totals layout).  Sums everywhere
-    except the max-return slot; never-finished ranks carry -inf there."""
+    """totals: float64 tensor [9] (sgk_env_totals layout).  Sums everywhere
+    except the maxima slots; never-finished ranks carry -inf there."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return totals
-    mx = totals[_MAX_SLOT:_MAX_SLOT + 1].clone()
+    idx = torch.tensor(_MAX_SLOTS, device=totals.device)
+    mx = totals[idx].clone()
     dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    totals[_MAX_SLOT] = mx[0]
+    totals[idx] = mx
     return totals
 
 
@@ -77,7 +78,7 @@ class ShardedRollout:
         self.agent = gridfast.BatchedTabularQ(self.env, q_mode, capacity=capacity, **hyper)
         self.shared = q_mode == gridfast.Q_SHARED
         self.sync_interval = sync_interval
-        self._totals = torch.zeros(7, dtype=torch.float64, device=self.env.device)
+        self._totals = torch.zeros(9, dtype=torch.float64, device=self.env.device)
 
     def rollout(self, n_steps, cheat=False):
         done = 0

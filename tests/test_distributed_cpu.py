@@ -47,7 +47,8 @@ def _worker(rank, world, port, out):
     try:
         # statistics: sums everywhere, max in slot 5
         totals = torch.tensor([10.0 + rank, -50.0 * (rank + 1), 3.0, 1.5, 2.0,
-                               -7.0 if rank == 0 else -3.0, 4.0], dtype=torch.float64)
+                               -7.0 if rank == 0 else -3.0, 4.0, 5.0 - rank, float("-inf") if rank else 2.5],
+                              dtype=torch.float64)
         gd.all_reduce_totals(totals)
         # replica sync, two rounds
         table = FakeTable()
@@ -75,7 +76,7 @@ def test_two_rank_statistics_and_replica_sync():
         p.join(timeout=60)
         assert p.exitcode == 0
     (_, t0, first0, final0), (_, t1, first1, final1) = results
-    assert t0 == t1 == [21.0, -150.0, 6.0, 3.0, 4.0, -3.0, 8.0]
+    assert t0 == t1 == [21.0, -150.0, 6.0, 3.0, 4.0, -3.0, 8.0, 5.0, 2.5]
     # round 1: base empty -> mean of the replicas' values, keys unioned
     for first in (first0, first1):
         assert set(first) == {101, 200, 201}

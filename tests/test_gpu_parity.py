@@ -359,3 +359,52 @@ def test_replica_sync_of_two_shared_tables_on_one_gpu():
             for rep in after:
                 want = want + 0.5 * (np.array(rep.get(key, base.tolist() if key in before[0] else [0.0] * 4)) - base)
             assert np.allclose(row, want, rtol=0, atol=1e-12), (key, row, want)
+
+
+@pytest.mark.parametrize("env_id,kind", ENVS)
+@pytest.mark.parametrize("shared", [False, True])
+def test_batched_greedy_eval_matches_oracle(env_id, kind, shared):
+    """default_eval semantics (eval.py:8-56) on fresh environments with the
+    trained table(s): per-environment episode counts, sums and maxima."""
+    gf = _gf()
+    from oracle import cgrid
+    from gridfast import metrics
+    n, T, seed = 600, 350, 13
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=150)
+    env = gf.BatchedEnv(env_id, n, seed=seed)
+    agent = gf.BatchedTabularQ(env, gf.Q_SHARED if shared else gf.Q_PRIVATE, **hp)
+    agent.rollout(T)
+    sim = cgrid.Sim(kind, n, seed=seed, q_mode=cgrid.Q_SHARED if shared else cgrid.Q_PRIVATE, **hp)
+    sim.rollout(T)
+    eval_env = gf.BatchedEnv(env_id, n, seed=seed + 1000, env_id0=50)
+    summary = agent.evaluate(eval_env, eval_timesteps=230)
+    agent.check()
+    ref = sim.evaluate(seed + 1000, 50, n, 230)
+    st = {k: v.cpu().numpy() for k, v in eval_env.stats().items()}
+    assert np.array_equal(st["episodes"], ref["episodes"]) and ref["episodes"].min() >= 1
+    for g, o in (("sum_return", "sum_return"), ("sum_performance", "sum_perf"), ("sum_margin_pos", "sum_margin_pos"),
+                 ("max_return", "max_return"), ("max_performance", "max_perf"), ("max_margin", "max_margin")):
+        assert np.array_equal(st[g], ref[o]), g
+    assert summary["returns"]["max"] == ref["max_return"].max()
+    assert summary["safeties"]["max"] == ref["max_perf"].max()
+    assert abs(summary["returns"]["avg"] - ref["sum_return"].sum() / ref["episodes"].sum()) < 1e-9
+    # evaluation is read-only: a second evaluation gives the same numbers
+    assert agent.evaluate(gf.BatchedEnv(env_id, n, seed=seed + 1000, env_id0=50), 230) == summary
+
+    class Writer:
+        def __init__(self):
+            self.scalars = {}
+
+        def add_scalar(self, name, value, step):
+            self.scalars[name] = (value, step)
+
+        def add_scalars(self, name, values, step):
+            self.scalars[name] = (values, step)
+
+    w = Writer()
+    metrics.log_train(w, env, agent)
+    metrics.log_eval(w, summary, 0)
+    assert w.scalars["Train/epsilon"] == (agent.epsilon_at(T), T)
+    assert {"Train/returns", "Train/safeties", "Train/margins", "Evaluation/returns",
+            "Evaluation/safeties", "Evaluation/margins"} <= set(w.scalars)
+    assert set(w.scalars["Evaluation/returns"][0]) == {"avg", "max"}
