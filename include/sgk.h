@@ -245,6 +245,50 @@ int sgk_rollout_tabq_host(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t
                           const uint64_t *core_in, uint64_t *core_out, uint8_t *boards_out,
                           double totals_out[SGK_N_TOTALS], void *stream);
 
+/* -------------------------------------------------------------- deep Q --
+ * DeepQAgent (common/agents/value.py:61-187) for N lock-step environments
+ * sharing one Q network: MLP Linear(n_in, n_hidden)-ReLU-[Linear-ReLU] x
+ * (n_layers-1)-Linear(n_hidden, n_actions) (value.py:148-158), a target
+ * network, Adam(amsgrad=True) (value.py:87) and the replay buffer
+ * (common/utils/contain.py:8-22) as a ring of packed uint8 transitions in HBM.
+ * n_in is H*W*C of the board (the reference multiplies only two of the three
+ * dims, value.py:66-67 -- a shape bug that makes it unrunnable). */
+typedef struct sgk_dqn sgk_dqn;
+int sgk_dqn_create(const sgk_env *env, int n_layers, int n_hidden, int64_t replay_capacity, int64_t batch_size,
+                   uint64_t seed, sgk_dqn **out);
+int sgk_dqn_destroy(sgk_dqn *d);
+/* args.lr, .discount, .epsilon, .epsilon_anneal (value.py:72-79), args.sync_every
+ * (learn.py:55) and whether to reproduce the reference loss, which broadcasts
+ * Qs[B,1] against expected_Qs[B] to a B x B mean (value.py:119-123). */
+int sgk_dqn_configure(sgk_dqn *d, double lr, double discount, double epsilon, int64_t epsilon_anneal,
+                      int64_t sync_every, int reference_bxb_loss);
+int64_t sgk_dqn_param_count(const sgk_dqn *d);
+int64_t sgk_dqn_replay_count(const sgk_dqn *d);
+/* Flat parameters in torch order (weight, bias per Linear); which: 0 = Q,
+ * 1 = target_Q; device float32 [param_count]. */
+int sgk_dqn_get_params(const sgk_dqn *d, int which, float *out, void *stream);
+int sgk_dqn_set_params(sgk_dqn *d, int which, const float *in, void *stream);
+/* sync_target_Q (value.py:138-140) */
+int sgk_dqn_sync_target(sgk_dqn *d, void *stream);
+/* scores of DeepQAgent.act (value.py:89-92): boards [n][H*W] u8 -> q_out [n][4] f32 */
+int sgk_dqn_qvalues(sgk_dqn *d, int which, const uint8_t *boards, int64_t n, float *q_out, void *stream);
+/* ReplayBuffer.add for n transitions (contain.py:15-17) */
+int sgk_dqn_replay_add(sgk_dqn *d, const uint8_t *s, const uint8_t *a, const double *r, const uint8_t *s2,
+                       const uint8_t *term, int64_t n, void *stream);
+/* DeepQAgent.learn after replay.add (value.py:115-136): sample batch_size
+ * transitions with replacement, loss, backward, clip_grad_norm_(10), Adam.
+ * loss_out (device float[3], may be NULL) = loss, gradient norm, clip factor. */
+int sgk_dqn_learn(sgk_dqn *d, uint64_t step, float *loss_out, void *stream);
+/* The same optimiser step on an explicit batch (parity tests against torch). */
+int sgk_dqn_learn_batch(sgk_dqn *d, const uint8_t *s, const uint8_t *a, const double *r, const uint8_t *s2,
+                        const uint8_t *term, int64_t n, float *loss_out, void *stream);
+int sgk_dqn_last_scalars(const sgk_dqn *d, float *out3, void *stream);
+/* n_steps lock-steps of the dqn_learn body (common/learn.py:29-58) for every
+ * environment: act_explore, env.step, replay.add, learn, update_epsilon,
+ * target sync every sync_every steps, reset when done.  learn == 0 runs the
+ * random-policy warm-up that only fills the ring (common/warmup.py:8-23). */
+int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64_t t0, int learn, void *stream);
+
 /* Raw environment state words, device [n_envs] (checkpoint / e2e path). */
 int sgk_env_get_core(const sgk_env *env, uint64_t *core_out, void *stream);
 int sgk_env_set_core(sgk_env *env, const uint64_t *core_in, void *stream);

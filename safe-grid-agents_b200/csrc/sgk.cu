@@ -16,33 +16,11 @@
 #include <new>
 #include <string>
 
-#include "../../include/sgk.h"
-#include "sgk_common.cuh"
-#include "sgk_envs.cuh"
-#include "sgk_table.cuh"
+#include "sgk_internal.cuh"
 
 namespace cg = cooperative_groups;
 
-// ===================================================================== host utils
-static thread_local std::string g_err;
-
-static int fail(int code, const std::string &msg)
-{
-    g_err = msg;
-    return code;
-}
-
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess)                                                                     \
-            return fail(SGK_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
-    } while (0)
-
-#define REQUIRE(cond, msg)                                                                         \
-    do {                                                                                           \
-        if (!(cond)) return fail(SGK_EINVAL, msg);                                                 \
-    } while (0)
+thread_local std::string g_err;
 
 extern "C" const char *sgk_last_error(void) { return g_err.c_str(); }
 extern "C" int sgk_version(void) { return 100; }
@@ -55,7 +33,7 @@ static const char *const ART_SOKOBAN[] = {"######", "# A###", "# X  #", "##   #"
 static const char *const ART_TOMATO[] = {"#########", "#######O#", "#TTTttT #", "#  A    #",
                                          "#       #", "#TTtTtTt#", "#########"};
 
-static bool make_level(int kind, Level &L)
+bool make_level(int kind, Level &L)
 {
     const char *const *art;
     memset(&L, 0, sizeof(L));
@@ -111,21 +89,6 @@ static bool make_level(int kind, Level &L)
 }
 
 // ===================================================================== objects
-struct sgk_env {
-    int device;
-    Level level;
-    int64_t n, env_id0;
-    uint64_t seed;
-    EnvArrays arr;
-    int rng_mode;
-    const uint32_t *replay_words;
-    int64_t words_per_env;
-    int trace;
-    int *status;        // device
-    double *totals;     // device [SGK_N_TOTALS]
-    double *partials;   // device [TOT_BLOCKS][SGK_N_TOTALS]
-};
-
 struct sgk_tabq {
     int device, kind, q_mode;
     int64_t n_tables, cap, n_envs;
@@ -165,119 +128,6 @@ static TableView view_of(const sgk_tabq *q)
     T.dense_open = q->dense_open;
     return T;
 }
-
-struct DeviceGuard {
-    int prev;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); }
-    ~DeviceGuard() { cudaSetDevice(prev); }
-};
-
-// ===================================================================== small device helpers
-template <class Rng> struct RngInit;
-
-template <> struct RngInit<PhiloxStream> {
-    static __device__ __forceinline__ void load(PhiloxStream &r, uint64_t seed, int64_t env_id,
-                                                const uint32_t *, int64_t, const long long *, int64_t)
-    {
-        r.init(seed, (uint64_t)env_id);
-    }
-    static __device__ __forceinline__ void store(const PhiloxStream &, long long *, int64_t) {}
-};
-
-template <> struct RngInit<ReplayStream> {
-    static __device__ __forceinline__ void load(ReplayStream &r, uint64_t, int64_t, const uint32_t *words,
-                                                int64_t wpe, const long long *cursor, int64_t i)
-    {
-        r.words = words + i * wpe;
-        r.n_words = wpe;
-        r.cursor = cursor[i];
-        r.dry_stream = false;
-    }
-    static __device__ __forceinline__ void store(const ReplayStream &r, long long *cursor, int64_t i) { cursor[i] = r.cursor; }
-};
-
-__device__ __forceinline__ uint64_t dbits(double x)
-{
-    return x != x ? 0x7ff8000000000000ull : (uint64_t)__double_as_longlong(x);
-}
-
-template <int KIND>
-__device__ __forceinline__ uint64_t trace_fold(const Level &L, const EnvRegs &e, uint64_t h, int action, const StepOut &o)
-{
-    h = fold64(h, (uint64_t)action | ((uint64_t)(o.done ? 1 : 0) << 8));
-    for (int c0 = 0; c0 < L.HW; c0 += 8) {
-        uint64_t w = 0;
-        for (int j = 0; j < 8 && c0 + j < L.HW; j++) w |= (uint64_t)render_cell<KIND>(L, e, c0 + j) << (8 * j);
-        h = fold64(h, w);
-    }
-    h = fold64(h, dbits(o.reward));
-    h = fold64(h, o.hidden_none ? 0x7ff8000000000000ull : dbits(o.hidden));
-    return h;
-}
-
-// episode statistics of one environment, kept in registers inside rollouts
-struct EpStats {
-    double last_return, last_perf, sum_return, sum_perf, sum_margin_pos, max_return, max_perf, max_margin;
-    unsigned long long counts;
-    __device__ __forceinline__ void load(const EnvArrays &A, int64_t i)
-    {
-        last_return = A.last_return[i]; last_perf = A.last_perf[i];
-        sum_return = A.sum_return[i]; sum_perf = A.sum_perf[i];
-        sum_margin_pos = A.sum_margin_pos[i]; max_return = A.max_return[i];
-        max_perf = A.max_perf[i]; max_margin = A.max_margin[i];
-        counts = A.counts[i];
-    }
-    __device__ __forceinline__ void store(const EnvArrays &A, int64_t i) const
-    {
-        A.last_return[i] = last_return; A.last_perf[i] = last_perf;
-        A.sum_return[i] = sum_return; A.sum_perf[i] = sum_perf;
-        A.sum_margin_pos[i] = sum_margin_pos; A.max_return[i] = max_return;
-        A.max_perf[i] = max_perf; A.max_margin[i] = max_margin;
-        A.counts[i] = counts;
-    }
-    // what track_metrics records at the end of an episode (meters.py:76-83)
-    __device__ __forceinline__ void episode_end(EnvRegs &e)
-    {
-        const double perf = e.hidden_cum;   // 0 when the episode produced none
-        const double margin = __dsub_rn(e.ep_return, perf);
-        const bool first = (counts & 0xFFFFFFFFFFull) == 0;
-        last_return = e.ep_return; last_perf = perf;
-        sum_return = __dadd_rn(sum_return, e.ep_return);
-        sum_perf = __dadd_rn(sum_perf, perf);
-        if (margin > 0) { sum_margin_pos = __dadd_rn(sum_margin_pos, margin); counts += 1ull << 40; }
-        if (first || e.ep_return > max_return) max_return = e.ep_return;
-        if (first || perf > max_perf) max_perf = perf;
-        if (first || margin > max_margin) max_margin = margin;
-        counts += 1ull;
-        e.flags |= SGK_F_PERF;
-    }
-};
-
-// Block-cooperative coalesced store of one board per thread: render into
-// shared memory, then write the block's contiguous byte range as 16 B words.
-template <int KIND>
-__device__ __forceinline__ void store_boards(const Level &L, const EnvRegs &e, bool valid, uint8_t *board_out,
-                                             int64_t n, uint8_t *smem)
-{
-    const int hw = L.HW;
-    if (valid)
-        for (int c = 0; c < hw; c++) smem[threadIdx.x * hw + c] = render_cell<KIND>(L, e, c);
-    __syncthreads();
-    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
-    const int64_t count = min((int64_t)blockDim.x, n - first);
-    const int64_t bytes = count * hw;
-    uint8_t *dst = board_out + first * hw;
-    if (count == blockDim.x && (((uintptr_t)dst) & 15) == 0 && (bytes & 15) == 0) {
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(smem);
-        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-        for (int64_t k = threadIdx.x; k < bytes / 16; k += blockDim.x) d4[k] = s4[k];
-    } else {
-        for (int64_t k = threadIdx.x; k < bytes; k += blockDim.x) dst[k] = smem[k];
-    }
-    __syncthreads();
-}
-
-#define SGK_BLOCK 128
 
 // ===================================================================== unfused env kernels
 struct EnvKernelArgs {
@@ -484,18 +334,35 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_shared_b(const __grid_
 
 // explore thresholds for lock-steps t0 .. t0+n-1: explore iff u53 < thr[k].
 // epsilon_at(k) per value.py:23-28,54-58, in float64 with IEEE division.
-__global__ void k_eps_thresholds(unsigned long long *thr, int64_t n, uint64_t t0, double one_minus_eps, int64_t anneal)
+__global__ void k_eps_thresholds(unsigned long long *thr, int64_t n, uint64_t t0, double one_minus_eps, int64_t anneal, int zero_first)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint64_t t = t0 + (uint64_t)k;
+    // tabular agent: epsilon forced to 0 at step 0 and for anneal == 1 (value.py:27-28);
+    // deep-Q agent: entry 0 (= 1.0) is used at step 0 (value.py:72-76)
+    const bool zero = zero_first && (t == 0 || anneal <= 1);
     double eps = 0.0;
-    if (t > 0 && anneal > 1) {
-        const uint64_t idx = t < (uint64_t)(anneal - 1) ? t : (uint64_t)(anneal - 1);
+    if (!zero) {
+        const uint64_t last = (uint64_t)(anneal > 1 ? anneal - 1 : 0);
+        const uint64_t idx = t < last ? t : last;
         eps = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(one_minus_eps, (double)idx), (double)anneal));
     }
     // u = X / 2^53 < eps  <=>  X < ceil(eps * 2^53)  (X integer, scaling exact)
     thr[k] = eps <= 0.0 ? 0ull : (unsigned long long)ceil(eps * 9007199254740992.0);
+}
+
+int ensure_eps_thresholds(unsigned long long **thr, int64_t *thr_cap, int64_t n_steps, uint64_t t0, double epsilon,
+                          int64_t anneal, int zero_first, cudaStream_t st)
+{
+    if (*thr_cap < n_steps) {
+        if (*thr) cudaFree(*thr);
+        *thr = nullptr; *thr_cap = 0;
+        CU(cudaMalloc(thr, (size_t)n_steps * 8));
+        *thr_cap = n_steps;
+    }
+    k_eps_thresholds<<<grid_for(n_steps, 256), 256, 0, st>>>(*thr, n_steps, t0, 1 - epsilon, anneal, zero_first);
+    return launch_check("k_eps_thresholds");
 }
 
 // ===================================================================== fused rollouts
@@ -978,8 +845,6 @@ __global__ void k_delta_apply(const TableView T, const uint64_t *keys_in, const 
 }
 
 // ===================================================================== C ABI: environments
-static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
-
 static EnvKernelArgs env_args(const sgk_env *env, uint64_t step)
 {
     EnvKernelArgs a;
@@ -987,25 +852,6 @@ static EnvKernelArgs env_args(const sgk_env *env, uint64_t step)
     a.seed = env->seed; a.step = step; a.words = env->replay_words; a.wpe = env->words_per_env;
     a.status = env->status; a.trace = env->trace;
     return a;
-}
-
-template <class T> struct type_tag { using type = T; };
-
-template <class F> static int by_kind(int kind, F f)
-{
-    switch (kind) {
-    case SGK_ENV_BOAT: return f(std::integral_constant<int, 0>());
-    case SGK_ENV_SOKOBAN: return f(std::integral_constant<int, 1>());
-    case SGK_ENV_TOMATO: return f(std::integral_constant<int, 2>());
-    }
-    return fail(SGK_EINVAL, "unknown environment kind");
-}
-
-static int launch_check(const char *what)
-{
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(SGK_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
-    return SGK_OK;
 }
 
 extern "C" int sgk_env_destroy(sgk_env *env)
@@ -1448,14 +1294,7 @@ extern "C" int sgk_tabq_restore_base(sgk_tabq *q, void *stream)
 // ===================================================================== C ABI: fused rollouts
 static int ensure_thresholds(sgk_tabq *q, int64_t n_steps, uint64_t t0, cudaStream_t st)
 {
-    if (q->thr_cap < n_steps) {
-        if (q->thr) cudaFree(q->thr);
-        q->thr = nullptr; q->thr_cap = 0;
-        CU(cudaMalloc(&q->thr, (size_t)n_steps * 8));
-        q->thr_cap = n_steps;
-    }
-    k_eps_thresholds<<<grid_for(n_steps, 256), 256, 0, st>>>(q->thr, n_steps, t0, 1 - q->epsilon, q->anneal);
-    return launch_check("k_eps_thresholds");
+    return ensure_eps_thresholds(&q->thr, &q->thr_cap, n_steps, t0, q->epsilon, q->anneal, 1, st);
 }
 
 static RolloutArgs rollout_args(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat)

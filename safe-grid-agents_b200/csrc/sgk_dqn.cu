@@ -1,0 +1,689 @@
+// sgk_dqn.cu -- the deep-Q agent of the rollout path.
+//
+// Replaces DeepQAgent (safe_grid_agents/common/agents/value.py:61-187), its
+// ReplayBuffer (common/utils/contain.py:8-22), dqn_warmup
+// (common/warmup.py:8-23) and the dqn_learn body (common/learn.py:29-58) for N
+// lock-step environments sharing ONE Q network:
+//
+//   per lock-step:  Q(s) for all N boards -> epsilon-greedy action ->
+//                   env.step -> append N transitions to the HBM replay ring ->
+//                   one optimiser step on a batch sampled from the ring
+//                   (online forward, target forward, loss, backward,
+//                   clip_grad_norm_(10), Adam(amsgrad)) -> target sync every
+//                   sync_every lock-steps.
+//
+// This file is the fp32 reference-semantics implementation: every GEMM is a
+// plain FFMA tile kernel, so results track torch's fp32 to rounding.  The
+// tcgen05 tensor-core forward lives in sgk_mlp_tc.cuh and is checked against
+// this path.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+
+#include "sgk_internal.cuh"
+
+#define DQN_MAX_LAYERS 6   // linear layers
+
+// ===================================================================== object
+struct sgk_dqn {
+    int device, kind, hw, n_actions;
+    int n_linear;                     // n_layers + 1 (value.py:148-158)
+    int dims[DQN_MAX_LAYERS + 1];     // n_in, hidden..., n_actions
+    int64_t w_off[DQN_MAX_LAYERS], b_off[DQN_MAX_LAYERS], n_params;
+    float *params[2];                 // 0 = Q, 1 = target_Q
+    float *grads, *adam_m, *adam_v, *adam_vmax;
+    int64_t adam_step;
+    // replay ring (contain.py:8-22): packed uint8 boards, SoA
+    int64_t cap, count;
+    uint8_t *r_s, *r_s2, *r_a, *r_term;
+    float *r_r;
+    // hyper-parameters (value.py:64-87, agent_parser_configs.yaml:26-63)
+    double lr, discount, epsilon;
+    int64_t anneal, sync_every, batch;
+    int bxb_loss;                     // reproduce the reference's B x B broadcast MSE
+    uint64_t seed;
+    // work buffers
+    int64_t rows_cap;                 // rows the activation buffers can hold
+    float *x, *x2, *act[DQN_MAX_LAYERS], *act_t[DQN_MAX_LAYERS], *dact[2], *y, *scalars;
+    uint8_t *b_a, *b_term; float *b_r; int64_t *b_idx;
+    float *partials; int64_t partials_cap;
+    float *q_env; uint8_t *boards_env; int64_t env_rows;
+    unsigned long long *thr; int64_t thr_cap;
+    int *status;
+};
+
+static const int SPLITS = 64;
+
+// ===================================================================== kernels
+// C[M,N] (+)= opA[M,K] * opB[K,N], fp32 FFMA, 64x64x16 tiles, 4x4 per thread.
+//   MODE 0 (NT): A[M,K] row-major, B given as W[N,K] row-major        (forward)
+//   MODE 1 (NN): A[M,K] row-major, B[K,N] row-major                   (dX = dY W)
+//   MODE 2 (TN): A given as [K,M] row-major, B[K,N] row-major         (dW = dY^T X)
+// blockIdx.z splits K; split z writes C + z * M * ldc (partials, reduced later).
+// Epilogue: + bias[n]; relu; * (mask[m,n] > 0).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const float *__restrict__ A, int lda,
+                                              const float *__restrict__ B, int ldb, float *__restrict__ C, int ldc,
+                                              const float *__restrict__ bias, int relu, const float *__restrict__ mask,
+                                              int ldmask, int k_chunk)
+{
+    __shared__ float As[16][65], Bs[16][65];
+    const int bm = blockIdx.y * 64, bn = blockIdx.x * 64;
+    const int k0 = blockIdx.z * k_chunk, k1 = min(K, k0 + k_chunk);
+    C += (size_t)blockIdx.z * M * ldc;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int kt = k0; kt < k1; kt += 16) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int e = threadIdx.x + r * 256;
+            int mm, kk;
+            if (MODE == 2) { mm = e & 63; kk = e >> 6; } else { mm = e >> 4; kk = e & 15; }
+            const int m = bm + mm, k = kt + kk;
+            float v = 0.f;
+            if (m < M && k < k1) v = MODE == 2 ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k];
+            As[kk][mm] = v;
+            int nn, kb;
+            if (MODE == 0) { nn = e >> 4; kb = e & 15; } else { nn = e & 63; kb = e >> 6; }
+            const int n = bn + nn, k2 = kt + kb;
+            float w = 0.f;
+            if (n < N && k2 < k1) w = MODE == 0 ? B[(size_t)n * ldb + k2] : B[(size_t)k2 * ldb + n];
+            Bs[kb][nn] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int m = bm + ty * 4 + i, n = bn + tx * 4 + j;
+            if (m < M && n < N) {
+                float v = acc[i][j];
+                if (bias) v += bias[n];
+                if (relu) v = fmaxf(v, 0.f);
+                if (mask) v = mask[(size_t)m * ldmask + n] > 0.f ? v : 0.f;
+                C[(size_t)m * ldc + n] = v;
+            }
+        }
+}
+
+// out[i] = sum over z of partial[z][i] in index order (deterministic)
+__global__ void k_reduce_splits(const float *partial, float *out, int64_t n, int splits)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int z = 0; z < splits; z++) s += partial[(size_t)z * n + i];
+    out[i] = s;
+}
+
+// column sums of dY[rows, n] for the bias gradients: partial[z][n]
+__global__ void k_colsum_partial(const float *dy, int rows, int n, int ld, float *partial, int chunk)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+    float s = 0.f;
+    for (int r = r0; r < r1; r++) s += dy[(size_t)r * ld + c];
+    partial[(size_t)blockIdx.y * n + c] = s;
+}
+
+__global__ void k_f64_to_f32(const double *in, float *out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+__global__ void k_u8_to_f32(const uint8_t *in, float *out, int64_t n)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        out[k] = (float)in[k];
+}
+
+// ReplayBuffer.sample (contain.py:19-22): `batch` indices uniform with
+// replacement over the filled part of the ring; gathers the batch.
+__global__ void k_replay_sample(uint64_t seed, uint64_t step, int64_t fill, int64_t batch, int hw,
+                                const uint8_t *r_s, const uint8_t *r_s2, const uint8_t *r_a, const float *r_r,
+                                const uint8_t *r_term, float *x, float *x2, uint8_t *b_a, float *b_r, uint8_t *b_term,
+                                int64_t *b_idx)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    uint32_t w[4];
+    philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)step, 0x40u | ((uint32_t)((step >> 32) & 0xFFFFFF) << 8),
+                  (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5bd1e995u, w);
+    const uint64_t u = ((uint64_t)w[0] << 32) | w[1];
+    const int64_t idx = (int64_t)(u % (uint64_t)fill);
+    b_idx[b] = idx;
+    for (int c = 0; c < hw; c++) {
+        x[b * hw + c] = (float)r_s[idx * hw + c];
+        x2[b * hw + c] = (float)r_s2[idx * hw + c];
+    }
+    b_a[b] = r_a[idx];
+    b_r[b] = r_r[idx];
+    b_term[b] = r_term[idx];
+}
+
+__global__ void k_replay_add(int64_t cap, int64_t pos0, int64_t n, int hw, const uint8_t *s, const uint8_t *a,
+                             const double *r, const uint8_t *s2, const uint8_t *term, uint8_t *r_s, uint8_t *r_s2,
+                             uint8_t *r_a, float *r_r, uint8_t *r_term)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t slot = (pos0 + i) % cap;
+    for (int c = 0; c < hw; c++) { r_s[slot * hw + c] = s[i * hw + c]; r_s2[slot * hw + c] = s2[i * hw + c]; }
+    r_a[slot] = a[i] & 3;
+    r_r[slot] = (float)r[i];
+    r_term[slot] = term[i] ? 1 : 0;
+}
+
+// expected_Qs = discount * max_a target_Q(s') [terminals -> 0] + rewards (value.py:120-122)
+__global__ void k_td_target(const float *qt, int n_actions, const float *r, const uint8_t *term, float discount, float *y,
+                            int64_t batch)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    float m = qt[b * n_actions];
+    for (int a = 1; a < n_actions; a++) m = fmaxf(m, qt[b * n_actions + a]);
+    if (term[b]) m = 0.f;
+    y[b] = discount * m + r[b];
+}
+
+// loss and dL/dQ.  bxb: F.mse_loss(Qs[B,1], y[B]) broadcasts to B x B
+// (value.py:119-123): L = mean_ij (q_i - y_j)^2, dL/dq_i = (2/B)(q_i - mean(y)).
+// Otherwise the per-sample TD loss.  One block, deterministic tree.
+// scalars[0] = loss.
+__global__ void __launch_bounds__(1024) k_loss_grad(const float *q, const uint8_t *a, const float *y, int n_actions,
+                                                    int64_t batch, int bxb, float *dq, float *scalars)
+{
+    __shared__ double sh[4][1024];
+    double sq = 0, sq2 = 0, sy = 0, sy2 = 0, sd2 = 0;
+    for (int64_t b = threadIdx.x; b < batch; b += blockDim.x) {
+        const double qv = q[b * n_actions + a[b]], yv = y[b];
+        sq += qv; sq2 += qv * qv; sy += yv; sy2 += yv * yv; sd2 += (qv - yv) * (qv - yv);
+    }
+    double v[4] = {sq, sq2, sy, bxb ? sy2 : sd2};
+    for (int k = 0; k < 4; k++) sh[k][threadIdx.x] = v[k];
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) for (int k = 0; k < 4; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+        __syncthreads();
+    }
+    const double B = (double)batch;
+    const double mq = sh[0][0] / B, mq2 = sh[1][0] / B, my = sh[2][0] / B, last = sh[3][0] / B;
+    if (threadIdx.x == 0) scalars[0] = (float)(bxb ? (mq2 - 2.0 * mq * my + last) : last);
+    for (int64_t b = threadIdx.x; b < batch; b += blockDim.x) {
+        const float qv = q[b * n_actions + a[b]];
+        const float tgt = bxb ? (float)my : y[b];
+        for (int k = 0; k < n_actions; k++) dq[b * n_actions + k] = 0.f;
+        dq[b * n_actions + a[b]] = (float)(2.0 / B) * (qv - tgt);
+    }
+}
+
+// total gradient norm (clip_grad_norm_, value.py:128): scalars[1] = norm,
+// scalars[2] = clip coefficient min(1, 10 / (norm + 1e-6)).
+__global__ void __launch_bounds__(1024) k_grad_norm(const float *g, int64_t n, float max_norm, float *scalars)
+{
+    __shared__ double sh[1024];
+    double s = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)g[i] * g[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 512; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float norm = (float)sqrt(sh[0]);
+        scalars[1] = norm;
+        scalars[2] = fminf(1.f, max_norm / (norm + 1e-6f));
+    }
+}
+
+// torch.optim.Adam(amsgrad=True) single-tensor update, defaults betas
+// (0.9, 0.999), eps 1e-8, no weight decay (value.py:87).
+__global__ void k_adam_amsgrad(float *p, const float *g, float *m, float *v, float *vmax, int64_t n, const float *scalars,
+                               float lr, float bc1, float bc2_sqrt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float grad = g[i] * scalars[2];
+    const float mi = m[i] + (grad - m[i]) * (float)(1.0 - 0.9);    // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * 0.999f + (float)(1.0 - 0.999) * grad * grad;
+    const float vm = fmaxf(vmax[i], vi);
+    m[i] = mi; v[i] = vi; vmax[i] = vm;
+    const float denom = sqrtf(vm) / bc2_sqrt + 1e-8f;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+}
+
+// nn.Linear default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias
+__global__ void k_init_params(float *p, int64_t off, int64_t n, float bound, uint64_t seed)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[4];
+    const uint64_t c = (uint64_t)(off + i);
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), 0x9e3779b9u, 0x51u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    const float u = (float)(w[0] >> 8) * (1.0f / 16777216.0f);
+    p[off + i] = (2.f * u - 1.f) * bound;
+}
+
+// One lock-step of acting for every environment: epsilon-greedy on the Q row
+// (value.py:94-111: argmax w.p. 1-eps+eps/A, else uniform == "u < eps ->
+// uniform action"), env.step, transition appended to the replay ring, reset
+// when done (train.py:62-70).  random_policy: dqn_warmup (warmup.py:8-23).
+struct DqnStepArgs {
+    Level level;
+    EnvArrays arr;
+    int64_t n, env_id0;
+    uint64_t seed, step;
+    const uint32_t *words;
+    int64_t wpe;
+    int *status;
+    const float *q;
+    unsigned long long thr;
+    int random_policy;
+    int64_t cap, pos0;
+    uint8_t *r_s, *r_s2, *r_a, *r_term;
+    float *r_r;
+};
+
+template <int KIND, class Rng>
+__global__ void __launch_bounds__(SGK_BLOCK) k_dqn_step(const __grid_constant__ DqnStepArgs p)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const Level &L = p.level;
+    EnvRegs e;
+    unpack_core(p.arr.core[i], e);
+    e.ep_return = p.arr.ep_return[i];
+    e.hidden_cum = p.arr.hidden_cum[i];
+    Rng rng;
+    RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+    rng.set_step(p.step);
+    int a;
+    if (p.random_policy) {
+        a = rng.random_action();
+    } else {
+        const float4 q = *reinterpret_cast<const float4 *>(p.q + i * 4);
+        a = 0; float m = q.x;
+        if (q.y > m) { m = q.y; a = 1; }
+        if (q.z > m) { m = q.z; a = 2; }
+        if (q.w > m) { m = q.w; a = 3; }
+        if (rng.agent_uniform() < p.thr) a = rng.agent_choice();
+    }
+    const int64_t slot = (p.pos0 + i) % p.cap;
+    uint8_t *s = p.r_s + slot * L.HW, *s2 = p.r_s2 + slot * L.HW;
+    for (int c = 0; c < L.HW; c++) s[c] = render_cell<KIND>(L, e, c);
+    const StepOut o = env_step<KIND>(L, e, a, rng);
+    for (int c = 0; c < L.HW; c++) s2[c] = render_cell<KIND>(L, e, c);
+    p.r_a[slot] = (uint8_t)a;
+    p.r_r[slot] = (float)o.reward;
+    p.r_term[slot] = o.done ? 1 : 0;
+    if (o.done) {
+        EpStats st;
+        st.load(p.arr, i);
+        st.episode_end(e);
+        st.store(p.arr, i);
+        rng.set_step(p.step + 1);
+        env_reset<KIND>(L, e, rng);
+    }
+    RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+    if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
+    p.arr.core[i] = pack_core(e);
+    p.arr.ep_return[i] = e.ep_return;
+    p.arr.hidden_cum[i] = e.hidden_cum;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(SGK_BLOCK) k_dqn_render_f32(const __grid_constant__ Level L, const uint64_t *core, int64_t n, float *x)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvRegs e;
+    unpack_core(core[i], e);
+    for (int c = 0; c < L.HW; c++) x[i * L.HW + c] = (float)render_cell<KIND>(L, e, c);
+}
+
+// ===================================================================== host helpers
+static int gemm(int mode, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+                const float *bias, int relu, const float *mask, int ldmask, int splits, cudaStream_t st)
+{
+    const int k_chunk = ((K + splits - 1) / splits + 15) / 16 * 16;
+    const dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+    if (mode == 0) k_gemm<0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+    else if (mode == 1) k_gemm<1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+    else k_gemm<2><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+    return launch_check("k_gemm");
+}
+
+static int ensure_rows(sgk_dqn *d, int64_t rows)
+{
+    if (d->rows_cap >= rows) return SGK_OK;
+    auto re = [&](float **p, size_t n) -> int {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        CU(cudaMalloc(p, n * sizeof(float)));
+        return SGK_OK;
+    };
+    int rc;
+    int widest = 0;
+    for (int l = 0; l <= d->n_linear; l++) widest = d->dims[l] > widest ? d->dims[l] : widest;
+    if ((rc = re(&d->x, (size_t)rows * d->dims[0]))) return rc;
+    if ((rc = re(&d->x2, (size_t)rows * d->dims[0]))) return rc;
+    for (int l = 0; l < d->n_linear; l++) {
+        if ((rc = re(&d->act[l], (size_t)rows * d->dims[l + 1]))) return rc;
+        if ((rc = re(&d->act_t[l], (size_t)rows * d->dims[l + 1]))) return rc;
+    }
+    for (int k = 0; k < 2; k++) if ((rc = re(&d->dact[k], (size_t)rows * widest))) return rc;
+    if ((rc = re(&d->y, (size_t)rows))) return rc;
+    if ((rc = re(&d->b_r, (size_t)rows))) return rc;
+    if (d->b_a) cudaFree(d->b_a);
+    if (d->b_term) cudaFree(d->b_term);
+    if (d->b_idx) cudaFree(d->b_idx);
+    CU(cudaMalloc(&d->b_a, (size_t)rows));
+    CU(cudaMalloc(&d->b_term, (size_t)rows));
+    CU(cudaMalloc(&d->b_idx, (size_t)rows * 8));
+    d->rows_cap = rows;
+    return SGK_OK;
+}
+
+// forward through network `which` on x[rows, n_in] -> acts[l]; returns Q in acts[n_linear-1]
+static int forward(sgk_dqn *d, int which, const float *x, int64_t rows, float *const *acts, cudaStream_t st)
+{
+    const float *in = x;
+    for (int l = 0; l < d->n_linear; l++) {
+        const int K = d->dims[l], N = d->dims[l + 1];
+        const float *W = d->params[which] + d->w_off[l], *b = d->params[which] + d->b_off[l];
+        int rc = gemm(0, (int)rows, N, K, in, K, W, K, acts[l], N, b, l + 1 < d->n_linear, nullptr, 0, 1, st);
+        if (rc != SGK_OK) return rc;
+        in = acts[l];
+    }
+    return SGK_OK;
+}
+
+// ===================================================================== C ABI
+extern "C" int sgk_dqn_destroy(sgk_dqn *d)
+{
+    if (!d) return SGK_OK;
+    DeviceGuard g(d->device);
+    void *ptrs[] = {d->params[0], d->params[1], d->grads, d->adam_m, d->adam_v, d->adam_vmax, d->r_s, d->r_s2, d->r_a,
+                    d->r_term, d->r_r, d->x, d->x2, d->dact[0], d->dact[1], d->y, d->scalars, d->b_a, d->b_term, d->b_r,
+                    d->b_idx, d->partials, d->q_env, d->boards_env, d->thr, d->status};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int l = 0; l < DQN_MAX_LAYERS; l++) { if (d->act[l]) cudaFree(d->act[l]); if (d->act_t[l]) cudaFree(d->act_t[l]); }
+    delete d;
+    return SGK_OK;
+}
+
+extern "C" int sgk_dqn_create(const sgk_env *env, int n_layers, int n_hidden, int64_t replay_capacity, int64_t batch_size,
+                              uint64_t seed, sgk_dqn **out)
+{
+    REQUIRE(env != nullptr && out != nullptr, "bad argument");
+    REQUIRE(n_layers >= 1 && n_layers + 1 <= DQN_MAX_LAYERS, "n_layers out of range");
+    REQUIRE(n_hidden >= 1 && n_hidden <= 4096, "n_hidden out of range");
+    REQUIRE(replay_capacity >= 1 && batch_size >= 1, "replay_capacity and batch_size must be positive");
+    DeviceGuard g(env->device);
+    sgk_dqn *d = new (std::nothrow) sgk_dqn();
+    REQUIRE(d != nullptr, "out of host memory");
+    memset(d, 0, sizeof(*d));
+    d->device = env->device; d->kind = env->level.kind; d->hw = env->level.HW; d->n_actions = SGK_NA;
+    d->n_linear = n_layers + 1;
+    // n_input: the reference multiplies only two of the three (C,H,W) dims
+    // (value.py:66-67, a shape bug); the board has C*H*W cells
+    d->dims[0] = d->hw;
+    for (int l = 1; l < d->n_linear; l++) d->dims[l] = n_hidden;
+    d->dims[d->n_linear] = d->n_actions;
+    int64_t off = 0;
+    for (int l = 0; l < d->n_linear; l++) {
+        d->w_off[l] = off; off += (int64_t)d->dims[l] * d->dims[l + 1];
+        d->b_off[l] = off; off += d->dims[l + 1];
+    }
+    d->n_params = off;
+    d->cap = replay_capacity; d->batch = batch_size; d->seed = seed;
+    d->lr = 1e-3; d->discount = 0.99; d->epsilon = 0.01; d->anneal = 100000; d->sync_every = 10000; d->bxb_loss = 1;
+    const size_t pb = (size_t)d->n_params * sizeof(float);
+    bool ok = true;
+    for (int k = 0; k < 2; k++) ok = ok && cudaMalloc(&d->params[k], pb) == cudaSuccess;
+    float **zs[] = {&d->grads, &d->adam_m, &d->adam_v, &d->adam_vmax};
+    for (float **z : zs) ok = ok && cudaMalloc(z, pb) == cudaSuccess && cudaMemset(*z, 0, pb) == cudaSuccess;
+    const size_t rb = (size_t)d->cap * d->hw;
+    ok = ok && cudaMalloc(&d->r_s, rb) == cudaSuccess && cudaMalloc(&d->r_s2, rb) == cudaSuccess &&
+         cudaMalloc(&d->r_a, (size_t)d->cap) == cudaSuccess && cudaMalloc(&d->r_term, (size_t)d->cap) == cudaSuccess &&
+         cudaMalloc(&d->r_r, (size_t)d->cap * 4) == cudaSuccess && cudaMalloc(&d->scalars, 8 * sizeof(float)) == cudaSuccess &&
+         cudaMalloc(&d->status, sizeof(int)) == cudaSuccess && cudaMemset(d->status, 0, sizeof(int)) == cudaSuccess;
+    if (!ok) { sgk_dqn_destroy(d); return fail(SGK_ECUDA, "cudaMalloc failed for the deep-Q agent"); }
+    for (int l = 0; l < d->n_linear; l++) {
+        const float bound = 1.0f / sqrtf((float)d->dims[l]);
+        const int64_t nw = (int64_t)d->dims[l] * d->dims[l + 1], nb = d->dims[l + 1];
+        k_init_params<<<grid_for(nw, 256), 256>>>(d->params[0], d->w_off[l], nw, bound, seed);
+        k_init_params<<<grid_for(nb, 256), 256>>>(d->params[0], d->b_off[l], nb, bound, seed);
+        // target_Q is an independently initialised network (value.py:83)
+        k_init_params<<<grid_for(nw, 256), 256>>>(d->params[1], d->w_off[l], nw, bound, seed ^ 0xabcdef12345ull);
+        k_init_params<<<grid_for(nb, 256), 256>>>(d->params[1], d->b_off[l], nb, bound, seed ^ 0xabcdef12345ull);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) { sgk_dqn_destroy(d); return fail(SGK_ECUDA, "parameter init failed"); }
+    *out = d;
+    return SGK_OK;
+}
+
+extern "C" int sgk_dqn_configure(sgk_dqn *d, double lr, double discount, double epsilon, int64_t epsilon_anneal,
+                                 int64_t sync_every, int bxb_loss)
+{
+    REQUIRE(d != nullptr, "d is NULL");
+    REQUIRE(epsilon_anneal >= 1 && sync_every >= 1, "epsilon_anneal and sync_every must be >= 1");
+    d->lr = lr; d->discount = discount; d->epsilon = epsilon; d->anneal = epsilon_anneal; d->sync_every = sync_every;
+    d->bxb_loss = bxb_loss ? 1 : 0;
+    return SGK_OK;
+}
+
+extern "C" int64_t sgk_dqn_param_count(const sgk_dqn *d) { return d ? d->n_params : 0; }
+extern "C" int64_t sgk_dqn_replay_count(const sgk_dqn *d) { return d ? (d->count < d->cap ? d->count : d->cap) : 0; }
+
+extern "C" int sgk_dqn_get_params(const sgk_dqn *d, int which, float *out, void *stream)
+{
+    REQUIRE(d != nullptr && out != nullptr && (which == 0 || which == 1), "bad argument");
+    DeviceGuard g(d->device);
+    CU(cudaMemcpyAsync(out, d->params[which], (size_t)d->n_params * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}
+
+extern "C" int sgk_dqn_set_params(sgk_dqn *d, int which, const float *in, void *stream)
+{
+    REQUIRE(d != nullptr && in != nullptr && (which == 0 || which == 1), "bad argument");
+    DeviceGuard g(d->device);
+    CU(cudaMemcpyAsync(d->params[which], in, (size_t)d->n_params * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}
+
+extern "C" int sgk_dqn_sync_target(sgk_dqn *d, void *stream)
+{
+    REQUIRE(d != nullptr, "d is NULL");
+    DeviceGuard g(d->device);
+    CU(cudaMemcpyAsync(d->params[1], d->params[0], (size_t)d->n_params * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}
+
+extern "C" int sgk_dqn_qvalues(sgk_dqn *d, int which, const uint8_t *boards, int64_t n, float *q_out, void *stream)
+{
+    REQUIRE(d != nullptr && boards && q_out && n > 0 && (which == 0 || which == 1), "bad argument");
+    DeviceGuard g(d->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_rows(d, n);
+    if (rc != SGK_OK) return rc;
+    k_u8_to_f32<<<(unsigned)std::min<int64_t>((n * d->hw + 255) / 256, 148 * 16), 256, 0, st>>>(boards, d->x, n * d->hw);
+    rc = forward(d, which, d->x, n, d->act, st);
+    if (rc != SGK_OK) return rc;
+    CU(cudaMemcpyAsync(q_out, d->act[d->n_linear - 1], (size_t)n * d->n_actions * 4, cudaMemcpyDeviceToDevice, st));
+    return SGK_OK;
+}
+
+extern "C" int sgk_dqn_replay_add(sgk_dqn *d, const uint8_t *s, const uint8_t *a, const double *r, const uint8_t *s2,
+                                  const uint8_t *term, int64_t n, void *stream)
+{
+    REQUIRE(d != nullptr && s && a && r && s2 && term && n > 0, "bad argument");
+    REQUIRE(n <= d->cap, "more transitions than the ring holds");
+    DeviceGuard g(d->device);
+    k_replay_add<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(d->cap, d->count % d->cap, n, d->hw, s, a, r, s2, term,
+                                                                     d->r_s, d->r_s2, d->r_a, d->r_r, d->r_term);
+    d->count += n;
+    return launch_check("k_replay_add");
+}
+
+// loss, backward, clip, Adam on the batch already staged in x / x2 / b_a / b_r / b_term
+static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
+{
+    const int L = d->n_linear, A = d->n_actions;
+    int rc;
+    if ((rc = forward(d, 0, d->x, B, d->act, st))) return rc;        // Qs = Q(states)
+    if ((rc = forward(d, 1, d->x2, B, d->act_t, st))) return rc;     // target_Q(successors)
+    k_td_target<<<grid_for(B, 256), 256, 0, st>>>(d->act_t[L - 1], A, d->b_r, d->b_term, (float)d->discount, d->y, B);
+    float *dcur = d->dact[0], *dnext = d->dact[1];
+    k_loss_grad<<<1, 1024, 0, st>>>(d->act[L - 1], d->b_a, d->y, A, B, d->bxb_loss, dcur, d->scalars);
+    if ((rc = launch_check("k_loss_grad"))) return rc;
+    // partial buffer for the split-K weight / bias gradients
+    int64_t need = 0;
+    for (int l = 0; l < L; l++) need = std::max<int64_t>(need, (int64_t)SPLITS * (d->dims[l] + 1) * d->dims[l + 1]);
+    if (d->partials_cap < need) {
+        if (d->partials) cudaFree(d->partials);
+        d->partials = nullptr; d->partials_cap = 0;
+        CU(cudaMalloc(&d->partials, (size_t)need * 4));
+        d->partials_cap = need;
+    }
+    for (int l = L - 1; l >= 0; l--) {
+        const int K = d->dims[l], N = d->dims[l + 1];
+        const float *in = l == 0 ? d->x : d->act[l - 1];
+        // dW[N,K] = dY^T[N,B] * in[B,K], split over the batch
+        if ((rc = gemm(2, N, K, (int)B, dcur, N, in, K, d->partials, K, nullptr, 0, nullptr, 0, SPLITS, st))) return rc;
+        k_reduce_splits<<<grid_for((int64_t)N * K, 256), 256, 0, st>>>(d->partials, d->grads + d->w_off[l], (int64_t)N * K, SPLITS);
+        const int chunk = (int)((B + SPLITS - 1) / SPLITS);
+        k_colsum_partial<<<dim3((N + 127) / 128, SPLITS), 128, 0, st>>>(dcur, (int)B, N, N, d->partials, chunk);
+        k_reduce_splits<<<grid_for(N, 256), 256, 0, st>>>(d->partials, d->grads + d->b_off[l], N, SPLITS);
+        if (l > 0) {
+            // dX[B,K] = dY[B,N] * W[N,K], masked by relu'(in)
+            const float *W = d->params[0] + d->w_off[l];
+            if ((rc = gemm(1, (int)B, K, N, dcur, N, W, K, dnext, K, nullptr, 0, in, K, 1, st))) return rc;
+            float *t = dcur; dcur = dnext; dnext = t;
+        }
+    }
+    k_grad_norm<<<1, 1024, 0, st>>>(d->grads, d->n_params, 10.f, d->scalars);
+    d->adam_step += 1;
+    const double bc1 = 1.0 - pow(0.9, (double)d->adam_step), bc2 = 1.0 - pow(0.999, (double)d->adam_step);
+    k_adam_amsgrad<<<grid_for(d->n_params, 256), 256, 0, st>>>(d->params[0], d->grads, d->adam_m, d->adam_v, d->adam_vmax,
+                                                               d->n_params, d->scalars, (float)d->lr, (float)bc1, (float)sqrt(bc2));
+    if ((rc = launch_check("k_adam_amsgrad"))) return rc;
+    if (loss_out) CU(cudaMemcpyAsync(loss_out, d->scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return SGK_OK;
+}
+
+extern "C" int sgk_dqn_learn_batch(sgk_dqn *d, const uint8_t *s, const uint8_t *a, const double *r, const uint8_t *s2,
+                                   const uint8_t *term, int64_t n, float *loss_out, void *stream)
+{
+    REQUIRE(d != nullptr && s && a && r && s2 && term && n > 0, "bad argument");
+    DeviceGuard g(d->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_rows(d, n);
+    if (rc != SGK_OK) return rc;
+    k_u8_to_f32<<<(unsigned)std::min<int64_t>((n * d->hw + 255) / 256, 148 * 16), 256, 0, st>>>(s, d->x, n * d->hw);
+    k_u8_to_f32<<<(unsigned)std::min<int64_t>((n * d->hw + 255) / 256, 148 * 16), 256, 0, st>>>(s2, d->x2, n * d->hw);
+    CU(cudaMemcpyAsync(d->b_a, a, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(d->b_term, term, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    // rewards arrive as float64 (the env's dtype); the network works in float32
+    k_f64_to_f32<<<grid_for(n, 256), 256, 0, st>>>(r, d->b_r, n);
+    return learn_staged(d, n, loss_out, st);
+}
+
+extern "C" int sgk_dqn_learn(sgk_dqn *d, uint64_t step, float *loss_out, void *stream)
+{
+    REQUIRE(d != nullptr, "d is NULL");
+    REQUIRE(d->count > 0, "the replay ring is empty");
+    DeviceGuard g(d->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t B = d->batch, fill = d->count < d->cap ? d->count : d->cap;
+    int rc = ensure_rows(d, B);
+    if (rc != SGK_OK) return rc;
+    k_replay_sample<<<grid_for(B, 128), 128, 0, st>>>(d->seed, step, fill, B, d->hw, d->r_s, d->r_s2, d->r_a, d->r_r, d->r_term,
+                                                      d->x, d->x2, d->b_a, d->b_r, d->b_term, d->b_idx);
+    if ((rc = launch_check("k_replay_sample"))) return rc;
+    return learn_staged(d, B, loss_out, st);
+}
+
+extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64_t t0, int learn, void *stream)
+{
+    REQUIRE(env != nullptr && d != nullptr && n_steps > 0, "bad argument");
+    REQUIRE(env->device == d->device && env->level.kind == d->kind, "agent was created for a different environment kind");
+    REQUIRE(env->n <= d->cap, "replay capacity is smaller than one lock-step of transitions");
+    DeviceGuard g(env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_rows(d, std::max<int64_t>(env->n, d->batch));
+    if (rc != SGK_OK) return rc;
+    if (d->env_rows < env->n) {
+        if (d->q_env) cudaFree(d->q_env);
+        d->q_env = nullptr; d->env_rows = 0;
+        CU(cudaMalloc(&d->q_env, (size_t)env->n * d->n_actions * 4));
+        d->env_rows = env->n;
+    }
+    const bool replay = env->rng_mode == SGK_RNG_REPLAY;
+    for (int64_t k = 0; k < n_steps; k++) {
+        const uint64_t t = t0 + (uint64_t)k;
+        DqnStepArgs a;
+        a.level = env->level; a.arr = env->arr; a.n = env->n; a.env_id0 = env->env_id0; a.seed = env->seed; a.step = t;
+        a.words = env->replay_words; a.wpe = env->words_per_env; a.status = env->status;
+        a.random_policy = learn ? 0 : 1;
+        a.cap = d->cap; a.pos0 = d->count % d->cap;
+        a.r_s = d->r_s; a.r_s2 = d->r_s2; a.r_a = d->r_a; a.r_term = d->r_term; a.r_r = d->r_r;
+        a.q = d->q_env; a.thr = 0;
+        if (learn) {
+            // act: Q(s) for every environment's current board
+            rc = by_kind(env->level.kind, [&](auto K) {
+                constexpr int KIND = decltype(K)::value;
+                k_dqn_render_f32<KIND><<<grid_for(env->n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(env->level, env->arr.core, env->n, d->x);
+                return launch_check("k_dqn_render_f32");
+            });
+            if (rc != SGK_OK) return rc;
+            if ((rc = forward(d, 0, d->x, env->n, d->act, st))) return rc;
+            CU(cudaMemcpyAsync(d->q_env, d->act[d->n_linear - 1], (size_t)env->n * d->n_actions * 4, cudaMemcpyDeviceToDevice, st));
+            // epsilon of this agent-step: DeepQAgent keeps entry 0 (value.py:72-76)
+            const int64_t last = d->anneal > 1 ? d->anneal - 1 : 0;
+            const int64_t idx = (int64_t)t < last ? (int64_t)t : last;
+            const volatile double scaled = (1 - d->epsilon) * (double)idx;
+            const volatile double frac = scaled / (double)d->anneal;
+            const double eps = 1.0 - frac;
+            a.thr = eps <= 0.0 ? 0ull : (unsigned long long)ceil(eps * 9007199254740992.0);
+        }
+        rc = by_kind(env->level.kind, [&](auto K) {
+            constexpr int KIND = decltype(K)::value;
+            if (replay) k_dqn_step<KIND, ReplayStream><<<grid_for(env->n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a);
+            else k_dqn_step<KIND, PhiloxStream><<<grid_for(env->n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a);
+            return launch_check("k_dqn_step");
+        });
+        if (rc != SGK_OK) return rc;
+        d->count += env->n;
+        if (learn) {
+            if ((rc = sgk_dqn_learn(d, t, nullptr, stream))) return rc;
+            if (t % (uint64_t)d->sync_every == (uint64_t)d->sync_every - 1)   // learn.py:55-56
+                if ((rc = sgk_dqn_sync_target(d, stream))) return rc;
+        }
+    }
+    return SGK_OK;
+}
+
+extern "C" int sgk_dqn_last_scalars(const sgk_dqn *d, float *out3, void *stream)
+{
+    REQUIRE(d != nullptr && out3 != nullptr, "bad argument");
+    DeviceGuard g(d->device);
+    CU(cudaMemcpyAsync(out3, d->scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}

