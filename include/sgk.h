@@ -283,6 +283,11 @@ int sgk_dqn_learn(sgk_dqn *d, uint64_t step, float *loss_out, void *stream);
 int sgk_dqn_learn_batch(sgk_dqn *d, const uint8_t *s, const uint8_t *a, const double *r, const uint8_t *s2,
                         const uint8_t *term, int64_t n, float *loss_out, void *stream);
 int sgk_dqn_last_scalars(const sgk_dqn *d, float *out3, void *stream);
+/* Run every forward pass (acting, online and target networks in learn) as one
+ * fused tcgen05 kernel: TF32 operands, fp32 accumulation in TMEM.  Covers the
+ * reference's default architecture (n_layers 2, n_hidden <= 100).  Off by
+ * default: the fp32 path is the parity reference. */
+int sgk_dqn_set_tensor_cores(sgk_dqn *d, int enabled);
 /* n_steps lock-steps of the dqn_learn body (common/learn.py:29-58) for every
  * environment: act_explore, env.step, replay.add, learn, update_epsilon,
  * target sync every sync_every steps, reset when done.  learn == 0 runs the

@@ -22,6 +22,7 @@
 #include <new>
 
 #include "sgk_internal.cuh"
+#include "sgk_mlp_tc.cuh"
 
 #define DQN_MAX_LAYERS 6   // linear layers
 
@@ -51,6 +52,9 @@ struct sgk_dqn {
     float *q_env; uint8_t *boards_env; int64_t env_rows;
     unsigned long long *thr; int64_t thr_cap;
     int *status;
+    int use_tc;                       // forward passes on tcgen05 (TF32) instead of fp32 FFMA
+    uint8_t *xb, *xb2;                // uint8 copies of the staged batch (tensor-core input)
+    int sm_count;
 };
 
 static const int SPLITS = 64;
@@ -156,8 +160,8 @@ __global__ void k_u8_to_f32(const uint8_t *in, float *out, int64_t n)
 // replacement over the filled part of the ring; gathers the batch.
 __global__ void k_replay_sample(uint64_t seed, uint64_t step, int64_t fill, int64_t batch, int hw,
                                 const uint8_t *r_s, const uint8_t *r_s2, const uint8_t *r_a, const float *r_r,
-                                const uint8_t *r_term, float *x, float *x2, uint8_t *b_a, float *b_r, uint8_t *b_term,
-                                int64_t *b_idx)
+                                const uint8_t *r_term, float *x, float *x2, uint8_t *xb, uint8_t *xb2, uint8_t *b_a, float *b_r,
+                                uint8_t *b_term, int64_t *b_idx)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
@@ -168,8 +172,9 @@ __global__ void k_replay_sample(uint64_t seed, uint64_t step, int64_t fill, int6
     const int64_t idx = (int64_t)(u % (uint64_t)fill);
     b_idx[b] = idx;
     for (int c = 0; c < hw; c++) {
-        x[b * hw + c] = (float)r_s[idx * hw + c];
-        x2[b * hw + c] = (float)r_s2[idx * hw + c];
+        const uint8_t v = r_s[idx * hw + c], v2 = r_s2[idx * hw + c];
+        x[b * hw + c] = (float)v; x2[b * hw + c] = (float)v2;
+        xb[b * hw + c] = v; xb2[b * hw + c] = v2;
     }
     b_a[b] = r_a[idx];
     b_r[b] = r_r[idx];
@@ -357,6 +362,16 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_render_f32(const __grid_const
     for (int c = 0; c < L.HW; c++) x[i * L.HW + c] = (float)render_cell<KIND>(L, e, c);
 }
 
+template <int KIND>
+__global__ void __launch_bounds__(SGK_BLOCK) k_dqn_render_u8(const __grid_constant__ Level L, const uint64_t *core, int64_t n, uint8_t *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvRegs e;
+    unpack_core(core[i], e);
+    for (int c = 0; c < L.HW; c++) out[i * L.HW + c] = render_cell<KIND>(L, e, c);
+}
+
 // ===================================================================== host helpers
 static int gemm(int mode, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C, int ldc,
                 const float *bias, int relu, const float *mask, int ldmask, int splits, cudaStream_t st)
@@ -396,6 +411,10 @@ static int ensure_rows(sgk_dqn *d, int64_t rows)
     CU(cudaMalloc(&d->b_a, (size_t)rows));
     CU(cudaMalloc(&d->b_term, (size_t)rows));
     CU(cudaMalloc(&d->b_idx, (size_t)rows * 8));
+    if (d->xb) cudaFree(d->xb);
+    if (d->xb2) cudaFree(d->xb2);
+    CU(cudaMalloc(&d->xb, (size_t)rows * d->dims[0]));
+    CU(cudaMalloc(&d->xb2, (size_t)rows * d->dims[0]));
     d->rows_cap = rows;
     return SGK_OK;
 }
@@ -414,6 +433,34 @@ static int forward(sgk_dqn *d, int which, const float *x, int64_t rows, float *c
     return SGK_OK;
 }
 
+static bool tc_supported(const sgk_dqn *d)
+{
+    return d->n_linear == 3 && d->dims[1] == d->dims[2] && d->dims[1] <= 100 && d->dims[0] <= tc::MAX_K_IN &&
+           d->n_actions <= 8;
+}
+
+// the fused tensor-core forward: boards (uint8) -> Q, optionally H1 / H2 in fp32
+static int forward_tc(sgk_dqn *d, int which, const uint8_t *boards, int64_t rows, float *q_out, float *h1, float *h2,
+                      cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(tc::k_mlp_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem::TOTAL));
+        attr_set = true;
+    }
+    tc::Params p;
+    const float *P = d->params[which];
+    p.w1 = P + d->w_off[0]; p.b1 = P + d->b_off[0];
+    p.w2 = P + d->w_off[1]; p.b2 = P + d->b_off[1];
+    p.w3 = P + d->w_off[2]; p.b3 = P + d->b_off[2];
+    p.n_in = d->dims[0]; p.n_hidden = d->dims[1]; p.n_out = d->n_actions;
+    p.boards = boards; p.rows = rows; p.q_out = q_out; p.h1_out = h1; p.h2_out = h2;
+    const int64_t tiles = (rows + tc::TILE_M - 1) / tc::TILE_M;
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, d->sm_count);
+    tc::k_mlp_forward_tc<<<grid, tc::TILE_M, tc::Smem::TOTAL, st>>>(p);
+    return launch_check("k_mlp_forward_tc");
+}
+
 // ===================================================================== C ABI
 extern "C" int sgk_dqn_destroy(sgk_dqn *d)
 {
@@ -421,7 +468,7 @@ extern "C" int sgk_dqn_destroy(sgk_dqn *d)
     DeviceGuard g(d->device);
     void *ptrs[] = {d->params[0], d->params[1], d->grads, d->adam_m, d->adam_v, d->adam_vmax, d->r_s, d->r_s2, d->r_a,
                     d->r_term, d->r_r, d->x, d->x2, d->dact[0], d->dact[1], d->y, d->scalars, d->b_a, d->b_term, d->b_r,
-                    d->b_idx, d->partials, d->q_env, d->boards_env, d->thr, d->status};
+                    d->b_idx, d->partials, d->q_env, d->boards_env, d->thr, d->status, d->xb, d->xb2};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < DQN_MAX_LAYERS; l++) { if (d->act[l]) cudaFree(d->act[l]); if (d->act_t[l]) cudaFree(d->act_t[l]); }
     delete d;
@@ -453,6 +500,7 @@ extern "C" int sgk_dqn_create(const sgk_env *env, int n_layers, int n_hidden, in
     }
     d->n_params = off;
     d->cap = replay_capacity; d->batch = batch_size; d->seed = seed;
+    cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, env->device);
     d->lr = 1e-3; d->discount = 0.99; d->epsilon = 0.01; d->anneal = 100000; d->sync_every = 10000; d->bxb_loss = 1;
     const size_t pb = (size_t)d->n_params * sizeof(float);
     bool ok = true;
@@ -523,6 +571,7 @@ extern "C" int sgk_dqn_qvalues(sgk_dqn *d, int which, const uint8_t *boards, int
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_rows(d, n);
     if (rc != SGK_OK) return rc;
+    if (d->use_tc) return forward_tc(d, which, boards, n, q_out, nullptr, nullptr, st);
     k_u8_to_f32<<<(unsigned)std::min<int64_t>((n * d->hw + 255) / 256, 148 * 16), 256, 0, st>>>(boards, d->x, n * d->hw);
     rc = forward(d, which, d->x, n, d->act, st);
     if (rc != SGK_OK) return rc;
@@ -547,8 +596,14 @@ static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
 {
     const int L = d->n_linear, A = d->n_actions;
     int rc;
-    if ((rc = forward(d, 0, d->x, B, d->act, st))) return rc;        // Qs = Q(states)
-    if ((rc = forward(d, 1, d->x2, B, d->act_t, st))) return rc;     // target_Q(successors)
+    if (d->use_tc) {
+        // tensor-core forwards; H1 / H2 come back in fp32 for the backward pass
+        if ((rc = forward_tc(d, 0, d->xb, B, d->act[2], d->act[0], d->act[1], st))) return rc;
+        if ((rc = forward_tc(d, 1, d->xb2, B, d->act_t[2], nullptr, nullptr, st))) return rc;
+    } else {
+        if ((rc = forward(d, 0, d->x, B, d->act, st))) return rc;        // Qs = Q(states)
+        if ((rc = forward(d, 1, d->x2, B, d->act_t, st))) return rc;     // target_Q(successors)
+    }
     k_td_target<<<grid_for(B, 256), 256, 0, st>>>(d->act_t[L - 1], A, d->b_r, d->b_term, (float)d->discount, d->y, B);
     float *dcur = d->dact[0], *dnext = d->dact[1];
     k_loss_grad<<<1, 1024, 0, st>>>(d->act[L - 1], d->b_a, d->y, A, B, d->bxb_loss, dcur, d->scalars);
@@ -598,6 +653,8 @@ extern "C" int sgk_dqn_learn_batch(sgk_dqn *d, const uint8_t *s, const uint8_t *
     if (rc != SGK_OK) return rc;
     k_u8_to_f32<<<(unsigned)std::min<int64_t>((n * d->hw + 255) / 256, 148 * 16), 256, 0, st>>>(s, d->x, n * d->hw);
     k_u8_to_f32<<<(unsigned)std::min<int64_t>((n * d->hw + 255) / 256, 148 * 16), 256, 0, st>>>(s2, d->x2, n * d->hw);
+    CU(cudaMemcpyAsync(d->xb, s, (size_t)n * d->hw, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(d->xb2, s2, (size_t)n * d->hw, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(d->b_a, a, (size_t)n, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(d->b_term, term, (size_t)n, cudaMemcpyDeviceToDevice, st));
     // rewards arrive as float64 (the env's dtype); the network works in float32
@@ -615,7 +672,7 @@ extern "C" int sgk_dqn_learn(sgk_dqn *d, uint64_t step, float *loss_out, void *s
     int rc = ensure_rows(d, B);
     if (rc != SGK_OK) return rc;
     k_replay_sample<<<grid_for(B, 128), 128, 0, st>>>(d->seed, step, fill, B, d->hw, d->r_s, d->r_s2, d->r_a, d->r_r, d->r_term,
-                                                      d->x, d->x2, d->b_a, d->b_r, d->b_term, d->b_idx);
+                                                      d->x, d->x2, d->xb, d->xb2, d->b_a, d->b_r, d->b_term, d->b_idx);
     if ((rc = launch_check("k_replay_sample"))) return rc;
     return learn_staged(d, B, loss_out, st);
 }
@@ -647,14 +704,20 @@ extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64
         a.q = d->q_env; a.thr = 0;
         if (learn) {
             // act: Q(s) for every environment's current board
+            const bool use_tc = d->use_tc != 0;
             rc = by_kind(env->level.kind, [&](auto K) {
                 constexpr int KIND = decltype(K)::value;
-                k_dqn_render_f32<KIND><<<grid_for(env->n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(env->level, env->arr.core, env->n, d->x);
-                return launch_check("k_dqn_render_f32");
+                if (use_tc) k_dqn_render_u8<KIND><<<grid_for(env->n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(env->level, env->arr.core, env->n, d->xb);
+                else k_dqn_render_f32<KIND><<<grid_for(env->n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(env->level, env->arr.core, env->n, d->x);
+                return launch_check("k_dqn_render");
             });
             if (rc != SGK_OK) return rc;
-            if ((rc = forward(d, 0, d->x, env->n, d->act, st))) return rc;
-            CU(cudaMemcpyAsync(d->q_env, d->act[d->n_linear - 1], (size_t)env->n * d->n_actions * 4, cudaMemcpyDeviceToDevice, st));
+            if (use_tc) {
+                if ((rc = forward_tc(d, 0, d->xb, env->n, d->q_env, nullptr, nullptr, st))) return rc;
+            } else {
+                if ((rc = forward(d, 0, d->x, env->n, d->act, st))) return rc;
+                CU(cudaMemcpyAsync(d->q_env, d->act[d->n_linear - 1], (size_t)env->n * d->n_actions * 4, cudaMemcpyDeviceToDevice, st));
+            }
             // epsilon of this agent-step: DeepQAgent keeps entry 0 (value.py:72-76)
             const int64_t last = d->anneal > 1 ? d->anneal - 1 : 0;
             const int64_t idx = (int64_t)t < last ? (int64_t)t : last;
@@ -677,6 +740,14 @@ extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64
                 if ((rc = sgk_dqn_sync_target(d, stream))) return rc;
         }
     }
+    return SGK_OK;
+}
+
+extern "C" int sgk_dqn_set_tensor_cores(sgk_dqn *d, int enabled)
+{
+    REQUIRE(d != nullptr, "d is NULL");
+    REQUIRE(!enabled || tc_supported(d), "the tensor-core forward covers n_layers == 2, n_hidden <= 100, boards <= 64 cells");
+    d->use_tc = enabled ? 1 : 0;
     return SGK_OK;
 }
 

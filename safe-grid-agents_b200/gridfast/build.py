@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libsgk.so")
 SOURCES = ["sgk.cu", "sgk_dqn.cu"]
-HEADERS = ["sgk_common.cuh", "sgk_envs.cuh", "sgk_table.cuh", "sgk_internal.cuh", "../../include/sgk.h"]
+HEADERS = ["sgk_common.cuh", "sgk_envs.cuh", "sgk_table.cuh", "sgk_internal.cuh", "sgk_mlp_tc.cuh", "../../include/sgk.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

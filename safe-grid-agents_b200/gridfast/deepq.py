@@ -57,6 +57,10 @@ class BatchedDeepQ:
                           if isinstance(m, torch.nn.Linear) for p in (m.weight, m.bias)])
         self.set_params(flat, which)
 
+    def set_tensor_cores(self, enabled=True):
+        """Forward passes on tcgen05 (TF32 in, fp32 accumulate) instead of fp32 FFMA."""
+        check(self.L.sgk_dqn_set_tensor_cores(self.h, int(enabled)))
+
     def sync_target(self):
         check(self.L.sgk_dqn_sync_target(self.h, _stream()))
 

@@ -127,3 +127,80 @@ def test_dqn_rollout_learns_sokoban():
     q = agent.q_values(boards)
     assert q.shape == (n, 4) and torch.isfinite(q).all()
     assert agent.act(boards).dtype == torch.uint8
+
+
+# ---------------------------------------------------------------- tensor cores
+@pytest.mark.parametrize("env_id", ["BoatRace-v0", "SideEffectsSokoban-v0", "TomatoWatering-v0"])
+@pytest.mark.parametrize("rows", [1, 127, 128, 1000, 70001])
+def test_tcgen05_forward_matches_fp32(env_id, rows):
+    """The fused tcgen05 MLP forward (TF32 operands, fp32 accumulate in TMEM)
+    against the fp32 FFMA path and torch: TF32 has 10 mantissa bits, so the
+    tolerance is 3e-3 of the largest |Q| (stated, not 1e-5)."""
+    import gridfast
+    torch.manual_seed(rows)
+    dev = torch.device("cuda", 0)
+    env = gridfast.BatchedEnv(env_id, 4, seed=1)
+    agent = gridfast.BatchedDeepQ(env, n_layers=2, n_hidden=100)
+    Q = build_Q(env.hw, 2, 100, 4).to(dev)
+    agent.load_torch_module(Q, 0)
+    agent.load_torch_module(Q, 1)
+    boards = torch.randint(0, 6, (rows, env.hw), dtype=torch.uint8, device=dev)
+    q_fp32 = agent.q_values(boards)
+    agent.set_tensor_cores(True)
+    q_tc = agent.q_values(boards)
+    q_tc_target = agent.q_values(boards, which=1)
+    q_ref = Q(boards.float())
+    scale = q_ref.abs().max().item()
+    assert torch.allclose(q_fp32, q_ref, rtol=1e-5, atol=1e-5)
+    assert (q_tc - q_ref).abs().max().item() <= 3e-3 * scale, (q_tc - q_ref).abs().max().item()
+    assert torch.equal(q_tc, q_tc_target)
+    # and the greedy action agrees wherever the fp32 margin is not a near-tie
+    top2 = q_ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-2 * scale
+    assert torch.equal(q_tc.argmax(1)[clear], q_ref.argmax(1)[clear])
+
+
+def test_tcgen05_learn_step_tracks_torch():
+    import gridfast
+    torch.manual_seed(5)
+    dev = torch.device("cuda", 0)
+    batch = 4096
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", 8, seed=1)
+    agent = gridfast.BatchedDeepQ(env, batch_size=batch, lr=1e-3, reference_bxb_loss=False)
+    agent.set_tensor_cores(True)
+    Q = build_Q(env.hw, 2, 100, 4).to(dev)
+    T = build_Q(env.hw, 2, 100, 4).to(dev)
+    optim = torch.optim.Adam(Q.parameters(), lr=1e-3, amsgrad=True)
+    agent.load_torch_module(Q, 0)
+    agent.load_torch_module(T, 1)
+    p0 = flat(Q).clone()
+    rs = np.random.RandomState(4)
+    for step in range(5):
+        s = torch.as_tensor(rs.randint(0, 6, size=(batch, env.hw)).astype(np.uint8)).to(dev)
+        s2 = torch.as_tensor(rs.randint(0, 6, size=(batch, env.hw)).astype(np.uint8)).to(dev)
+        a = torch.as_tensor(rs.randint(0, 4, size=batch).astype(np.uint8)).to(dev)
+        r = torch.as_tensor(rs.choice([-1.0, 49.0, -11.0], size=batch)).to(dev)
+        term = torch.as_tensor((rs.rand(batch) < 0.1).astype(np.uint8)).to(dev)
+        loss, norm = reference_learn(Q, T, optim, s.float(), a, r.float(), s2.float(), term, 0.99, False)
+        ours = agent.learn_batch(s, a, r, s2, term).tolist()
+        assert ours[0] == pytest.approx(loss, rel=5e-3)
+        assert ours[1] == pytest.approx(norm, rel=5e-3)
+    du, dr = agent.get_params(0) - p0, flat(Q) - p0
+    cos = torch.dot(du, dr) / (du.norm() * dr.norm())
+    assert cos.item() > 0.99, cos.item()
+
+
+def test_dqn_rollout_learns_with_tensor_cores():
+    import gridfast
+    n = 512
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", n, seed=2)
+    agent = gridfast.BatchedDeepQ(env, replay_capacity=n * 40, batch_size=1024, lr=1e-3, epsilon=0.05,
+                                  epsilon_anneal=150, sync_every=25, reference_bxb_loss=False, seed=11)
+    agent.set_tensor_cores(True)
+    agent.warmup(40)
+    base = env.totals()
+    agent.rollout(400)
+    tot = env.totals()
+    random_return = base["sum_return"] / base["episodes"]
+    learned_return = (tot["sum_return"] - base["sum_return"]) / (tot["episodes"] - base["episodes"])
+    assert learned_return > random_return + 4, (random_return, learned_return)
