@@ -116,6 +116,37 @@ def unfused_agent(env_id, n, reps=10):
     torch.cuda.empty_cache()
 
 
+def dqn(n, batch, T, use_tc, reps=3, label=None):
+    """C5: side-effects sokoban, one shared 36-100-100-4 Q network, HBM replay ring."""
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", n, seed=0)
+    agent = gridfast.BatchedDeepQ(env, replay_capacity=100 * n, batch_size=batch, lr=1e-3, epsilon=0.01,
+                                  epsilon_anneal=100000, sync_every=10000, reference_bxb_loss=True)
+    agent.set_tensor_cores(use_tc)
+    agent.warmup(100)
+    sec = timed(lambda: agent.rollout(T), reps, warm=1)
+    flop = T * (n * 28000.0 + batch * 4 * 28000.0)
+    emit(measurement=label or "dqn_rollout", env="SideEffectsSokoban-v0", n_envs=n, learn_batch=batch, locksteps=T,
+         forward="tcgen05 tf32" if use_tc else "fp32 ffma", seconds_per_call=sec, env_steps_per_s=n * T / sec,
+         us_per_lockstep=1e6 * sec / T, samples_learned_per_s=batch * T / sec, model_TFLOPs=flop / sec / 1e12,
+         loss_norm_clip=agent.last_scalars())
+    del agent, env
+    torch.cuda.empty_cache()
+
+
+def mlp_forward(rows, use_tc, reps=10):
+    """The forward kernel alone: rows x (36-100-100-4), 28.0 kFLOP per row."""
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", 4, seed=0)
+    agent = gridfast.BatchedDeepQ(env)
+    agent.set_tensor_cores(use_tc)
+    boards = torch.randint(0, 6, (rows, env.hw), dtype=torch.uint8, device="cuda")
+    sec = timed(lambda: agent.q_values(boards), reps)
+    emit(measurement="mlp_forward", rows=rows, forward="tcgen05 tf32" if use_tc else "fp32 ffma", seconds_per_call=sec,
+         rows_per_s=rows / sec, TFLOPs=rows * 28000.0 / sec / 1e12,
+         frac_of_measured_bf16_tensor_peak=rows * 28000.0 / sec / 1e12 / 1648.6 if use_tc else None)
+    del agent, env
+    torch.cuda.empty_cache()
+
+
 def main():
     P, S = gridfast.Q_PRIVATE, gridfast.Q_SHARED
     which = sys.argv[1:] or ["fused", "tomato", "large", "unfused"]
@@ -134,6 +165,12 @@ def main():
     if "large" in which:
         fused("BoatRace-v0", 1 << 24, 200, P, reps=3, label="large-N boat private 2^24 x 200")
         fused("SideEffectsSokoban-v0", 1 << 22, 200, P, reps=3, label="large-N sokoban private 2^22 x 200")
+    if "dqn" in which:
+        for use_tc in (False, True):
+            mlp_forward(1 << 20, use_tc)
+        for use_tc in (False, True):
+            dqn(4096, 4096, 200, use_tc, label="C5 sokoban DQN 4096 envs, batch 4096")
+            dqn(4096, 64 * 4096, 50, use_tc, label="C5 sokoban DQN 4096 envs, batch 64 per env-step")
     if "unfused" in which:
         for env_id in B_ALG:
             unfused_step(env_id, 1 << 24)

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Small drivers for ncu captures of single kernels (see profiles/).
+
+    ncu --set full -k regex:k_env_step ... python scripts/profile_targets.py step
+    ncu --set full -k regex:k_mlp_forward_tc ... python scripts/profile_targets.py mlp
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "safe-grid-agents_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import gridfast  # noqa: E402
+
+what = sys.argv[1]
+if what == "step":
+    n = 1 << 24
+    env = gridfast.BatchedEnv("BoatRace-v0", n, seed=0)
+    acts = torch.randint(0, 4, (n,), dtype=torch.uint8, device="cuda")
+    out = (env._u8(n, env.hw), env._f64(n), env._f64(n), env._u8(n))
+    for t in range(4):
+        env.step(acts, step=t, out=out)
+elif what == "mlp":
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", 4, seed=0)
+    agent = gridfast.BatchedDeepQ(env)
+    agent.set_tensor_cores(True)
+    boards = torch.randint(0, 6, (1 << 20, env.hw), dtype=torch.uint8, device="cuda")
+    for _ in range(4):
+        agent.q_values(boards)
+elif what == "shared":
+    env = gridfast.BatchedEnv("BoatRace-v0", 65536, seed=0)
+    agent = gridfast.BatchedTabularQ(env, gridfast.Q_SHARED)
+    for _ in range(3):
+        agent.rollout(200)
+torch.cuda.synchronize()
