@@ -144,7 +144,7 @@ def cpu_port_rate(n_procs, n_steps):
     return sum(r[0] for r in res) / wall
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the CPU implementation of the path on all host cores.
     /root/reference is pure Python whose env half is an absent third-party
     dependency, so it cannot be compiled into oracle/_ref; the arm times the
@@ -178,15 +178,17 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 # ----------------------------------------------------------------- ours
-def run_ours(args):
+def run_ours(args, out):
     import torch
     import torch.distributed as dist
 
     import gridfast
+    from gridfast.distributed import _MAX_SLOTS
+    MAX_COLS = list(_MAX_SLOTS)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,20 +212,25 @@ def run_ours(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    def one_step():
+    # Private-Q rollouts need no data-path collective.  Episode statistics are
+    # kept per bench step and all-reduced (NCCL) once per sync interval -- here
+    # the K timed steps -- so ranks never wait for each other inside a step; the
+    # collective is timed as the last ("drain") segment of the region.
+    def one_step(buf):
         agent.rollout(T)                      # 2 launches: thresholds + fused rollout
-        env.totals_device(totals)             # 1 launch
-        if world > 1:                         # episode statistics all-reduce (NCCL)
-            dist.all_reduce(totals)
+        env.totals_device(buf)                # 2 launches: partial + final reduction
 
     for _ in range(W):
-        one_step()
+        one_step(totals)
+    if world > 1:
+        dist.all_reduce(totals)
     agent.check()
     barrier()
 
     # ---- device-timed region: K steps, CUDA events on the launching stream
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stats = torch.zeros(K, 9, dtype=torch.float64, device=dev)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     kstart = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     kend = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     with ClockSampler(local) as clocks:
@@ -233,10 +240,15 @@ def run_ours(args):
             kstart[k].record()
             agent.rollout(T)
             kend[k].record()
-            env.totals_device(totals)
-            if world > 1:
-                dist.all_reduce(totals)
+            env.totals_device(stats[k])
             ends[k].record()
+        starts[K].record()                    # sync interval ends: one all-reduce of all K rows
+        if world > 1:                         # sums, and maxima for the max_* columns
+            maxima = stats[:, MAX_COLS].clone()
+            dist.all_reduce(stats)
+            dist.all_reduce(maxima, op=dist.ReduceOp.MAX)
+            stats[:, MAX_COLS] = maxima
+        ends[K].record()
         barrier()
     agent.check()
     step_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
@@ -288,7 +300,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_env_step": B_ALG, "peak_source": peak_src,
                          "kernel_ms_per_launch": kernel_ms / K},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": 3 * K,
+            "gpu_launches": 4 * K,
             "clocks": clocks.summary(),
         }
         if world == 1:
@@ -297,9 +309,18 @@ def run_ours(args):
             line["cpu_baseline"] = {
                 "value": rate, "unit": "env-steps/s", "cores": 1, "kind": "port",
                 "sample": "150000 env-steps of boat-race tabular-Q, python oracle port, 1 process (%.1f s)" % (time.perf_counter() - t)}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """Keep stdout for the single JSON line: libraries (NCCL prints its version
+    banner to stdout) are redirected to stderr for the whole run."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -309,10 +330,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
+    out = _claim_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, out)
     else:
-        run_ours(args)
+        run_ours(args, out)
 
 
 if __name__ == "__main__":
