@@ -80,14 +80,26 @@ typedef struct {
     int overflow;
 } cg_rng;
 
-static void rng_call(const cg_rng *g, int call, uint32_t out[4])
+static void rng_call_at(const cg_rng *g, int call, uint64_t index, uint32_t out[4])
 {
     uint32_t c[4];
     c[0] = (uint32_t)g->env_id;
     c[1] = (uint32_t)(g->env_id >> 32);
-    c[2] = (uint32_t)g->step;
-    c[3] = (uint32_t)(call & 0xFF) | ((uint32_t)((g->step >> 32) & 0xFFFFFF) << 8);
+    c[2] = (uint32_t)index;
+    c[3] = (uint32_t)(call & 0xFF) | ((uint32_t)((index >> 32) & 0xFFFFFF) << 8);
     philox4x32_10(c, g->key, out);
+}
+
+static void rng_call(const cg_rng *g, int call, uint32_t out[4]) { rng_call_at(g, call, g->step, out); }
+
+/* agent draws: call 0 at index step >> 1 serves two steps; (a, b) = (w0, w1)
+ * on even steps, (w2, w3) on odd steps (see oracle/rng.py) */
+static void rng_agent_words(const cg_rng *g, uint32_t *a, uint32_t *b)
+{
+    uint32_t w[4];
+    rng_call_at(g, 0, g->step >> 1, w);
+    *a = w[2 * (g->step & 1)];
+    *b = w[2 * (g->step & 1) + 1];
 }
 
 static uint32_t rng_next_word(cg_rng *g)
@@ -98,29 +110,26 @@ static uint32_t rng_next_word(cg_rng *g)
 
 static double rng_agent_uniform(cg_rng *g)
 {
-    if (g->mode == CG_RNG_REPLAY) {
-        uint32_t a = rng_next_word(g), b = rng_next_word(g);
-        return words_to_double(a, b);
-    }
-    uint32_t w[4];
-    rng_call(g, 0, w);
-    return words_to_double(w[0], w[1]);
+    uint32_t a, b;
+    if (g->mode == CG_RNG_REPLAY) { a = rng_next_word(g); b = rng_next_word(g); }
+    else rng_agent_words(g, &a, &b);
+    return words_to_double(a, b);
 }
 
 static int rng_agent_choice(cg_rng *g)
 {
     if (g->mode == CG_RNG_REPLAY) return (int)(rng_next_word(g) & (NA - 1));
-    uint32_t w[4];
-    rng_call(g, 0, w);
-    return (int)(w[2] & (NA - 1));
+    uint32_t a, b;
+    rng_agent_words(g, &a, &b);
+    return (int)(a & (NA - 1));
 }
 
 static int rng_random_action(cg_rng *g)
 {
     if (g->mode == CG_RNG_REPLAY) return (int)(rng_next_word(g) & (NA - 1));
-    uint32_t w[4];
-    rng_call(g, 0, w);
-    return (int)(w[3] & (NA - 1));
+    uint32_t a, b;
+    rng_agent_words(g, &a, &b);
+    return (int)(b & (NA - 1));
 }
 
 static double rng_env_uniform(cg_rng *g, int slot, int at_reset)

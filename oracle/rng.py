@@ -18,16 +18,22 @@ Three interchangeable streams implement the same four draws:
                     choice(4) = randint(0,4) = w & 3.
 ``PhiloxRng``       Philox4x32-10 (Salmon et al., SC'11, "Random123") in
                     counter mode.  key = (seed_lo, seed_hi); counter =
-                    (env_lo, env_hi, step_lo, call | step_hi<<8).  One call
+                    (env_lo, env_hi, index_lo, call | index_hi<<8).  One call
                     gives four words; the draw is addressed by *purpose*, not
                     by position in a sequence, so the value an environment
                     sees at (seed, env, step, purpose) never depends on how
                     many other draws happened:
-                      call 0          w0,w1 -> agent uniform, w2 -> explore
-                                      action, w3 -> RandomAgent action
-                      call 1+k//2     pair k%2 -> tomato k drying draw (step)
-                      call 8+k//2     pair k%2 -> tomato k drying draw at the
-                                      reset that precedes agent step `step`
+                      call 0, index = step >> 1: one call serves two agent
+                                      steps; words (a, b) = (w0, w1) for even
+                                      steps, (w2, w3) for odd steps; agent
+                                      uniform from (a, b), explore action
+                                      a & 3, RandomAgent action b & 3 (low bits
+                                      the 53-bit uniform does not use)
+                      call 1+k//2, index = step: pair k%2 -> tomato k drying
+                                      draw of the step
+                      call 8+k//2, index = step: pair k%2 -> tomato k drying
+                                      draw at the reset that precedes agent
+                                      step `step`
 """
 import numpy as np
 
@@ -137,30 +143,35 @@ class PhiloxRng:
         self.env_id = env_id
         self.step = step
 
-    def _call(self, call):
-        if call not in self._cache:
+    def _call(self, call, index):
+        if (call, index) not in self._cache:
             ctr = (
                 self.env_id & _MASK,
                 (self.env_id >> 32) & _MASK,
-                self.step & _MASK,
-                (call & 0xFF) | (((self.step >> 32) & 0xFFFFFF) << 8),
+                index & _MASK,
+                (call & 0xFF) | (((index >> 32) & 0xFFFFFF) << 8),
             )
-            self._cache[call] = philox4x32_10(ctr, self.key)
-        return self._cache[call]
+            self._cache[(call, index)] = philox4x32_10(ctr, self.key)
+        return self._cache[(call, index)]
+
+    def _agent_words(self):
+        w = self._call(CALL_AGENT, self.step >> 1)
+        h = 2 * (self.step & 1)
+        return w[h], w[h + 1]
 
     def agent_uniform(self):
-        w = self._call(CALL_AGENT)
-        return words_to_double(w[0], w[1])
+        a, b = self._agent_words()
+        return words_to_double(a, b)
 
     def agent_choice(self, n):
-        return self._call(CALL_AGENT)[2] & _pow2_mask(n)
+        return self._agent_words()[0] & _pow2_mask(n)
 
     def random_action(self, n):
-        return self._call(CALL_AGENT)[3] & _pow2_mask(n)
+        return self._agent_words()[1] & _pow2_mask(n)
 
     def env_uniform(self, slot, at_reset=False):
         base = CALL_ENV_RESET if at_reset else CALL_ENV_STEP
-        w = self._call(base + slot // 2)
+        w = self._call(base + slot // 2, self.step)
         p = 2 * (slot % 2)
         return words_to_double(w[p], w[p + 1])
 

@@ -117,27 +117,52 @@ __host__ __device__ __forceinline__ uint64_t words_to_u53(uint32_t a, uint32_t b
 
 struct PhiloxStream {
     uint32_t k0, k1, e0, e1;
-    uint32_t s0, s1;      // step lo / hi
-    uint32_t w[4];        // cached agent call
+    uint32_t s0, s1;      // step lo / hi (environment draws)
+    uint32_t p0, p1;      // agent call counter words: step >> 1
+    uint32_t half;        // step & 1: which half of the agent call this step uses
+    uint32_t w[4];        // cached agent call (serves two consecutive steps)
+    uint32_t have_p0, have_p1;
+    static constexpr bool kCounterMode = true;
     __device__ __forceinline__ void init(uint64_t seed, uint64_t env_id)
     {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
         e0 = (uint32_t)env_id; e1 = (uint32_t)(env_id >> 32);
-        s0 = s1 = 0;
+        s0 = s1 = p0 = p1 = half = 0;
+        have_p0 = have_p1 = 0xFFFFFFFFu;   // nothing cached
     }
     __device__ __forceinline__ void set_step(uint64_t step)
     {
         s0 = (uint32_t)step;
         s1 = (uint32_t)((step >> 32) & 0xFFFFFF) << 8;
+        const uint64_t pair = step >> 1;
+        p0 = (uint32_t)pair;
+        p1 = (uint32_t)((pair >> 32) & 0xFFFFFF) << 8;
+        half = (uint32_t)step & 1u;
     }
     __device__ __forceinline__ void call(int c, uint32_t out[4]) const
     {
         philox4x32_10(e0, e1, s0, (uint32_t)c | s1, k0, k1, out);
     }
-    // agent: one call serves the uniform, the explore action and the random action
-    __device__ __forceinline__ uint64_t agent_uniform() { call(SGK_CALL_AGENT, w); return words_to_u53(w[0], w[1]); }
-    __device__ __forceinline__ int agent_choice() { return (int)(w[2] & (SGK_NA - 1)); }
-    __device__ __forceinline__ int random_action() { call(SGK_CALL_AGENT, w); return (int)(w[3] & (SGK_NA - 1)); }
+    // Agent draws: ONE Philox call serves two consecutive agent-steps (counter
+    // word 2 = step >> 1): step parity selects the word pair (a, b); the 53-bit
+    // uniform uses a >> 5 and b >> 6, the explore action is a & 3 and the
+    // random-policy action b & 3 -- low bits the uniform does not use.  The
+    // step index is warp-uniform in lock-step rollouts, so the refill branch
+    // never diverges.
+    __device__ __forceinline__ void refill()
+    {
+        if (have_p0 != p0 || have_p1 != p1) {
+            philox4x32_10(e0, e1, p0, (uint32_t)SGK_CALL_AGENT | p1, k0, k1, w);
+            have_p0 = p0; have_p1 = p1;
+        }
+    }
+    __device__ __forceinline__ uint64_t agent_uniform()
+    {
+        refill();
+        return words_to_u53(half ? w[2] : w[0], half ? w[3] : w[1]);
+    }
+    __device__ __forceinline__ int agent_choice() { return (int)((half ? w[2] : w[0]) & (SGK_NA - 1)); }
+    __device__ __forceinline__ int random_action() { refill(); return (int)((half ? w[3] : w[1]) & (SGK_NA - 1)); }
     // tomato: which of the watered tomatoes (slot mask) dry this frame
     __device__ __forceinline__ uint32_t dry_mask(uint32_t watered, bool at_reset) const
     {
@@ -162,6 +187,7 @@ struct ReplayStream {
     const uint32_t *words;
     long long cursor, n_words;
     bool dry_stream;
+    static constexpr bool kCounterMode = false;  // strictly sequential consumption
     __device__ __forceinline__ void set_step(uint64_t) {}
     __device__ __forceinline__ uint32_t next()
     {

@@ -101,28 +101,35 @@ def test_warmup_fills_ring_with_oracle_random_walk():
     assert np.array_equal(env.render().cpu().numpy(), sim.boards())
 
 
+def _train_and_score(agent, env, train_steps=1500, score_steps=300):
+    agent.warmup(40)
+    base = env.totals()
+    random_return = base["sum_return"] / base["episodes"]
+    agent.rollout(train_steps)
+    mid = env.totals()
+    agent.rollout(score_steps)
+    tot = env.totals()
+    tail_return = (tot["sum_return"] - mid["sum_return"]) / (tot["episodes"] - mid["episodes"])
+    return random_return, tail_return
+
+
 def test_dqn_rollout_learns_sokoban():
     """End to end: warm-up, then act/step/learn lock-steps.  Statistical
-    parity only (SURVEY hard part H7): the greedy policy must reach the goal
-    far more often than the random policy, and the bookkeeping must be exact."""
+    parity only (SURVEY hard part H7): after training, the epsilon-greedy
+    policy must collect clearly more return per episode than the random policy
+    (random ~28, optimum 45), and the bookkeeping must be exact."""
     import gridfast
     n = 512
     env = gridfast.BatchedEnv("SideEffectsSokoban-v0", n, seed=2)
     agent = gridfast.BatchedDeepQ(env, replay_capacity=n * 40, batch_size=1024, lr=1e-3, epsilon=0.05,
                                   epsilon_anneal=150, sync_every=25, reference_bxb_loss=False, seed=11)
-    agent.warmup(40)
-    base = env.totals()
-    random_return = base["sum_return"] / base["episodes"]
     p0 = agent.get_params(0).clone()
-    agent.rollout(400)
+    random_return, tail_return = _train_and_score(agent, env)
     loss, norm, clip = agent.last_scalars()
     assert np.isfinite(loss) and np.isfinite(norm) and 0 < clip <= 1
     assert not torch.equal(agent.get_params(0), p0)
-    tot = env.totals()
-    learned_return = (tot["sum_return"] - base["sum_return"]) / (tot["episodes"] - base["episodes"])
-    assert learned_return > random_return + 4, (random_return, learned_return)
-    # sync_every = 25 and t = 439 is a sync step (439 % 25 == 14 -> not); check the last sync at t = 424
-    assert env.t == 440
+    assert tail_return > random_return + 5, (random_return, tail_return)
+    assert env.t == 40 + 1500 + 300
     boards = env.render()
     q = agent.q_values(boards)
     assert q.shape == (n, 4) and torch.isfinite(q).all()
@@ -197,10 +204,5 @@ def test_dqn_rollout_learns_with_tensor_cores():
     agent = gridfast.BatchedDeepQ(env, replay_capacity=n * 40, batch_size=1024, lr=1e-3, epsilon=0.05,
                                   epsilon_anneal=150, sync_every=25, reference_bxb_loss=False, seed=11)
     agent.set_tensor_cores(True)
-    agent.warmup(40)
-    base = env.totals()
-    agent.rollout(400)
-    tot = env.totals()
-    random_return = base["sum_return"] / base["episodes"]
-    learned_return = (tot["sum_return"] - base["sum_return"]) / (tot["episodes"] - base["episodes"])
-    assert learned_return > random_return + 4, (random_return, learned_return)
+    random_return, tail_return = _train_and_score(agent, env)
+    assert tail_return > random_return + 5, (random_return, tail_return)

@@ -408,3 +408,36 @@ def test_batched_greedy_eval_matches_oracle(env_id, kind, shared):
     assert {"Train/returns", "Train/safeties", "Train/margins", "Evaluation/returns",
             "Evaluation/safeties", "Evaluation/margins"} <= set(w.scalars)
     assert set(w.scalars["Evaluation/returns"][0]) == {"avg", "max"}
+
+
+def test_bad_arguments_fail_loudly():
+    """Error behaviour at the boundary: every misuse raises SgkError with the
+    library's message; nothing is silently clamped."""
+    gf = _gf()
+    with pytest.raises(ValueError):
+        gf.BatchedEnv("NoSuchEnv-v0", 4)
+    with pytest.raises(gf.SgkError, match="n_envs"):
+        gf.BatchedEnv("BoatRace-v0", 0)
+    env = gf.BatchedEnv("BoatRace-v0", 3)          # ragged: far below one block
+    assert env.render().shape == (3, 25)
+    with pytest.raises(gf.SgkError, match="power of two"):
+        gf.BatchedTabularQ(env, gf.Q_PRIVATE, capacity=12)
+    with pytest.raises(gf.SgkError, match="epsilon_anneal"):
+        gf.BatchedTabularQ(env, gf.Q_PRIVATE, epsilon_anneal=0)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE)
+    other = gf.BatchedEnv("SideEffectsSokoban-v0", 3)
+    with pytest.raises(gf.SgkError, match="different environment"):
+        gf._lib.check(env.L.sgk_rollout_tabq(other.h, agent.h, 5, 0, 0, None))
+    with pytest.raises(gf.SgkError, match="n_steps"):
+        agent.rollout(0)
+    shared = gf.BatchedTabularQ(env, gf.Q_SHARED)
+    with pytest.raises(gf.SgkError, match="private"):
+        shared.enable_ssrl(0.01, 5)
+    with pytest.raises(gf.SgkError, match="shared"):
+        agent.delta_export()
+    # a single environment and a single lock-step still work
+    one = gf.BatchedEnv("TomatoWatering-v0", 1, seed=3)
+    a1 = gf.BatchedTabularQ(one, gf.Q_SHARED)
+    a1.rollout(1)
+    a1.check()
+    assert one.t == 1
