@@ -304,6 +304,7 @@ def run_ours(args, out):
             "clocks": clocks.summary(),
         }
         if world == 1:
+            line["hbm_point"] = hbm_point(torch, gridfast, peak)
             t = time.perf_counter()
             rate = cpu_port_rate(1, 150000)
             line["cpu_baseline"] = {
@@ -321,6 +322,32 @@ def _claim_stdout():
     real = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     return real
+
+
+def hbm_point(torch, gridfast, peak):
+    """The HBM-honest data point next to the fused headline: the UNFUSED
+    env.step kernel (state in HBM, one lock-step per launch, boards / reward /
+    hidden / done written out) at 2^24 boat-race environments -- inputs and
+    outputs far larger than L2 -- reported in bytes the kernel actually moves
+    (ncu: profiles/r01_env_step_boat_2p24_ncu_full.txt)."""
+    n = 1 << 24
+    env = gridfast.BatchedEnv(ENV_ID, n, seed=0)
+    acts = torch.randint(0, 4, (n,), dtype=torch.uint8, device=env.device)
+    out = (env._u8(n, env.hw), env._f64(n), env._f64(n), env._u8(n))
+    for t in range(3):
+        env.step(acts, step=t, out=out)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    a.record()
+    for t in range(reps):
+        env.step(acts, step=3 + t, out=out)
+    b.record()
+    torch.cuda.synchronize()
+    sec = a.elapsed_time(b) / 1e3 / reps
+    moved = 8 * 2 * 3 + 1 + env.hw + 8 + 8 + 1       # core/return/hidden r+w, action, board, reward, hidden, done
+    gbs = n * moved / sec / 1e9
+    return {"kernel": "k_env_step<boat,philox>", "n_envs": n, "env_steps_per_s": n / sec,
+            "bytes_moved_per_env_step": moved, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak}
 
 
 def main():
