@@ -108,6 +108,7 @@ struct sgk_tabq {
     double *scr_target;
     int64_t scr_cap;
     unsigned long long epoch;
+    double *pub_target;        // [2][n_envs], shared small-table rollouts
     // shared-table replica sync: the table as of the last sync
     unsigned long long *base_keys;
     double *base_q;
@@ -378,6 +379,7 @@ struct RolloutArgs {
     const unsigned long long *thr;
     double lr, discount;
     int cheat;
+    double *pub_target;           // shared small-table rollouts: [2][n] published TD targets
     // SSRL
     double c_prior;
     uint32_t *ssrl_hist;
@@ -609,6 +611,153 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared(const __gri
         }
         grid.sync();
     }
+#pragma unroll
+    for (int j = 0; j < EPT; j++) {
+        const int64_t i = tid + (int64_t)j * nthreads;
+        if (i < p.n) {
+            p.arr.core[i] = pack_core(e[j]);
+            p.arr.ep_return[i] = e[j].ep_return;
+            p.arr.hidden_cum[i] = e[j].hidden_cum;
+        }
+    }
+    if (status) *p.status = status;
+}
+
+// Shared table small enough for shared memory (<= 512 slots: boat race,
+// sokoban): ONE grid barrier per lock-step instead of two, and no L2 round
+// trips on the lookup path.
+//   * every block keeps a full snapshot of the table (keys + float64 rows) in
+//     shared memory; phase A probes and reads rows there;
+//   * each environment publishes its TD target to a per-environment array
+//     (double-buffered by step parity) and the election runs block-first:
+//     shared-memory atomicMin per (state, action), then ONE global atomicMax
+//     per block and word (winner words double-buffered and epoch-tagged);
+//   * after the barrier every block applies ALL winners' updates to its own
+//     snapshot (same float64 arithmetic in every block => identical
+//     snapshots), refreshes the key snapshot, and proceeds; block 0 writes
+//     the rows back to HBM when the rollout ends.
+// Semantics are exactly those of k_rollout_shared (lowest environment id wins).
+template <int KIND, class Rng, bool TRACE, int EPT>
+__global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared_small(const __grid_constant__ RolloutArgs p)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Level &L = p.level;
+    const uint32_t cap = p.T.cap, n_words = cap * SGK_NA;
+    unsigned long long *keys_s = reinterpret_cast<unsigned long long *>(smem_raw);
+    double *q_s = reinterpret_cast<double *>(keys_s + cap);
+    uint32_t *blk_min = reinterpret_cast<uint32_t *>(q_s + n_words);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    int status = 0;
+    for (uint32_t s = threadIdx.x; s < cap; s += blockDim.x) keys_s[s] = p.T.keys[s];
+    for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) q_s[w] = p.T.q[w];
+    EnvRegs e[EPT];
+    uint32_t slot[EPT], nslot[EPT], act[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; j++) {
+        const int64_t i = tid + (int64_t)j * nthreads;
+        if (i < p.n) {
+            unpack_core(p.arr.core[i], e[j]);
+            e[j].ep_return = p.arr.ep_return[i];
+            e[j].hidden_cum = p.arr.hidden_cum[i];
+            slot[j] = SGK_NOSLOT;
+        }
+    }
+    // probe the snapshot; unknown keys are inserted in the global table
+    auto find = [&](uint64_t key) -> uint32_t {
+        uint32_t s = home_slot(key, p.T.log_cap);
+        for (uint32_t n = 0; n < cap; n++) {
+            const unsigned long long k = keys_s[s];
+            if (k == key) return s;
+            if (k == 0ull) break;
+            s = (s + 1) & (cap - 1);
+        }
+        s = find_shared(p.T, key, &status);
+        keys_s[s] = key;          // benign race: every writer stores the same value
+        return s;
+    };
+    __syncthreads();
+    for (int64_t k = 0; k < p.n_steps; k++) {
+        const uint64_t t = p.t0 + (uint64_t)k;
+        const unsigned long long thr = p.thr[k];
+        const unsigned long long epoch = (unsigned long long)(t + 1) << 32;
+        unsigned long long *winner = p.T.winner + (size_t)(t & 1) * n_words;
+        double *pub = p.pub_target + (size_t)(t & 1) * p.n;
+        for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) blk_min[w] = 0xFFFFFFFFu;
+        __syncthreads();
+        // ---- phase A: act, step, publish target, elect inside the block
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+            const int64_t i = tid + (int64_t)j * nthreads;
+            if (i >= p.n) continue;
+            Rng rng;
+            RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+            rng.set_step(t);
+            const uint64_t key = obs_key<KIND>(L, e[j]);
+            if (slot[j] == SGK_NOSLOT) slot[j] = find(key);
+            QRow row;
+            row.v0 = q_s[slot[j] * 4 + 0]; row.v1 = q_s[slot[j] * 4 + 1];
+            row.v2 = q_s[slot[j] * 4 + 2]; row.v3 = q_s[slot[j] * 4 + 3];
+            int a = argmax_first(row);
+            if (rng.agent_uniform() < thr) a = rng.agent_choice();
+            const StepOut o = env_step<KIND>(L, e[j], a, rng);
+            const double r = p.cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;
+            const uint64_t nkey = obs_key<KIND>(L, e[j]);
+            nslot[j] = nkey == key ? slot[j] : find(nkey);
+            QRow nrow;
+            nrow.v0 = q_s[nslot[j] * 4 + 0]; nrow.v1 = q_s[nslot[j] * 4 + 1];
+            nrow.v2 = q_s[nslot[j] * 4 + 2]; nrow.v3 = q_s[nslot[j] * 4 + 3];
+            pub[i] = __dadd_rn(r, __dmul_rn(p.discount, row_max(nrow)));
+            act[j] = (uint32_t)a | (o.done ? 4u : 0u);
+            if (TRACE) p.arr.trace_hash[i] = trace_fold<KIND>(L, e[j], p.arr.trace_hash[i], a, o);
+            atomicMin(&blk_min[slot[j] * SGK_NA + (uint32_t)a], (uint32_t)i);
+            RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+            if (rng.overflowed()) status = SGK_ST_REPLAY_DRY;
+        }
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+            const uint32_t m = blk_min[w];
+            if (m != 0xFFFFFFFFu) {
+                const unsigned long long mine = epoch | (0xFFFFFFFFull - (unsigned long long)m);
+                if (*reinterpret_cast<volatile unsigned long long *>(winner + w) < mine) atomicMax(winner + w, mine);
+            }
+        }
+        grid.sync();
+        // ---- every block applies all winners' updates to its own snapshot
+        for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+            const unsigned long long win = __ldcg(winner + w);
+            if ((win >> 32) == (epoch >> 32)) {
+                const unsigned long long env_i = 0xFFFFFFFFull - (win & 0xFFFFFFFFull);
+                const double target = __ldcg(pub + env_i);
+                const double q_sa = q_s[w];
+                q_s[w] = __dadd_rn(q_sa, __dmul_rn(p.lr, __dsub_rn(target, q_sa)));
+            }
+        }
+        for (uint32_t s = threadIdx.x; s < cap; s += blockDim.x) keys_s[s] = __ldcg(p.T.keys + s);
+        // ---- finished episodes reset
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+            const int64_t i = tid + (int64_t)j * nthreads;
+            if (i >= p.n) continue;
+            slot[j] = nslot[j];
+            if (act[j] & 4u) {
+                EpStats st;
+                st.load(p.arr, i);
+                st.episode_end(e[j]);
+                st.store(p.arr, i);
+                Rng rng;
+                RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+                rng.set_step(t + 1);
+                env_reset<KIND>(L, e[j], rng);
+                RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
+                slot[j] = SGK_NOSLOT;
+            }
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0)
+        for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) p.T.q[w] = q_s[w];
 #pragma unroll
     for (int j = 0; j < EPT; j++) {
         const int64_t i = tid + (int64_t)j * nthreads;
@@ -1066,7 +1215,7 @@ extern "C" int sgk_tabq_destroy(sgk_tabq *q)
     if (!q) return SGK_OK;
     DeviceGuard g(q->device);
     void *ptrs[] = {q->keys, q->q, q->c, q->winner, q->status, q->thr, q->scr_slot, q->scr_target,
-                    q->ssrl_hist, q->ssrl_budget, q->ssrl_counts, q->base_keys, q->base_q};
+                    q->ssrl_hist, q->ssrl_budget, q->ssrl_counts, q->base_keys, q->base_q, q->pub_target};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete q;
     return SGK_OK;
@@ -1106,7 +1255,8 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
               cudaMalloc(&q->q, slots * 8 * SGK_NA) == cudaSuccess && cudaMemset(q->q, 0, slots * 8 * SGK_NA) == cudaSuccess &&
               cudaMalloc(&q->status, sizeof(int)) == cudaSuccess && cudaMemset(q->status, 0, sizeof(int)) == cudaSuccess;
     if (ok && q_mode == SGK_Q_SHARED)
-        ok = cudaMalloc(&q->winner, slots * 8 * SGK_NA) == cudaSuccess && cudaMemset(q->winner, 0, slots * 8 * SGK_NA) == cudaSuccess;
+        ok = cudaMalloc(&q->winner, 2 * slots * 8 * SGK_NA) == cudaSuccess && cudaMemset(q->winner, 0, 2 * slots * 8 * SGK_NA) == cudaSuccess &&
+             cudaMalloc(&q->pub_target, 2 * (size_t)env->n * 8) == cudaSuccess;
     if (!ok) {
         sgk_tabq_destroy(q);
         return fail(SGK_ECUDA, "cudaMalloc failed for the Q table (" + std::to_string(slots * 40 >> 20) + " MiB)");
@@ -1305,12 +1455,14 @@ static RolloutArgs rollout_args(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint
     a.seed = env->seed; a.t0 = t0; a.words = env->replay_words; a.wpe = env->words_per_env;
     a.status = env->status; a.cheat = cheat;
     if (q) {
-        a.T = view_of(q); a.thr = q->thr; a.lr = q->lr; a.discount = q->discount;
+        a.T = view_of(q); a.thr = q->thr; a.lr = q->lr; a.discount = q->discount; a.pub_target = q->pub_target;
         a.c_prior = q->c_prior; a.ssrl_hist = q->ssrl_hist; a.ssrl_hist_len = q->ssrl_hist_len;
         a.ssrl_budget = q->ssrl_budget; a.ssrl_counts = q->ssrl_counts;
     }
     return a;
 }
+
+#define SGK_SMALL_TABLE_SLOTS 512
 
 template <int KIND, class Rng, bool TRACE>
 static int launch_shared(const RolloutArgs &a, cudaStream_t st)
@@ -1318,16 +1470,20 @@ static int launch_shared(const RolloutArgs &a, cudaStream_t st)
     int dev = 0, sms = 0;
     CU(cudaGetDevice(&dev));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const bool small = a.T.cap <= SGK_SMALL_TABLE_SLOTS;
+    const size_t smem = small ? (size_t)a.T.cap * (8 + 8 * SGK_NA + 4 * SGK_NA) : 0;
     auto try_ept = [&](auto E) -> int {
         constexpr int EPT = decltype(E)::value;
+        void *fn = small ? (void *)k_rollout_shared_small<KIND, Rng, TRACE, EPT> : (void *)k_rollout_shared<KIND, Rng, TRACE, EPT>;
         int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_shared<KIND, Rng, TRACE, EPT>, SGK_BLOCK_SHARED, 0));
+        if (small) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_shared_small<KIND, Rng, TRACE, EPT>, SGK_BLOCK_SHARED, smem));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_shared<KIND, Rng, TRACE, EPT>, SGK_BLOCK_SHARED, 0));
         const int64_t max_blocks = (int64_t)per_sm * sms;
         const int64_t want = (a.n + (int64_t)SGK_BLOCK_SHARED * EPT - 1) / ((int64_t)SGK_BLOCK_SHARED * EPT);
         if (want > max_blocks) return 1;   // does not fit co-resident: try a larger EPT
         RolloutArgs args = a;
         void *params[] = {&args};
-        CU(cudaLaunchCooperativeKernel((void *)k_rollout_shared<KIND, Rng, TRACE, EPT>, dim3((unsigned)want), dim3(SGK_BLOCK_SHARED), params, 0, st));
+        CU(cudaLaunchCooperativeKernel(fn, dim3((unsigned)want), dim3(SGK_BLOCK_SHARED), params, smem, st));
         return SGK_OK;
     };
     int rc = try_ept(std::integral_constant<int, 1>());
@@ -1356,6 +1512,13 @@ extern "C" int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint
     return by_kind(env->level.kind, [&](auto K) {
         constexpr int KIND = decltype(K)::value;
         if (shared) {
+            // election words carry the lock-step as an epoch tag and are only
+            // ever raised (atomicMax): if this call does not continue past every
+            // epoch used so far (a fresh run on a used table, or after unfused
+            // learn calls), start from cleared words
+            if (t0 + 1 <= q->epoch)
+                CU(cudaMemsetAsync(q->winner, 0, 2 * (size_t)q->cap * SGK_NA * 8, st));
+            q->epoch = t0 + (uint64_t)n_steps;
             if (replay) return launch_shared<KIND, ReplayStream, true>(a, st);
             if (trace) return launch_shared<KIND, PhiloxStream, true>(a, st);
             return launch_shared<KIND, PhiloxStream, false>(a, st);
