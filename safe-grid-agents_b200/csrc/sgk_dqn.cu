@@ -52,25 +52,91 @@ struct sgk_dqn {
     float *q_env; uint8_t *boards_env; int64_t env_rows;
     unsigned long long *thr; int64_t thr_cap;
     int *status;
+    double *loss_partial;             // [LOSS_BLOCKS][5]
     int use_tc;                       // forward passes on tcgen05 (TF32) instead of fp32 FFMA
     uint8_t *xb, *xb2;                // uint8 copies of the staged batch (tensor-core input)
     int sm_count;
 };
 
-static const int SPLITS = 64;
+static const int SPLITS = 256;   // upper bound of the batch splits of the weight-gradient GEMMs
 
 // ===================================================================== kernels
-// C[M,N] (+)= opA[M,K] * opB[K,N], fp32 FFMA, 64x64x16 tiles, 4x4 per thread.
+// C[M,N] = opA[M,K] * opB[K,N], fp32 FFMA, 128x128x8 block tiles, 8x8 per thread.
 //   MODE 0 (NT): A[M,K] row-major, B given as W[N,K] row-major        (forward)
 //   MODE 1 (NN): A[M,K] row-major, B[K,N] row-major                   (dX = dY W)
 //   MODE 2 (TN): A given as [K,M] row-major, B[K,N] row-major         (dW = dY^T X)
-// blockIdx.z splits K; split z writes C + z * M * ldc (partials, reduced later).
-// Epilogue: + bias[n]; relu; * (mask[m,n] > 0).
+// blockIdx.z splits K; split z writes C + z * M * ldc (partials, reduced later
+// in index order => deterministic).  Epilogue: + bias[n]; relu; * (mask[m,n] > 0).
+#define GEMM_BM 128
+#define GEMM_BN 128
+#define GEMM_BK 8
 template <int MODE>
 __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const float *__restrict__ A, int lda,
                                               const float *__restrict__ B, int ldb, float *__restrict__ C, int ldc,
                                               const float *__restrict__ bias, int relu, const float *__restrict__ mask,
                                               int ldmask, int k_chunk)
+{
+    __shared__ __align__(16) float As[GEMM_BK][GEMM_BM + 4], Bs[GEMM_BK][GEMM_BN + 4];
+    const int bm = blockIdx.y * GEMM_BM, bn = blockIdx.x * GEMM_BN;
+    const int k0 = blockIdx.z * k_chunk, k1 = min(K, k0 + k_chunk);
+    C += (size_t)blockIdx.z * M * ldc;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[8][8] = {};
+    for (int kt = k0; kt < k1; kt += GEMM_BK) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int e = threadIdx.x + r * 256;      // 0 .. 1023 = 8 x 128
+            int mm, kk;
+            if (MODE == 2) { mm = e & 127; kk = e >> 7; } else { mm = e >> 3; kk = e & 7; }
+            const int m = bm + mm, k = kt + kk;
+            float v = 0.f;
+            if (m < M && k < k1) v = MODE == 2 ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k];
+            As[kk][mm] = v;
+            int nn, kb;
+            if (MODE == 0) { nn = e >> 3; kb = e & 7; } else { nn = e & 127; kb = e >> 7; }
+            const int n = bn + nn, k2 = kt + kb;
+            float w = 0.f;
+            if (n < N && k2 < k1) w = MODE == 0 ? B[(size_t)n * ldb + k2] : B[(size_t)k2 * ldb + n];
+            Bs[kb][nn] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK; kk++) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 8]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 8 + 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int m = bm + ty * 8 + i, n = bn + tx * 8 + j;
+            if (m < M && n < N) {
+                float v = acc[i][j];
+                if (bias) v += bias[n];
+                if (relu) v = fmaxf(v, 0.f);
+                if (mask) v = mask[(size_t)m * ldmask + n] > 0.f ? v : 0.f;
+                C[(size_t)m * ldc + n] = v;
+            }
+        }
+}
+
+// Small problems (few 128x128 tiles): 64x64x16 tiles, 4x4 per thread, so that
+// enough CTAs exist to fill the machine.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_gemm_small(int M, int N, int K, const float *__restrict__ A, int lda,
+                                                    const float *__restrict__ B, int ldb, float *__restrict__ C, int ldc,
+                                                    const float *__restrict__ bias, int relu, const float *__restrict__ mask,
+                                                    int ldmask, int k_chunk)
 {
     __shared__ float As[16][65], Bs[16][65];
     const int bm = blockIdx.y * 64, bn = blockIdx.x * 64;
@@ -128,20 +194,37 @@ __global__ void k_reduce_splits(const float *partial, float *out, int64_t n, int
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float s = 0.f;
-    for (int z = 0; z < splits; z++) s += partial[(size_t)z * n + i];
-    out[i] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int z = 0;
+    for (; z + 3 < splits; z += 4) {
+        s0 += partial[(size_t)z * n + i];
+        s1 += partial[(size_t)(z + 1) * n + i];
+        s2 += partial[(size_t)(z + 2) * n + i];
+        s3 += partial[(size_t)(z + 3) * n + i];
+    }
+    for (; z < splits; z++) s0 += partial[(size_t)z * n + i];
+    out[i] = (s0 + s1) + (s2 + s3);
 }
 
-// column sums of dY[rows, n] for the bias gradients: partial[z][n]
+// column sums of dY[rows, n] for the bias gradients: partial[z][n].  Many row
+// chunks (COL_SPLITS) and four independent accumulators per thread: the loop
+// is latency-bound otherwise.  Fixed chunking and order => deterministic.
+static const int COL_SPLITS = 1024;
 __global__ void k_colsum_partial(const float *dy, int rows, int n, int ld, float *partial, int chunk)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
-    float s = 0.f;
-    for (int r = r0; r < r1; r++) s += dy[(size_t)r * ld + c];
-    partial[(size_t)blockIdx.y * n + c] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = r0;
+    for (; r + 3 < r1; r += 4) {
+        s0 += dy[(size_t)r * ld + c];
+        s1 += dy[(size_t)(r + 1) * ld + c];
+        s2 += dy[(size_t)(r + 2) * ld + c];
+        s3 += dy[(size_t)(r + 3) * ld + c];
+    }
+    for (; r < r1; r++) s0 += dy[(size_t)r * ld + c];
+    partial[(size_t)blockIdx.y * n + c] = (s0 + s1) + (s2 + s3);
 }
 
 __global__ void k_f64_to_f32(const double *in, float *out, int64_t n)
@@ -208,33 +291,56 @@ __global__ void k_td_target(const float *qt, int n_actions, const float *r, cons
 
 // loss and dL/dQ.  bxb: F.mse_loss(Qs[B,1], y[B]) broadcasts to B x B
 // (value.py:119-123): L = mean_ij (q_i - y_j)^2, dL/dq_i = (2/B)(q_i - mean(y)).
-// Otherwise the per-sample TD loss.  One block, deterministic tree.
-// scalars[0] = loss.
-__global__ void __launch_bounds__(1024) k_loss_grad(const float *q, const uint8_t *a, const float *y, int n_actions,
-                                                    int64_t batch, int bxb, float *dq, float *scalars)
+// Otherwise the per-sample TD loss.  Three stages, all with fixed chunking and
+// order (deterministic): per-block partial sums, one-block fold -> scalars[0] =
+// loss, scalars[3] = mean(y); elementwise dQ.
+static const int LOSS_BLOCKS = 256;
+__global__ void __launch_bounds__(256) k_loss_partial(const float *q, const uint8_t *a, const float *y, int n_actions,
+                                                      int64_t batch, double *partial)
 {
-    __shared__ double sh[4][1024];
-    double sq = 0, sq2 = 0, sy = 0, sy2 = 0, sd2 = 0;
-    for (int64_t b = threadIdx.x; b < batch; b += blockDim.x) {
+    __shared__ double sh[5][256];
+    const int64_t chunk = (batch + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(batch, lo + chunk);
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int64_t b = lo + threadIdx.x; b < hi; b += blockDim.x) {
         const double qv = q[b * n_actions + a[b]], yv = y[b];
-        sq += qv; sq2 += qv * qv; sy += yv; sy2 += yv * yv; sd2 += (qv - yv) * (qv - yv);
+        v[0] += qv; v[1] += qv * qv; v[2] += yv; v[3] += yv * yv; v[4] += (qv - yv) * (qv - yv);
     }
-    double v[4] = {sq, sq2, sy, bxb ? sy2 : sd2};
-    for (int k = 0; k < 4; k++) sh[k][threadIdx.x] = v[k];
+    for (int k = 0; k < 5; k++) sh[k][threadIdx.x] = v[k];
     __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) for (int k = 0; k < 4; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) for (int k = 0; k < 5; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
         __syncthreads();
     }
-    const double B = (double)batch;
-    const double mq = sh[0][0] / B, mq2 = sh[1][0] / B, my = sh[2][0] / B, last = sh[3][0] / B;
-    if (threadIdx.x == 0) scalars[0] = (float)(bxb ? (mq2 - 2.0 * mq * my + last) : last);
-    for (int64_t b = threadIdx.x; b < batch; b += blockDim.x) {
-        const float qv = q[b * n_actions + a[b]];
-        const float tgt = bxb ? (float)my : y[b];
-        for (int k = 0; k < n_actions; k++) dq[b * n_actions + k] = 0.f;
-        dq[b * n_actions + a[b]] = (float)(2.0 / B) * (qv - tgt);
+    if (threadIdx.x < 5) partial[blockIdx.x * 5 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void __launch_bounds__(256) k_loss_final(const double *partial, int n_partials, int64_t batch, int bxb, float *scalars)
+{
+    __shared__ double sh[5][256];
+    for (int k = 0; k < 5; k++) sh[k][threadIdx.x] = (int)threadIdx.x < n_partials ? partial[threadIdx.x * 5 + k] : 0.0;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) for (int k = 0; k < 5; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        const double B = (double)batch;
+        const double mq = sh[0][0] / B, mq2 = sh[1][0] / B, my = sh[2][0] / B, my2 = sh[3][0] / B, md2 = sh[4][0] / B;
+        scalars[0] = (float)(bxb ? (mq2 - 2.0 * mq * my + my2) : md2);
+        scalars[3] = (float)my;
+    }
+}
+
+__global__ void k_loss_dq(const float *q, const uint8_t *a, const float *y, int n_actions, int64_t batch, int bxb,
+                          const float *scalars, float *dq)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const float qv = q[b * n_actions + a[b]];
+    const float tgt = bxb ? scalars[3] : y[b];
+    for (int k = 0; k < n_actions; k++) dq[b * n_actions + k] = 0.f;
+    dq[b * n_actions + a[b]] = (float)(2.0 / (double)batch) * (qv - tgt);
 }
 
 // total gradient norm (clip_grad_norm_, value.py:128): scalars[1] = norm,
@@ -376,11 +482,20 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_render_u8(const __grid_consta
 static int gemm(int mode, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C, int ldc,
                 const float *bias, int relu, const float *mask, int ldmask, int splits, cudaStream_t st)
 {
-    const int k_chunk = ((K + splits - 1) / splits + 15) / 16 * 16;
-    const dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
-    if (mode == 0) k_gemm<0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
-    else if (mode == 1) k_gemm<1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
-    else k_gemm<2><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+    const long big_blocks = (long)((N + GEMM_BN - 1) / GEMM_BN) * ((M + GEMM_BM - 1) / GEMM_BM) * splits;
+    if (big_blocks >= 120) {
+        const int k_chunk = ((K + splits - 1) / splits + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+        const dim3 grid((N + GEMM_BN - 1) / GEMM_BN, (M + GEMM_BM - 1) / GEMM_BM, splits);
+        if (mode == 0) k_gemm<0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+        else if (mode == 1) k_gemm<1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+        else k_gemm<2><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+    } else {
+        const int k_chunk = ((K + splits - 1) / splits + 15) / 16 * 16;
+        const dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+        if (mode == 0) k_gemm_small<0><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+        else if (mode == 1) k_gemm_small<1><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+        else k_gemm_small<2><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, mask, ldmask, k_chunk);
+    }
     return launch_check("k_gemm");
 }
 
@@ -468,7 +583,7 @@ extern "C" int sgk_dqn_destroy(sgk_dqn *d)
     DeviceGuard g(d->device);
     void *ptrs[] = {d->params[0], d->params[1], d->grads, d->adam_m, d->adam_v, d->adam_vmax, d->r_s, d->r_s2, d->r_a,
                     d->r_term, d->r_r, d->x, d->x2, d->dact[0], d->dact[1], d->y, d->scalars, d->b_a, d->b_term, d->b_r,
-                    d->b_idx, d->partials, d->q_env, d->boards_env, d->thr, d->status, d->xb, d->xb2};
+                    d->b_idx, d->partials, d->q_env, d->boards_env, d->thr, d->status, d->xb, d->xb2, d->loss_partial};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < DQN_MAX_LAYERS; l++) { if (d->act[l]) cudaFree(d->act[l]); if (d->act_t[l]) cudaFree(d->act_t[l]); }
     delete d;
@@ -511,7 +626,8 @@ extern "C" int sgk_dqn_create(const sgk_env *env, int n_layers, int n_hidden, in
     ok = ok && cudaMalloc(&d->r_s, rb) == cudaSuccess && cudaMalloc(&d->r_s2, rb) == cudaSuccess &&
          cudaMalloc(&d->r_a, (size_t)d->cap) == cudaSuccess && cudaMalloc(&d->r_term, (size_t)d->cap) == cudaSuccess &&
          cudaMalloc(&d->r_r, (size_t)d->cap * 4) == cudaSuccess && cudaMalloc(&d->scalars, 8 * sizeof(float)) == cudaSuccess &&
-         cudaMalloc(&d->status, sizeof(int)) == cudaSuccess && cudaMemset(d->status, 0, sizeof(int)) == cudaSuccess;
+         cudaMalloc(&d->status, sizeof(int)) == cudaSuccess && cudaMemset(d->status, 0, sizeof(int)) == cudaSuccess &&
+         cudaMalloc(&d->loss_partial, 256 * 5 * sizeof(double)) == cudaSuccess;
     if (!ok) { sgk_dqn_destroy(d); return fail(SGK_ECUDA, "cudaMalloc failed for the deep-Q agent"); }
     for (int l = 0; l < d->n_linear; l++) {
         const float bound = 1.0f / sqrtf((float)d->dims[l]);
@@ -606,11 +722,14 @@ static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
     }
     k_td_target<<<grid_for(B, 256), 256, 0, st>>>(d->act_t[L - 1], A, d->b_r, d->b_term, (float)d->discount, d->y, B);
     float *dcur = d->dact[0], *dnext = d->dact[1];
-    k_loss_grad<<<1, 1024, 0, st>>>(d->act[L - 1], d->b_a, d->y, A, B, d->bxb_loss, dcur, d->scalars);
-    if ((rc = launch_check("k_loss_grad"))) return rc;
+    k_loss_partial<<<LOSS_BLOCKS, 256, 0, st>>>(d->act[L - 1], d->b_a, d->y, A, B, d->loss_partial);
+    k_loss_final<<<1, 256, 0, st>>>(d->loss_partial, LOSS_BLOCKS, B, d->bxb_loss, d->scalars);
+    k_loss_dq<<<grid_for(B, 256), 256, 0, st>>>(d->act[L - 1], d->b_a, d->y, A, B, d->bxb_loss, d->scalars, dcur);
+    if ((rc = launch_check("k_loss"))) return rc;
     // partial buffer for the split-K weight / bias gradients
     int64_t need = 0;
-    for (int l = 0; l < L; l++) need = std::max<int64_t>(need, (int64_t)SPLITS * (d->dims[l] + 1) * d->dims[l + 1]);
+    for (int l = 0; l < L; l++)
+        need = std::max<int64_t>(need, std::max<int64_t>((int64_t)SPLITS * d->dims[l] * d->dims[l + 1], (int64_t)COL_SPLITS * d->dims[l + 1]));
     if (d->partials_cap < need) {
         if (d->partials) cudaFree(d->partials);
         d->partials = nullptr; d->partials_cap = 0;
@@ -621,11 +740,13 @@ static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
         const int K = d->dims[l], N = d->dims[l + 1];
         const float *in = l == 0 ? d->x : d->act[l - 1];
         // dW[N,K] = dY^T[N,B] * in[B,K], split over the batch
-        if ((rc = gemm(2, N, K, (int)B, dcur, N, in, K, d->partials, K, nullptr, 0, nullptr, 0, SPLITS, st))) return rc;
-        k_reduce_splits<<<grid_for((int64_t)N * K, 256), 256, 0, st>>>(d->partials, d->grads + d->w_off[l], (int64_t)N * K, SPLITS);
-        const int chunk = (int)((B + SPLITS - 1) / SPLITS);
-        k_colsum_partial<<<dim3((N + 127) / 128, SPLITS), 128, 0, st>>>(dcur, (int)B, N, N, d->partials, chunk);
-        k_reduce_splits<<<grid_for(N, 256), 256, 0, st>>>(d->partials, d->grads + d->b_off[l], N, SPLITS);
+        const int w_splits = (int)std::min<int64_t>(SPLITS, (B + 63) / 64);
+        if ((rc = gemm(2, N, K, (int)B, dcur, N, in, K, d->partials, K, nullptr, 0, nullptr, 0, w_splits, st))) return rc;
+        k_reduce_splits<<<grid_for((int64_t)N * K, 256), 256, 0, st>>>(d->partials, d->grads + d->w_off[l], (int64_t)N * K, w_splits);
+        const int col_splits = (int)std::min<int64_t>(COL_SPLITS, (B + 31) / 32);
+        const int chunk = (int)((B + col_splits - 1) / col_splits);
+        k_colsum_partial<<<dim3((N + 127) / 128, col_splits), 128, 0, st>>>(dcur, (int)B, N, N, d->partials, chunk);
+        k_reduce_splits<<<grid_for(N, 256), 256, 0, st>>>(d->partials, d->grads + d->b_off[l], N, col_splits);
         if (l > 0) {
             // dX[B,K] = dY[B,N] * W[N,K], masked by relu'(in)
             const float *W = d->params[0] + d->w_off[l];

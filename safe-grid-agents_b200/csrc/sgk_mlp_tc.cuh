@@ -136,19 +136,29 @@ struct Smem {
 };
 
 // W[out][in] (global, row-major) -> chunk-major TF32 operand with `rows_pad`
-// rows and `k_pad` columns, zero padded
+// rows and `k_pad` columns, zero padded.  Consecutive threads take consecutive
+// 16-byte pieces of a weight row (coalesced global reads, float4 when the row
+// length allows), four pieces in flight per thread.
 __device__ __forceinline__ void stage_weights(uint8_t *dst, const float *w, int n_out, int n_in, int rows_pad, int k_pad)
 {
     const int chunks = k_pad / 4;
+    const bool vec = (n_in & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+#pragma unroll 4
     for (int e = threadIdx.x; e < chunks * rows_pad; e += blockDim.x) {
-        const int c = e / rows_pad, r = e - c * rows_pad;
+        const int r = e / chunks, c = e - r * chunks;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < n_out) {
-            const int k = 4 * c;
-            v.x = k + 0 < n_in ? to_tf32(w[(size_t)r * n_in + k + 0]) : 0.f;
-            v.y = k + 1 < n_in ? to_tf32(w[(size_t)r * n_in + k + 1]) : 0.f;
-            v.z = k + 2 < n_in ? to_tf32(w[(size_t)r * n_in + k + 2]) : 0.f;
-            v.w = k + 3 < n_in ? to_tf32(w[(size_t)r * n_in + k + 3]) : 0.f;
+        const int k = 4 * c;
+        if (r < n_out && k < n_in) {
+            const float *src = w + (size_t)r * n_in + k;
+            if (vec) {
+                v = __ldg(reinterpret_cast<const float4 *>(src));
+            } else {
+                v.x = __ldg(src);
+                v.y = k + 1 < n_in ? __ldg(src + 1) : 0.f;
+                v.z = k + 2 < n_in ? __ldg(src + 2) : 0.f;
+                v.w = k + 3 < n_in ? __ldg(src + 3) : 0.f;
+            }
+            v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
         }
         *reinterpret_cast<float4 *>(dst + (size_t)c * rows_pad * 16 + r * 16) = v;
     }
