@@ -268,6 +268,9 @@ int64_t sgk_dqn_replay_count(const sgk_dqn *d);
  * 1 = target_Q; device float32 [param_count]. */
 int sgk_dqn_get_params(const sgk_dqn *d, int which, float *out, void *stream);
 int sgk_dqn_set_params(sgk_dqn *d, int which, const float *in, void *stream);
+/* Gradients of the last learn step before clipping (what the reference logs as
+ * histograms with --log-gradients, value.py:129-133); same flat layout. */
+int sgk_dqn_get_grads(const sgk_dqn *d, float *out, void *stream);
 /* sync_target_Q (value.py:138-140) */
 int sgk_dqn_sync_target(sgk_dqn *d, void *stream);
 /* scores of DeepQAgent.act (value.py:89-92): boards [n][H*W] u8 -> q_out [n][4] f32 */
@@ -283,9 +286,11 @@ int sgk_dqn_learn(sgk_dqn *d, uint64_t step, float *loss_out, void *stream);
 int sgk_dqn_learn_batch(sgk_dqn *d, const uint8_t *s, const uint8_t *a, const double *r, const uint8_t *s2,
                         const uint8_t *term, int64_t n, float *loss_out, void *stream);
 int sgk_dqn_last_scalars(const sgk_dqn *d, float *out3, void *stream);
-/* Run every forward pass (acting, online and target networks in learn) as one
- * fused tcgen05 kernel: TF32 operands, fp32 accumulation in TMEM.  Covers the
- * reference's default architecture (n_layers 2, n_hidden <= 100).  Off by
+/* Run the network on the 5th-generation tensor cores: every forward pass
+ * (acting, online and target networks in learn) as one fused tcgen05 kernel,
+ * and the backward pass as an error-chain kernel plus sample-reduction
+ * weight-gradient kernels -- TF32 operands, fp32 accumulation in TMEM.  Covers
+ * the reference's default architecture (n_layers 2, n_hidden <= 100).  Off by
  * default: the fp32 path is the parity reference. */
 int sgk_dqn_set_tensor_cores(sgk_dqn *d, int enabled);
 /* n_steps lock-steps of the dqn_learn body (common/learn.py:29-58) for every

@@ -46,7 +46,7 @@ struct sgk_dqn {
     uint64_t seed;
     // work buffers
     int64_t rows_cap;                 // rows the activation buffers can hold
-    float *x, *x2, *act[DQN_MAX_LAYERS], *act_t[DQN_MAX_LAYERS], *dact[2], *y, *scalars;
+    float *x, *x2, *act[DQN_MAX_LAYERS], *act_t[DQN_MAX_LAYERS], *dact[3], *y, *scalars;
     uint8_t *b_a, *b_term; float *b_r; int64_t *b_idx;
     float *partials; int64_t partials_cap;
     float *q_env; uint8_t *boards_env; int64_t env_rows;
@@ -517,7 +517,7 @@ static int ensure_rows(sgk_dqn *d, int64_t rows)
         if ((rc = re(&d->act[l], (size_t)rows * d->dims[l + 1]))) return rc;
         if ((rc = re(&d->act_t[l], (size_t)rows * d->dims[l + 1]))) return rc;
     }
-    for (int k = 0; k < 2; k++) if ((rc = re(&d->dact[k], (size_t)rows * widest))) return rc;
+    for (int k = 0; k < 3; k++) if ((rc = re(&d->dact[k], (size_t)rows * widest))) return rc;
     if ((rc = re(&d->y, (size_t)rows))) return rc;
     if ((rc = re(&d->b_r, (size_t)rows))) return rc;
     if (d->b_a) cudaFree(d->b_a);
@@ -576,13 +576,57 @@ static int forward_tc(sgk_dqn *d, int which, const uint8_t *boards, int64_t rows
     return launch_check("k_mlp_forward_tc");
 }
 
+// backward pass on the tensor cores: error chain, then the three weight /
+// bias gradients as sample-reductions (sgk_mlp_tc.cuh)
+static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(tc::k_mlp_backward_data_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemBwd::TOTAL));
+        CU(cudaFuncSetAttribute(tc::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemWg::TOTAL));
+        attr_set = true;
+    }
+    const int H = d->dims[1], A = d->n_actions, n_in = d->dims[0];
+    const int64_t tiles = (B + tc::TILE_M - 1) / tc::TILE_M;
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, d->sm_count);
+    float *dh2 = d->dact[1], *dh1 = d->dact[2];
+    const float *P0 = d->params[0];
+    tc::BwdParams bp;
+    bp.w2 = P0 + d->w_off[1]; bp.w3 = P0 + d->w_off[2]; bp.n_hidden = H; bp.n_out = A;
+    bp.dq = dq; bp.h1 = d->act[0]; bp.h2 = d->act[1]; bp.dh1 = dh1; bp.dh2 = dh2; bp.rows = B;
+    tc::k_mlp_backward_data_tc<<<grid, tc::TILE_M, tc::SmemBwd::TOTAL, st>>>(bp);
+    int rc = launch_check("k_mlp_backward_data_tc");
+    if (rc != SGK_OK) return rc;
+    const int64_t need = (int64_t)d->sm_count * tc::TILE_M * tc::N_HID;
+    if (d->partials_cap < need) {
+        if (d->partials) cudaFree(d->partials);
+        d->partials = nullptr; d->partials_cap = 0;
+        CU(cudaMalloc(&d->partials, (size_t)need * 4));
+        d->partials_cap = need;
+    }
+    auto wgrad = [&](const float *P, int ldp, int mdim, const float *Q, int ldq, int ndim, int layer) -> int {
+        tc::WgradParams wp;
+        wp.P = P; wp.ldp = ldp; wp.mdim = mdim; wp.Q = Q; wp.ldq = ldq; wp.ndim = ndim;
+        wp.npad = (ndim + 1 + 15) / 16 * 16; wp.add_ones = 1; wp.rows = B; wp.partial = d->partials;
+        tc::k_wgrad_tc<<<grid, tc::TILE_M, tc::SmemWg::TOTAL, st>>>(wp);
+        const int total = mdim * (ndim + 1);
+        tc::k_wgrad_finish<<<(total + 255) / 256, 256, 0, st>>>(d->partials, (int)grid, wp.npad, mdim, ndim,
+                                                                d->grads + d->w_off[layer], d->grads + d->b_off[layer]);
+        return launch_check("k_wgrad_tc");
+    };
+    if ((rc = wgrad(dq, A, A, d->act[1], H, H, 2))) return rc;          // dW3, db3
+    if ((rc = wgrad(dh2, H, H, d->act[0], H, H, 1))) return rc;         // dW2, db2
+    if ((rc = wgrad(dh1, H, H, d->x, n_in, n_in, 0))) return rc;        // dW1, db1
+    return SGK_OK;
+}
+
 // ===================================================================== C ABI
 extern "C" int sgk_dqn_destroy(sgk_dqn *d)
 {
     if (!d) return SGK_OK;
     DeviceGuard g(d->device);
     void *ptrs[] = {d->params[0], d->params[1], d->grads, d->adam_m, d->adam_v, d->adam_vmax, d->r_s, d->r_s2, d->r_a,
-                    d->r_term, d->r_r, d->x, d->x2, d->dact[0], d->dact[1], d->y, d->scalars, d->b_a, d->b_term, d->b_r,
+                    d->r_term, d->r_r, d->x, d->x2, d->dact[0], d->dact[1], d->dact[2], d->y, d->scalars, d->b_a, d->b_term, d->b_r,
                     d->b_idx, d->partials, d->q_env, d->boards_env, d->thr, d->status, d->xb, d->xb2, d->loss_partial};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < DQN_MAX_LAYERS; l++) { if (d->act[l]) cudaFree(d->act[l]); if (d->act_t[l]) cudaFree(d->act_t[l]); }
@@ -672,6 +716,14 @@ extern "C" int sgk_dqn_set_params(sgk_dqn *d, int which, const float *in, void *
     return SGK_OK;
 }
 
+extern "C" int sgk_dqn_get_grads(const sgk_dqn *d, float *out, void *stream)
+{
+    REQUIRE(d != nullptr && out != nullptr, "bad argument");
+    DeviceGuard g(d->device);
+    CU(cudaMemcpyAsync(out, d->grads, (size_t)d->n_params * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SGK_OK;
+}
+
 extern "C" int sgk_dqn_sync_target(sgk_dqn *d, void *stream)
 {
     REQUIRE(d != nullptr, "d is NULL");
@@ -726,32 +778,36 @@ static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
     k_loss_final<<<1, 256, 0, st>>>(d->loss_partial, LOSS_BLOCKS, B, d->bxb_loss, d->scalars);
     k_loss_dq<<<grid_for(B, 256), 256, 0, st>>>(d->act[L - 1], d->b_a, d->y, A, B, d->bxb_loss, d->scalars, dcur);
     if ((rc = launch_check("k_loss"))) return rc;
-    // partial buffer for the split-K weight / bias gradients
-    int64_t need = 0;
-    for (int l = 0; l < L; l++)
-        need = std::max<int64_t>(need, std::max<int64_t>((int64_t)SPLITS * d->dims[l] * d->dims[l + 1], (int64_t)COL_SPLITS * d->dims[l + 1]));
-    if (d->partials_cap < need) {
-        if (d->partials) cudaFree(d->partials);
-        d->partials = nullptr; d->partials_cap = 0;
-        CU(cudaMalloc(&d->partials, (size_t)need * 4));
-        d->partials_cap = need;
-    }
-    for (int l = L - 1; l >= 0; l--) {
-        const int K = d->dims[l], N = d->dims[l + 1];
-        const float *in = l == 0 ? d->x : d->act[l - 1];
-        // dW[N,K] = dY^T[N,B] * in[B,K], split over the batch
-        const int w_splits = (int)std::min<int64_t>(SPLITS, (B + 63) / 64);
-        if ((rc = gemm(2, N, K, (int)B, dcur, N, in, K, d->partials, K, nullptr, 0, nullptr, 0, w_splits, st))) return rc;
-        k_reduce_splits<<<grid_for((int64_t)N * K, 256), 256, 0, st>>>(d->partials, d->grads + d->w_off[l], (int64_t)N * K, w_splits);
-        const int col_splits = (int)std::min<int64_t>(COL_SPLITS, (B + 31) / 32);
-        const int chunk = (int)((B + col_splits - 1) / col_splits);
-        k_colsum_partial<<<dim3((N + 127) / 128, col_splits), 128, 0, st>>>(dcur, (int)B, N, N, d->partials, chunk);
-        k_reduce_splits<<<grid_for(N, 256), 256, 0, st>>>(d->partials, d->grads + d->b_off[l], N, col_splits);
-        if (l > 0) {
-            // dX[B,K] = dY[B,N] * W[N,K], masked by relu'(in)
-            const float *W = d->params[0] + d->w_off[l];
-            if ((rc = gemm(1, (int)B, K, N, dcur, N, W, K, dnext, K, nullptr, 0, in, K, 1, st))) return rc;
-            float *t = dcur; dcur = dnext; dnext = t;
+    if (d->use_tc) {
+        if ((rc = backward_tc(d, B, dcur, st))) return rc;
+    } else {
+        // partial buffer for the split-K weight / bias gradients
+        int64_t need = 0;
+        for (int l = 0; l < L; l++)
+            need = std::max<int64_t>(need, std::max<int64_t>((int64_t)SPLITS * d->dims[l] * d->dims[l + 1], (int64_t)COL_SPLITS * d->dims[l + 1]));
+        if (d->partials_cap < need) {
+            if (d->partials) cudaFree(d->partials);
+            d->partials = nullptr; d->partials_cap = 0;
+            CU(cudaMalloc(&d->partials, (size_t)need * 4));
+            d->partials_cap = need;
+        }
+        for (int l = L - 1; l >= 0; l--) {
+            const int K = d->dims[l], N = d->dims[l + 1];
+            const float *in = l == 0 ? d->x : d->act[l - 1];
+            // dW[N,K] = dY^T[N,B] * in[B,K], split over the batch
+            const int w_splits = (int)std::min<int64_t>(SPLITS, (B + 63) / 64);
+            if ((rc = gemm(2, N, K, (int)B, dcur, N, in, K, d->partials, K, nullptr, 0, nullptr, 0, w_splits, st))) return rc;
+            k_reduce_splits<<<grid_for((int64_t)N * K, 256), 256, 0, st>>>(d->partials, d->grads + d->w_off[l], (int64_t)N * K, w_splits);
+            const int col_splits = (int)std::min<int64_t>(COL_SPLITS, (B + 31) / 32);
+            const int chunk = (int)((B + col_splits - 1) / col_splits);
+            k_colsum_partial<<<dim3((N + 127) / 128, col_splits), 128, 0, st>>>(dcur, (int)B, N, N, d->partials, chunk);
+            k_reduce_splits<<<grid_for(N, 256), 256, 0, st>>>(d->partials, d->grads + d->b_off[l], N, col_splits);
+            if (l > 0) {
+                // dX[B,K] = dY[B,N] * W[N,K], masked by relu'(in)
+                const float *W = d->params[0] + d->w_off[l];
+                if ((rc = gemm(1, (int)B, K, N, dcur, N, W, K, dnext, K, nullptr, 0, in, K, 1, st))) return rc;
+                float *t = dcur; dcur = dnext; dnext = t;
+            }
         }
     }
     k_grad_norm<<<1, 1024, 0, st>>>(d->grads, d->n_params, 10.f, d->scalars);

@@ -164,6 +164,28 @@ __device__ __forceinline__ void stage_weights(uint8_t *dst, const float *w, int 
     }
 }
 
+// 16-byte row accesses with a scalar tail (rows are n_hidden floats, 16-byte
+// aligned when n_hidden % 4 == 0): 4x fewer memory transactions than scalars.
+__device__ __forceinline__ float4 load4(const float *row, int col, int n, bool vec)
+{
+    if (vec && col + 3 < n) return *reinterpret_cast<const float4 *>(row + col);
+    float4 v;
+    v.x = col + 0 < n ? row[col + 0] : 0.f;
+    v.y = col + 1 < n ? row[col + 1] : 0.f;
+    v.z = col + 2 < n ? row[col + 2] : 0.f;
+    v.w = col + 3 < n ? row[col + 3] : 0.f;
+    return v;
+}
+
+__device__ __forceinline__ void store4(float *row, int col, int n, bool vec, float4 v)
+{
+    if (vec && col + 3 < n) { *reinterpret_cast<float4 *>(row + col) = v; return; }
+    if (col + 0 < n) row[col + 0] = v.x;
+    if (col + 1 < n) row[col + 1] = v.y;
+    if (col + 2 < n) row[col + 2] = v.z;
+    if (col + 3 < n) row[col + 3] = v.w;
+}
+
 // epilogue of a hidden layer: this thread's accumulator row -> bias, ReLU ->
 // next layer's A operand in shared memory (+ optional fp32 copy in HBM)
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *bias, uint8_t *h_smem, int row_in_tile,
@@ -176,9 +198,9 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = fmaxf(v[i] + bias[c8 * 8 + i], 0.f);
         if (h_out_row) {
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (c8 * 8 + i < n_hidden) h_out_row[c8 * 8 + i] = v[i];
+            const bool vec = (n_hidden & 3) == 0;
+            store4(h_out_row, c8 * 8, n_hidden, vec, make_float4(v[0], v[1], v[2], v[3]));
+            store4(h_out_row, c8 * 8 + 4, n_hidden, vec, make_float4(v[4], v[5], v[6], v[7]));
         }
         float4 lo = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
         float4 hi = make_float4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
@@ -306,6 +328,298 @@ __global__ void __launch_bounds__(TILE_M, 1) k_mlp_forward_tc(const Params p)
     }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+
+// ===================================================================== backward
+// Backward pass of the same network on the tensor cores, in two kernels.
+//
+// k_mlp_backward_data_tc: the error chain dQ -> dH2 -> dH1, the forward's
+// structure run with transposed weights:
+//     dH2 = (dQ  * W3) .* (H2 > 0)        M 128, N 112, K 8   (one MMA)
+//     dH1 = (dH2 * W2) .* (H1 > 0)        M 128, N 112, K 104
+// W3^T and W2^T are staged once per CTA as K-major B operands; the ReLU masks
+// come from the forward's H1 / H2 in HBM; dH2 goes back into shared memory as
+// the next A operand and both error signals are written out in fp32 for the
+// weight-gradient kernel.
+struct BwdParams {
+    const float *w2, *w3;          // W2[h][h], W3[n_out][h], torch layout
+    int n_hidden, n_out;
+    const float *dq;               // [rows][n_out]
+    const float *h1, *h2;          // [rows][n_hidden], post-ReLU
+    float *dh1, *dh2;              // [rows][n_hidden]
+    int64_t rows;
+};
+
+struct SmemBwd {
+    static constexpr int W3T = 0;                                   // [2][112][16 B]   (K = 8 actions padded)
+    static constexpr int W2T = W3T + 2 * Smem::CHUNK_H;             // [26][112][16 B]
+    static constexpr int DQ = W2T + (K_HID / 4) * Smem::CHUNK_H;    // [2][128][16 B]
+    static constexpr int DH = DQ + 2 * Smem::CHUNK_A;               // [26][128][16 B]
+    static constexpr int BAR = DH + (K_HID / 4) * Smem::CHUNK_A;
+    static constexpr int TOTAL = BAR + 16;
+};
+
+// B operand holding W^T: row r = input index (< n_in), K index = output index (< n_out)
+__device__ __forceinline__ void stage_weights_T(uint8_t *dst, const float *w, int n_out, int n_in, int rows_pad, int k_pad)
+{
+    const int chunks = k_pad / 4;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < chunks * rows_pad; e += blockDim.x) {
+        const int c = e / rows_pad, r = e - c * rows_pad;      // consecutive threads: consecutive r (coalesced reads of W rows)
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n_in) {
+            const int k = 4 * c;
+            v.x = k + 0 < n_out ? to_tf32(__ldg(w + (size_t)(k + 0) * n_in + r)) : 0.f;
+            v.y = k + 1 < n_out ? to_tf32(__ldg(w + (size_t)(k + 1) * n_in + r)) : 0.f;
+            v.z = k + 2 < n_out ? to_tf32(__ldg(w + (size_t)(k + 2) * n_in + r)) : 0.f;
+            v.w = k + 3 < n_out ? to_tf32(__ldg(w + (size_t)(k + 3) * n_in + r)) : 0.f;
+        }
+        *reinterpret_cast<float4 *>(dst + (size_t)c * rows_pad * 16 + r * 16) = v;
+    }
+}
+
+__device__ __forceinline__ uint32_t tmem_alloc_and_sync(uint32_t *slot, int warp, uint32_t cols_256_or_128)
+{
+    if (warp == 0) {
+        if (cols_256_or_128 == 256)
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(slot)) : "memory");
+        else
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *slot;
+}
+
+__global__ void __launch_bounds__(TILE_M, 1) k_mlp_backward_data_tc(const BwdParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_base_slot;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + SmemBwd::BAR);
+    const int warp = threadIdx.x >> 5;
+    stage_weights_T(smem + SmemBwd::W3T, p.w3, p.n_out, p.n_hidden, N_HID, 8);
+    stage_weights_T(smem + SmemBwd::W2T, p.w2, p.n_hidden, p.n_hidden, N_HID, K_HID);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t tmem = tmem_alloc_and_sync(&tmem_base_slot, warp, 256);
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t d0 = tmem, d1 = tmem + 128;
+    const uint32_t a_dq = smem_u32(smem + SmemBwd::DQ), a_dh = smem_u32(smem + SmemBwd::DH);
+    const uint32_t b_w3t = smem_u32(smem + SmemBwd::W3T), b_w2t = smem_u32(smem + SmemBwd::W2T);
+    constexpr uint32_t IDESC = make_idesc(TILE_M, N_HID);
+    uint32_t phase = 0;
+    const bool vec = (p.n_hidden & 3) == 0;
+    const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * TILE_M + threadIdx.x;
+        const bool valid = row < p.rows;
+        {   // dQ row -> A operand (K = 8: 4 actions + zero padding)
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const float *q = p.dq + row * p.n_out;
+                v.x = q[0];
+                v.y = p.n_out > 1 ? q[1] : 0.f;
+                v.z = p.n_out > 2 ? q[2] : 0.f;
+                v.w = p.n_out > 3 ? q[3] : 0.f;
+                v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            }
+            *reinterpret_cast<float4 *>(smem + SmemBwd::DQ + threadIdx.x * 16) = v;
+            *reinterpret_cast<float4 *>(smem + SmemBwd::DQ + Smem::CHUNK_A + threadIdx.x * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (threadIdx.x == 0) {
+            mma_tf32(d0, make_desc(a_dq, Smem::CHUNK_A, 128), make_desc(b_w3t, Smem::CHUNK_H, 128), IDESC, 0);
+            mma_commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+        // dH2 = D0 .* (H2 > 0) -> HBM and next A operand
+#pragma unroll 1
+        for (int c8 = 0; c8 < K_HID / 8; c8++) {
+            float v[8];
+            tmem_ld8(tmem_row + c8 * 8, v);
+            if (valid) {
+                const float4 m0 = load4(p.h2 + row * p.n_hidden, c8 * 8, p.n_hidden, vec);
+                const float4 m1 = load4(p.h2 + row * p.n_hidden, c8 * 8 + 4, p.n_hidden, vec);
+                v[0] = m0.x > 0.f ? v[0] : 0.f; v[1] = m0.y > 0.f ? v[1] : 0.f;
+                v[2] = m0.z > 0.f ? v[2] : 0.f; v[3] = m0.w > 0.f ? v[3] : 0.f;
+                v[4] = m1.x > 0.f ? v[4] : 0.f; v[5] = m1.y > 0.f ? v[5] : 0.f;
+                v[6] = m1.z > 0.f ? v[6] : 0.f; v[7] = m1.w > 0.f ? v[7] : 0.f;
+                store4(p.dh2 + row * p.n_hidden, c8 * 8, p.n_hidden, vec, make_float4(v[0], v[1], v[2], v[3]));
+                store4(p.dh2 + row * p.n_hidden, c8 * 8 + 4, p.n_hidden, vec, make_float4(v[4], v[5], v[6], v[7]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = 0.f;
+            }
+            float4 lo = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+            float4 hi = make_float4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
+            *reinterpret_cast<float4 *>(smem + SmemBwd::DH + (size_t)(2 * c8) * Smem::CHUNK_A + threadIdx.x * 16) = lo;
+            *reinterpret_cast<float4 *>(smem + SmemBwd::DH + (size_t)(2 * c8 + 1) * Smem::CHUNK_A + threadIdx.x * 16) = hi;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < K_HID / 8; k++)
+                mma_tf32(d1, make_desc(a_dh + k * 2 * Smem::CHUNK_A, Smem::CHUNK_A, 128),
+                         make_desc(b_w2t + k * 2 * Smem::CHUNK_H, Smem::CHUNK_H, 128), IDESC, k > 0);
+            mma_commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c8 = 0; c8 < K_HID / 8; c8++) {
+            float v[8];
+            tmem_ld8(tmem_row + 128 + c8 * 8, v);
+            if (valid) {
+                const float4 m0 = load4(p.h1 + row * p.n_hidden, c8 * 8, p.n_hidden, vec);
+                const float4 m1 = load4(p.h1 + row * p.n_hidden, c8 * 8 + 4, p.n_hidden, vec);
+                store4(p.dh1 + row * p.n_hidden, c8 * 8, p.n_hidden, vec,
+                       make_float4(m0.x > 0.f ? v[0] : 0.f, m0.y > 0.f ? v[1] : 0.f, m0.z > 0.f ? v[2] : 0.f, m0.w > 0.f ? v[3] : 0.f));
+                store4(p.dh1 + row * p.n_hidden, c8 * 8 + 4, p.n_hidden, vec,
+                       make_float4(m1.x > 0.f ? v[4] : 0.f, m1.y > 0.f ? v[5] : 0.f, m1.z > 0.f ? v[6] : 0.f, m1.w > 0.f ? v[7] : 0.f));
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+}
+
+// k_wgrad_tc: weight (and bias) gradients, a reduction over samples:
+//     D[m][n] = sum_b P[b][m] * Q[b][n]          (+ a column of ones appended
+//     to Q, so D[m][ndim] = sum_b P[b][m] is the bias gradient)
+// On the tensor core this is a GEMM whose K dimension is the sample index, so
+// both operands must have samples contiguous in 16-byte chunks.  Each thread
+// owns one sample of the 128-sample tile and scatters its P and Q rows
+// TRANSPOSED into shared memory (K-major operands [m][b] and [n][b]); 16
+// tcgen05.mma (K = 8 samples each) accumulate the tile into TMEM, which keeps
+// accumulating across all tiles of the CTA.  Each CTA finally writes its
+// [128][npad] partial; k_wgrad_finish folds the partials in CTA order
+// (deterministic).
+struct WgradParams {
+    const float *P; int ldp, mdim;     // A side: M = mdim (<= 128)
+    const float *Q; int ldq, ndim;     // B side: N = ndim (+1 ones column), padded to npad
+    int npad, add_ones;
+    int64_t rows;
+    float *partial;                    // [gridDim.x][128][npad]
+};
+
+struct SmemWg {
+    static constexpr int AT = 0;                       // [32][128][16 B]
+    static constexpr int BT = AT + 32 * Smem::CHUNK_A; // [32][npad][16 B], npad <= 112
+    static constexpr int BAR = BT + 32 * N_HID * 16;
+    static constexpr int TOTAL = BAR + 16;
+};
+
+// one sample's row -> column b of a K-major operand (stride 16 B between rows)
+__device__ __forceinline__ void scatter_row(uint8_t *dst, const float *row, int n, bool vec, bool valid)
+{
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            v[u] = (valid && c0 + 4 * u < n) ? load4(row, c0 + 4 * u, n, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int c = c0 + 4 * u;
+            if (c + 0 < n) *reinterpret_cast<float *>(dst + (c + 0) * 16) = to_tf32(v[u].x);
+            if (c + 1 < n) *reinterpret_cast<float *>(dst + (c + 1) * 16) = to_tf32(v[u].y);
+            if (c + 2 < n) *reinterpret_cast<float *>(dst + (c + 2) * 16) = to_tf32(v[u].z);
+            if (c + 3 < n) *reinterpret_cast<float *>(dst + (c + 3) * 16) = to_tf32(v[u].w);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TILE_M, 1) k_wgrad_tc(const WgradParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_base_slot;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + SmemWg::BAR);
+    const int warp = threadIdx.x >> 5;
+    const int chunk_b = p.npad * 16;
+    for (int e = threadIdx.x; e < (SmemWg::BAR) / 16; e += blockDim.x)
+        reinterpret_cast<float4 *>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t tmem = tmem_alloc_and_sync(&tmem_base_slot, warp, 128);
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t a_t = smem_u32(smem + SmemWg::AT), b_t = smem_u32(smem + SmemWg::BT);
+    const uint32_t idesc = make_idesc(TILE_M, p.npad);
+    uint32_t phase = 0;
+    bool first = true;
+    const int cb = threadIdx.x >> 2, l4 = threadIdx.x & 3;      // this sample's chunk and position in it
+    uint8_t *a_dst = smem + SmemWg::AT + (size_t)cb * Smem::CHUNK_A + l4 * 4;
+    uint8_t *b_dst = smem + SmemWg::BT + (size_t)cb * chunk_b + l4 * 4;
+    const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * TILE_M + threadIdx.x;
+        const bool valid = row < p.rows;
+        const float *prow = p.P + row * p.ldp, *qrow = p.Q + row * p.ldq;
+        // rows are read 8 x 16 bytes at a time (loads in flight together), then
+        // scattered transposed: element (sample b, column m) -> operand row m, K slot b
+        const bool pvec = (p.ldp & 3) == 0, qvec = (p.ldq & 3) == 0;
+        scatter_row(a_dst, prow, p.mdim, pvec, valid);
+        scatter_row(b_dst, qrow, p.ndim, qvec, valid);
+        if (p.add_ones) *reinterpret_cast<float *>(b_dst + p.ndim * 16) = valid ? 1.f : 0.f;
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < TILE_M / 8; s++)
+                mma_tf32(tmem, make_desc(a_t + s * 2 * Smem::CHUNK_A, Smem::CHUNK_A, 128),
+                         make_desc(b_t + s * 2 * chunk_b, chunk_b, 128), idesc, (!first || s > 0) ? 1u : 0u);
+            mma_commit(mbar);
+        }
+        first = false;
+        mbar_wait(mbar, phase); phase ^= 1;      // operands may be overwritten by the next tile
+        tc_fence_after();
+    }
+    // this thread's accumulator row (m = threadIdx.x) -> partial
+    float *out = p.partial + ((size_t)blockIdx.x * TILE_M + threadIdx.x) * p.npad;
+    for (int c8 = 0; c8 < p.npad / 8; c8++) {
+        float v[8];
+        tmem_ld8(tmem_row + c8 * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[c8 * 8 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
+}
+
+// dW[m][n] = sum_g partial[g][m][n], db[m] = sum_g partial[g][m][ndim]
+__global__ void k_wgrad_finish(const float *partial, int n_partials, int npad, int mdim, int ndim, float *dW, float *db)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = mdim * (ndim + 1);
+    if (idx >= total) return;
+    const int m = idx / (ndim + 1), n = idx - m * (ndim + 1);
+    float s0 = 0.f, s1 = 0.f;
+    int g = 0;
+    for (; g + 1 < n_partials; g += 2) {
+        s0 += partial[((size_t)g * TILE_M + m) * npad + n];
+        s1 += partial[((size_t)(g + 1) * TILE_M + m) * npad + n];
+    }
+    if (g < n_partials) s0 += partial[((size_t)g * TILE_M + m) * npad + n];
+    const float s = s0 + s1;
+    if (n < ndim) dW[(size_t)m * ndim + n] = s;
+    else if (db) db[m] = s;
 }
 
 }  // namespace tc

@@ -73,6 +73,7 @@ SYMBOLS = [
     ("sgk_dqn_replay_count", _i64, [_vp]),
     ("sgk_dqn_get_params", _i32, [_vp, _i32, _vp, _vp]),
     ("sgk_dqn_set_params", _i32, [_vp, _i32, _vp, _vp]),
+    ("sgk_dqn_get_grads", _i32, [_vp, _vp, _vp]),
     ("sgk_dqn_sync_target", _i32, [_vp, _vp]),
     ("sgk_dqn_qvalues", _i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
     ("sgk_dqn_replay_add", _i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -44,6 +44,12 @@ class BatchedDeepQ:
         check(self.L.sgk_dqn_get_params(self.h, which, _p(out), _stream()))
         return out
 
+    def get_grads(self):
+        """Gradients of the last learn step, before clipping (flat, torch order)."""
+        out = torch.empty(self.n_params, dtype=torch.float32, device=self.env.device)
+        check(self.L.sgk_dqn_get_grads(self.h, _p(out), _stream()))
+        return out
+
     def set_params(self, flat, which=0):
         flat = flat.to(self.env.device, torch.float32).contiguous()
         assert flat.numel() == self.n_params

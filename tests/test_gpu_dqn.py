@@ -167,6 +167,55 @@ def test_tcgen05_forward_matches_fp32(env_id, rows):
     assert torch.equal(q_tc.argmax(1)[clear], q_ref.argmax(1)[clear])
 
 
+@pytest.mark.parametrize("env_id", ["BoatRace-v0", "SideEffectsSokoban-v0", "TomatoWatering-v0"])
+@pytest.mark.parametrize("batch", [64, 1000, 20000])
+def test_tcgen05_backward_gradients_match_autograd(env_id, batch):
+    """Backward on the tensor cores (error chain + sample-reduction weight
+    gradients, TF32 operands) against torch autograd in fp32 and against the
+    fp32 FFMA backward.  TF32 keeps 10 mantissa bits and the gradients are sums
+    of cancelling terms, so the stated tolerance per parameter tensor is a
+    relative L2 error of 2e-2 and 5e-2 of the largest |gradient| pointwise
+    (measured: 3e-4 .. 1e-2, scripts/tc_grad_diag.py); overall cosine >= 0.9999."""
+    import gridfast
+    torch.manual_seed(batch)
+    dev = torch.device("cuda", 0)
+    env = gridfast.BatchedEnv(env_id, 4, seed=1)
+    rs = np.random.RandomState(batch)
+    s = torch.as_tensor(rs.randint(0, 6, size=(batch, env.hw)).astype(np.uint8)).to(dev)
+    s2 = torch.as_tensor(rs.randint(0, 6, size=(batch, env.hw)).astype(np.uint8)).to(dev)
+    a = torch.as_tensor(rs.randint(0, 4, size=batch).astype(np.uint8)).to(dev)
+    r = torch.as_tensor(rs.choice([-1.0, 2.0, 49.0], size=batch)).to(dev)
+    term = torch.as_tensor((rs.rand(batch) < 0.1).astype(np.uint8)).to(dev)
+    Q = build_Q(env.hw, 2, 100, 4).to(dev)
+    T = build_Q(env.hw, 2, 100, 4).to(dev)
+    Qs = Q(s.float()).gather(1, a.long().reshape(-1, 1)).reshape(-1)
+    nxt = T(s2.float()).max(1)[0]
+    nxt[term.bool()] = 0
+    loss = F.mse_loss(Qs, 0.99 * nxt + r.float())
+    loss.backward()
+    ref = torch.cat([p.grad.reshape(-1) for m in Q.modules() if isinstance(m, nn.Linear) for p in (m.weight, m.bias)])
+    grads = {}
+    for use_tc in (False, True):
+        agent = gridfast.BatchedDeepQ(env, batch_size=batch, reference_bxb_loss=False)
+        agent.load_torch_module(Q, 0)
+        agent.load_torch_module(T, 1)
+        agent.set_tensor_cores(use_tc)
+        agent.learn_batch(s, a, r, s2, term)
+        grads[use_tc] = agent.get_grads()
+    assert torch.allclose(grads[False], ref, rtol=1e-4, atol=1e-6 * ref.abs().max().item() + 1e-7)
+    off = 0
+    for m in Q.modules():
+        if isinstance(m, nn.Linear):
+            for prm in (m.weight, m.bias):
+                n = prm.numel()
+                g_ref, g_tc = ref[off:off + n], grads[True][off:off + n]
+                assert ((g_tc - g_ref).norm() / g_ref.norm()).item() <= 2e-2, (env_id, batch, off)
+                assert (g_tc - g_ref).abs().max().item() <= 5e-2 * g_ref.abs().max().item() + 1e-7, (env_id, batch, off)
+                off += n
+    cos = torch.dot(grads[True], ref) / (grads[True].norm() * ref.norm())
+    assert cos.item() >= 0.9999
+
+
 def test_tcgen05_learn_step_tracks_torch():
     import gridfast
     torch.manual_seed(5)
