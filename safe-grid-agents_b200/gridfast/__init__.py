@@ -5,7 +5,7 @@ Public surface
     BatchedDeepQ                        deep-Q agent (one network, N environments)
     GridworldEnv, make                  single-env adapter with the gym-style
                                         API the reference drives
-    GpuTabularQAgent                    drop-in for the reference TabularQAgent
+    GpuTabularQAgent, GpuDeepQAgent     drop-ins for the reference TabularQAgent / DeepQAgent
     register_with_reference             put them into the reference's
                                         ENV_MAP / AGENT_MAP registries
 There is no CPU fallback: constructing any of these without the CUDA library
@@ -15,11 +15,11 @@ from ._lib import (ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, Q_PRIVATE, Q_SHARED,
                    RNG_PHILOX, RNG_REPLAY, SgkError)
 from .batched import BatchedEnv, BatchedTabularQ, KIND_BY_ALIAS, KIND_BY_ID
 from .deepq import BatchedDeepQ
-from .adapters import (GpuTabularQAgent, GridworldEnv, make,
+from .adapters import (GpuDeepQAgent, GpuTabularQAgent, GridworldEnv, make,
                        register_with_reference)
 
 __all__ = [
-    "BatchedEnv", "BatchedTabularQ", "BatchedDeepQ", "GridworldEnv", "GpuTabularQAgent", "make",
+    "BatchedEnv", "BatchedTabularQ", "BatchedDeepQ", "GridworldEnv", "GpuTabularQAgent", "GpuDeepQAgent", "make",
     "register_with_reference", "SgkError", "ENV_BOAT", "ENV_SOKOBAN", "ENV_TOMATO",
     "Q_PRIVATE", "Q_SHARED", "RNG_PHILOX", "RNG_REPLAY", "KIND_BY_ALIAS", "KIND_BY_ID",
 ]

@@ -290,6 +290,7 @@ def register_with_reference(env_map=None, agent_map=None, gym_module=None, **env
     previous = None
     if agent_map is not None:
         agent_map["tabular-q"] = GpuTabularQAgent
+        agent_map["deep-q"] = GpuDeepQAgent
     if gym_module is not None:
         previous = gym_module.make
 
@@ -302,3 +303,102 @@ def register_with_reference(env_map=None, agent_map=None, gym_module=None, **env
 
         gym_module.make = _make
     return previous
+
+
+class _ReplayView:
+    """What dqn_warmup touches through `agent.replay` (common/warmup.py:21)."""
+
+    def __init__(self, agent):
+        self._agent = agent
+
+    def add(self, state, action, reward, successor, terminal):
+        self._agent._replay_add(state, action, reward, successor, terminal)
+
+    def __len__(self):
+        return int(self._agent.net.replay_count)
+
+
+class GpuDeepQAgent:
+    """Drop-in for DeepQAgent (common/agents/value.py:61-187) behind the
+    reference's dqn_warmup / dqn_learn loops (common/warmup.py:8-23,
+    common/learn.py:29-58): constructor (env, args) reading args.lr,
+    .discount, .epsilon, .epsilon_anneal, .batch_size, .n_layers, .n_hidden,
+    .replay_capacity; act, act_explore, learn(..., terminal, history),
+    update_epsilon, sync_target_Q, replay.add.  An N == 1 view of
+    BatchedDeepQ: the network, the replay ring and the optimiser live on the
+    GPU.  The exploration decision is drawn on the host from a private numpy
+    stream seeded with args.seed (the reference samples a torch Categorical on
+    the device, value.py:94-111 -- same distribution, different stream:
+    statistical parity only, SURVEY hard part H7)."""
+
+    def __init__(self, env, args):
+        if not isinstance(env, GridworldEnv):
+            raise SgkError("GpuDeepQAgent needs a gridfast GridworldEnv")
+        from .deepq import BatchedDeepQ
+        self.env = env
+        self.action_n = env.action_space.n
+        self.discount = args.discount
+        self.lr = args.lr
+        self.batch_size = args.batch_size
+        self._final_epsilon = args.epsilon
+        self._anneal = args.epsilon_anneal
+        self.net = BatchedDeepQ(
+            env.batched, n_layers=args.n_layers, n_hidden=args.n_hidden,
+            replay_capacity=args.replay_capacity, batch_size=args.batch_size, lr=args.lr,
+            discount=args.discount, epsilon=args.epsilon, epsilon_anneal=args.epsilon_anneal,
+            sync_every=getattr(args, "sync_every", 10000),
+            reference_bxb_loss=getattr(args, "reference_bxb_loss", True), seed=getattr(args, "seed", 0) or 0)
+        if getattr(args, "tensor_cores", False):
+            self.net.set_tensor_cores(True)
+        self.replay = _ReplayView(self)
+        self._k = 0
+        self.epsilon = self._epsilon_at(0)      # value.py:76: the first pop, no 0.0 override
+        dev = env.batched.device
+        hw = env.batched.hw
+        self._s = torch.zeros(1, hw, dtype=torch.uint8, device=dev)
+        self._s2 = torch.zeros(1, hw, dtype=torch.uint8, device=dev)
+        self._a = torch.zeros(1, dtype=torch.uint8, device=dev)
+        self._r = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._term = torch.zeros(1, dtype=torch.uint8, device=dev)
+        self._learn_steps = 0
+        self._rs = np.random.RandomState(getattr(args, "seed", 0) or 0)
+
+    def _epsilon_at(self, k):
+        last = self._anneal - 1 if self._anneal > 1 else 0
+        return 1.0 - (1 - self._final_epsilon) * min(k, last) / self._anneal
+
+    def _upload(self, buf, state):
+        buf.copy_(torch.from_numpy(np.asarray(state).reshape(1, -1).astype(np.uint8)))
+
+    def act(self, state):
+        """value.py:89-92: a 1-element tensor, like scores.argmax(1)."""
+        self._upload(self._s, state)
+        return self.net.q_values(self._s).argmax(1)
+
+    def act_explore(self, state):
+        if self._rs.random_sample() < self.epsilon:
+            return int(self._rs.randint(0, self.action_n))
+        return int(self.act(state).item())
+
+    def _replay_add(self, state, action, reward, successor, terminal):
+        self._upload(self._s, state)
+        self._upload(self._s2, successor)
+        self._a[0] = _as_int_action(action)
+        self._r[0] = float(reward)
+        self._term[0] = 1 if terminal else 0
+        self.net.replay_add(self._s, self._a, self._r, self._s2, self._term)
+
+    def learn(self, state, action, reward, successor, terminal, history):
+        self._replay_add(state, action, reward, successor, terminal)
+        scalars = self.net.learn(self._learn_steps)
+        self._learn_steps += 1
+        history["writer"].add_scalar("Train/value_loss", float(scalars[0].item()), history["t"])   # value.py:124
+        return history
+
+    def sync_target_Q(self):
+        self.net.sync_target()
+
+    def update_epsilon(self):
+        self._k += 1
+        self.epsilon = self._epsilon_at(self._k)
+        return self.epsilon

