@@ -18,16 +18,20 @@
  *   - safe-grid-gym's bookkeeping: episode_return, cumulative hidden reward
  *     and its per-step difference, last performance.
  *
- * Validated against the Python oracle (tests/test_oracle_c.py) and, through
- * the golden fixtures, against the live reference agent.
+ * Validated against the Python oracle and, through the golden fixtures,
+ * against the live reference agent (tests/test_oracle_envs.py,
+ * tests/test_oracle_golden.py).
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: no FMA contraction,
  * the float64 arithmetic must round exactly like numpy's).
  */
+#define _GNU_SOURCE
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #define CG_BOAT 0
 #define CG_SOKOBAN 1
@@ -541,60 +545,106 @@ static void ssrl_episode_end(cg_sim *s, int64_t i, cg_table *tab)
     s->hist_n[i] = 0;
 }
 
+/* One environment, one lock-step of the tabq_learn body.  In private mode
+ * it touches only environment i's state, so calls for different i commute. */
+typedef struct {
+    cg_sim *s;
+    int64_t step, lo, hi;
+    double eps;
+    unsigned char *actions_out, *done_out, *boards_out;
+    double *reward_out, *hidden_out;
+    int overflow;
+} cg_job;
+
+static void rollout_range(cg_job *j)
+{
+    cg_sim *s = j->s;
+    const cg_level *L = &s->L;
+    for (int64_t i = j->lo; i < j->hi; i++) {
+        cg_env *e = &s->env[i];
+        cg_rng *g = &s->rng[i];
+        cg_table *tab = &s->tab[s->q_mode == CG_Q_PRIVATE ? i : 0];
+        g->step = (uint64_t)s->t;
+        unsigned char skey[MAXHW];
+        memset(skey, 0, MAXHW);
+        memcpy(skey, e->board, (size_t)L->HW);
+        /* act_explore (value.py:37-42) */
+        int action;
+        if (rng_agent_uniform(g) < j->eps) action = rng_agent_choice(g);
+        else action = argmax_first(table_find(tab, skey, L->HW, s->c_prior)->q);
+        if (s->ssrl) hist_push(s, i, skey);
+        double r, h; int done;
+        env_step(L, e, g, action, &r, &h, &done);
+        double learn_r = r;
+        if (s->cheat) learn_r = (h != h) ? 0.0 : h;     /* learn.py:72-73; None -> 0 */
+        /* learn (value.py:44-52 / ssrl/agents.py:34-42) */
+        unsigned char nkey[MAXHW];
+        memset(nkey, 0, MAXHW);
+        memcpy(nkey, e->board, (size_t)L->HW);
+        if (s->ssrl) learn_r = learn_r * (1 - table_find(tab, skey, L->HW, s->c_prior)->c);
+        cg_entry *nx = table_find(tab, nkey, L->HW, s->c_prior);
+        double target = learn_r + s->discount * nx->q[argmax_first(nx->q)];
+        if (s->q_mode == CG_Q_PRIVATE) {
+            cg_entry *cur = table_find(tab, skey, L->HW, s->c_prior);
+            cur->q[action] += s->lr * (target - cur->q[action]);
+        } else {
+            table_find(tab, skey, L->HW, s->c_prior);
+            s->target[i] = target; s->act[i] = action; memcpy(s->skey + i * MAXHW, skey, MAXHW);
+        }
+        trace_fold(L, e, action, r, h, done);
+        int64_t o = j->step * s->n_envs + i;
+        if (j->actions_out) j->actions_out[o] = (unsigned char)action;
+        if (j->reward_out) j->reward_out[o] = r;
+        if (j->hidden_out) j->hidden_out[o] = h;
+        if (j->done_out) j->done_out[o] = (unsigned char)done;
+        if (j->boards_out) memcpy(j->boards_out + o * L->HW, e->board, (size_t)L->HW);
+        if (done) {
+            if (s->ssrl) ssrl_episode_end(s, i, tab);
+            g->step = (uint64_t)(s->t + 1);
+            env_reset(L, e, g);
+        }
+        j->overflow |= g->overflow;
+    }
+}
+
+static void *rollout_thread(void *arg) { rollout_range((cg_job *)arg); return NULL; }
+
+#define CG_MAX_THREADS 64
+static int cg_threads = 0;
+void cg_set_threads(int n) { cg_threads = n < 1 ? 1 : n > CG_MAX_THREADS ? CG_MAX_THREADS : n; }
+
 /* Optional [n_steps][n_envs] traces; any pointer may be NULL.
  * boards_out is [n_steps][n_envs][HW] (successor board of each step, before
- * the auto-reset). Returns 0, or -1 if a replay stream ran dry. */
+ * the auto-reset). Returns 0, or -1 if a replay stream ran dry.
+ * Private tables with many environments: the loop over environments runs on
+ * cg_threads host threads (environments are independent there). */
 int cg_rollout(cg_sim *s, int64_t n_steps, unsigned char *actions_out, double *reward_out,
                double *hidden_out, unsigned char *done_out, unsigned char *boards_out)
 {
     const cg_level *L = &s->L;
+    if (cg_threads == 0) {
+        long n = sysconf(_SC_NPROCESSORS_ONLN);
+        cg_set_threads(n > 0 ? (int)n : 1);
+    }
+    const int nt = (s->q_mode == CG_Q_PRIVATE && s->n_envs >= 4096) ? cg_threads : 1;
     for (int64_t step = 0; step < n_steps; step++, s->t++) {
-        double eps = cg_epsilon_at(s->epsilon, s->anneal, s->t);
-        for (int64_t i = 0; i < s->n_envs; i++) {
-            cg_env *e = &s->env[i];
-            cg_rng *g = &s->rng[i];
-            cg_table *tab = &s->tab[s->q_mode == CG_Q_PRIVATE ? i : 0];
-            g->step = (uint64_t)s->t;
-            unsigned char skey[MAXHW];
-            memset(skey, 0, MAXHW);
-            memcpy(skey, e->board, (size_t)L->HW);
-            /* act_explore (value.py:37-42) */
-            int action;
-            if (rng_agent_uniform(g) < eps) action = rng_agent_choice(g);
-            else action = argmax_first(table_find(tab, skey, L->HW, s->c_prior)->q);
-            if (s->ssrl) hist_push(s, i, skey);
-            double r, h; int done;
-            env_step(L, e, g, action, &r, &h, &done);
-            double learn_r = r;
-            if (s->cheat) learn_r = (h != h) ? 0.0 : h;     /* learn.py:72-73; None -> 0 */
-            /* learn (value.py:44-52 / ssrl/agents.py:34-42) */
-            unsigned char nkey[MAXHW];
-            memset(nkey, 0, MAXHW);
-            memcpy(nkey, e->board, (size_t)L->HW);
-            if (s->ssrl) learn_r = learn_r * (1 - table_find(tab, skey, L->HW, s->c_prior)->c);
-            cg_entry *nx = table_find(tab, nkey, L->HW, s->c_prior);
-            double target = learn_r + s->discount * nx->q[argmax_first(nx->q)];
-            if (s->q_mode == CG_Q_PRIVATE) {
-                cg_entry *cur = table_find(tab, skey, L->HW, s->c_prior);
-                cur->q[action] += s->lr * (target - cur->q[action]);
-            } else {
-                table_find(tab, skey, L->HW, s->c_prior);
-                s->target[i] = target; s->act[i] = action; memcpy(s->skey + i * MAXHW, skey, MAXHW);
-            }
-            trace_fold(L, e, action, r, h, done);
-            int64_t o = step * s->n_envs + i;
-            if (actions_out) actions_out[o] = (unsigned char)action;
-            if (reward_out) reward_out[o] = r;
-            if (hidden_out) hidden_out[o] = h;
-            if (done_out) done_out[o] = (unsigned char)done;
-            if (boards_out) memcpy(boards_out + o * L->HW, e->board, (size_t)L->HW);
-            if (done) {
-                if (s->ssrl) ssrl_episode_end(s, i, tab);
-                g->step = (uint64_t)(s->t + 1);
-                env_reset(L, e, g);
-            }
-            if (g->overflow) return -1;
+        cg_job jobs[CG_MAX_THREADS];
+        pthread_t tid[CG_MAX_THREADS];
+        const int64_t chunk = (s->n_envs + nt - 1) / nt;
+        for (int k = 0; k < nt; k++) {
+            cg_job *j = &jobs[k];
+            j->s = s; j->step = step; j->eps = cg_epsilon_at(s->epsilon, s->anneal, s->t);
+            j->lo = k * chunk; j->hi = j->lo + chunk < s->n_envs ? j->lo + chunk : s->n_envs;
+            if (j->lo > s->n_envs) j->lo = s->n_envs;
+            j->actions_out = actions_out; j->done_out = done_out; j->boards_out = boards_out;
+            j->reward_out = reward_out; j->hidden_out = hidden_out; j->overflow = 0;
         }
+        if (nt == 1) rollout_range(&jobs[0]);
+        else {
+            for (int k = 0; k < nt; k++) pthread_create(&tid[k], NULL, rollout_thread, &jobs[k]);
+            for (int k = 0; k < nt; k++) pthread_join(tid[k], NULL);
+        }
+        for (int k = 0; k < nt; k++) if (jobs[k].overflow) return -1;
         if (s->q_mode == CG_Q_SHARED) {
             /* synchronous batch: every env read Q_t above; per (state, action)
                the update of the lowest env id is applied, the others dropped */
@@ -696,15 +746,16 @@ void cg_get_boards(const cg_sim *s, unsigned char *out)
 }
 
 /* per env: episode_return, hidden_cum, last_return, last_perf, sum_return,
- * sum_perf, sum_margin_pos, max_return  (8 doubles) and episodes,
+ * sum_perf, sum_margin_pos, max_return, max_perf, max_margin (10 doubles) and episodes,
  * n_margin_pos, frame, perf_defined, hidden_defined (5 int64) */
 void cg_get_env_stats(const cg_sim *s, double *f_out, int64_t *i_out, uint64_t *hash_out)
 {
     for (int64_t i = 0; i < s->n_envs; i++) {
         const cg_env *e = &s->env[i];
-        double *f = f_out + i * 8; int64_t *n = i_out + i * 5;
+        double *f = f_out + i * 10; int64_t *n = i_out + i * 5;
         f[0] = e->episode_return; f[1] = e->hidden_cum; f[2] = e->last_return; f[3] = e->last_perf;
         f[4] = e->sum_return; f[5] = e->sum_perf; f[6] = e->sum_margin_pos; f[7] = e->max_return;
+        f[8] = e->max_perf; f[9] = e->max_margin;
         n[0] = e->episodes; n[1] = e->n_margin_pos; n[2] = e->frame; n[3] = e->perf_defined; n[4] = e->hidden_defined;
         if (hash_out) hash_out[i] = e->trace_hash;
     }

@@ -55,6 +55,7 @@ def lib():
         L.cg_epsilon_at.restype = dbl
         L.cg_epsilon_at.argtypes = [dbl, i64, i64]
         L.cg_philox.argtypes = [vp, vp, vp]
+        L.cg_set_threads.argtypes = [i32]
         _lib = L
     return _lib
 
@@ -129,13 +130,14 @@ class Sim:
         return b
 
     def env_stats(self):
-        f = np.zeros((self.n, 8), np.float64)
+        f = np.zeros((self.n, 10), np.float64)
         i = np.zeros((self.n, 5), np.int64)
         hsh = np.zeros(self.n, np.uint64)
         self.L.cg_get_env_stats(self.h, _ptr(f), _ptr(i), _ptr(hsh))
         return dict(episode_return=f[:, 0], hidden_cum=f[:, 1], last_return=f[:, 2],
                     last_perf=f[:, 3], sum_return=f[:, 4], sum_perf=f[:, 5],
-                    sum_margin_pos=f[:, 6], max_return=f[:, 7], episodes=i[:, 0],
+                    sum_margin_pos=f[:, 6], max_return=f[:, 7], max_perf=f[:, 8], max_margin=f[:, 9],
+                    episodes=i[:, 0],
                     n_margin_pos=i[:, 1], frame=i[:, 2], perf_defined=i[:, 3],
                     hidden_defined=i[:, 4], trace_hash=hsh)
 
@@ -156,6 +158,11 @@ class Sim:
         if with_c:
             return keys[:n], q[:n], c[:n]
         return keys[:n], q[:n]
+
+
+def set_threads(n):
+    """Host threads for private-table rollouts (default: all online cores)."""
+    lib().cg_set_threads(n)
 
 
 def epsilon_at(epsilon, anneal, k):

@@ -441,3 +441,59 @@ def test_bad_arguments_fail_loudly():
     a1.rollout(1)
     a1.check()
     assert one.t == 1
+
+
+# ------------------------------------------------------------------ full size, configs 3 and 4
+def test_full_size_sokoban_131072_envs_bit_exact():
+    """BASELINE config 3, one GPU's share: 131,072 side-effects-sokoban
+    environments, private Q, hidden-reward (safety performance) tracking;
+    500 lock-steps = 65.5M env-steps against the (threaded) C oracle."""
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed = 131072, 500, 1
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=100000)
+    env = gf.BatchedEnv("SideEffectsSokoban-v0", n, seed=seed)
+    env.set_trace(True)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **hp)
+    agent.rollout(T)
+    agent.check()
+    sim = cgrid.Sim(cgrid.SOKOBAN, n, seed=seed, **hp)
+    sim.rollout(T)
+    _cmp_stats(env, sim)
+    for i in (0, 65535, n - 1):
+        _cmp_table(env, agent, sim, i)
+    tot, ref = env.totals(), sim.env_stats()
+    assert tot["episodes"] == ref["episodes"].sum()
+    assert tot["sum_performance"] == ref["sum_perf"].sum()      # integer-valued: exact in any order
+    assert tot["max_margin"] == (ref["max_margin"][ref["episodes"] > 0]).max()
+
+
+def test_full_size_tomato_65536_envs_ssrl_and_shared():
+    """BASELINE config 4: 65,536 tomato-watering environments -- the SSRL agent
+    (private tables, corruption estimates, query budget) and the shared-table
+    agent, 200 lock-steps each, bit-exact against the C oracle."""
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed = 65536, 200, 2
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=100000)
+    env = gf.BatchedEnv("TomatoWatering-v0", n, seed=seed)
+    env.set_trace(True)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, capacity=1024, **hp)
+    agent.enable_ssrl(c_prior=0.01, budget=1)
+    agent.rollout(T)
+    agent.check()
+    sim = cgrid.Sim(cgrid.TOMATO, n, seed=seed, ssrl=True, c_prior=0.01, budget=1, **hp)
+    sim.rollout(T)
+    _cmp_stats(env, sim)
+    for i in (0, 40000, n - 1):
+        _cmp_table(env, agent, sim, i, with_c=True)
+    del agent, env, sim
+    env = gf.BatchedEnv("TomatoWatering-v0", n, seed=seed)
+    env.set_trace(True)
+    agent = gf.BatchedTabularQ(env, gf.Q_SHARED, **hp)
+    agent.rollout(T)
+    agent.check()
+    sim = cgrid.Sim(cgrid.TOMATO, n, seed=seed, q_mode=cgrid.Q_SHARED, **hp)
+    sim.rollout(T)
+    _cmp_stats(env, sim)
+    _cmp_table(env, agent, sim, 0)
