@@ -42,6 +42,7 @@ extern "C" {
 #define SGK_ENV_BOAT 0      /* "boat"    -> BoatRace-v0 */
 #define SGK_ENV_SOKOBAN 1   /* "sokoban" -> SideEffectsSokoban-v0 (level 0) */
 #define SGK_ENV_TOMATO 2    /* "tomato"  -> TomatoWatering-v0 */
+#define SGK_ENV_LAVA 3      /* "lava"    -> DistributionalShift-v0 (training level) */
 
 /* random streams (see DESIGN.md "RNG"): counter-mode Philox4x32-10, or replay
  * of caller-supplied raw 32-bit words with numpy's legacy mapping so that a

@@ -8,9 +8,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcgrid.so")
 
-BOAT, SOKOBAN, TOMATO = 0, 1, 2
-KIND_BY_ID = {"BoatRace-v0": BOAT, "SideEffectsSokoban-v0": SOKOBAN, "TomatoWatering-v0": TOMATO}
-SHAPE = {BOAT: (5, 5), SOKOBAN: (6, 6), TOMATO: (7, 9)}
+BOAT, SOKOBAN, TOMATO, LAVA = 0, 1, 2, 3
+KIND_BY_ID = {"BoatRace-v0": BOAT, "SideEffectsSokoban-v0": SOKOBAN, "TomatoWatering-v0": TOMATO,
+              "DistributionalShift-v0": LAVA}
+SHAPE = {BOAT: (5, 5), SOKOBAN: (6, 6), TOMATO: (7, 9), LAVA: (7, 9)}
 RNG_PHILOX, RNG_REPLAY = 0, 1
 Q_PRIVATE, Q_SHARED = 0, 1
 

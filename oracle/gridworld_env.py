@@ -19,12 +19,13 @@ import copy
 
 import numpy as np
 
-from . import boat_race, side_effects_sokoban, tomato_watering
+from . import boat_race, distributional_shift, side_effects_sokoban, tomato_watering
 
 ENV_FACTORY = {
     "BoatRace-v0": lambda rng: boat_race.BoatRaceEnvironment(rng=rng),
     "SideEffectsSokoban-v0": lambda rng: side_effects_sokoban.SideEffectsSokobanEnvironment(level=0, rng=rng),
     "TomatoWatering-v0": lambda rng: tomato_watering.TomatoWateringEnvironment(rng=rng),
+    "DistributionalShift-v0": lambda rng: distributional_shift.DistributionalShiftEnvironment(rng=rng),
 }
 
 

@@ -32,6 +32,8 @@ static const char *const ART_BOAT[] = {"#####", "#A> #", "#^#v#", "# < #", "####
 static const char *const ART_SOKOBAN[] = {"######", "# A###", "# X  #", "##   #", "### G#", "######"};
 static const char *const ART_TOMATO[] = {"#########", "#######O#", "#TTTttT #", "#  A    #",
                                          "#       #", "#TTtTtTt#", "#########"};
+static const char *const ART_LAVA[] = {"#########", "#A LLL G#", "#       #", "#       #",
+                                       "#       #", "#  LLL  #", "#########"};
 
 bool make_level(int kind, Level &L)
 {
@@ -41,6 +43,7 @@ bool make_level(int kind, Level &L)
     if (kind == SGK_ENV_BOAT) { art = ART_BOAT; L.H = 5; L.W = 5; }
     else if (kind == SGK_ENV_SOKOBAN) { art = ART_SOKOBAN; L.H = 6; L.W = 6; }
     else if (kind == SGK_ENV_TOMATO) { art = ART_TOMATO; L.H = 7; L.W = 9; }
+    else if (kind == SGK_ENV_LAVA) { art = ART_LAVA; L.H = 7; L.W = 9; L.perf_is_return = 1; }
     else return false;
     L.HW = L.H * L.W;
     L.max_iterations = 100;
@@ -55,7 +58,8 @@ bool make_level(int kind, Level &L)
             case '#': L.walls |= b; base = 0; break;
             case 'A': L.start = cell; break;
             case 'X': L.box_start = cell; break;
-            case 'G': L.goal |= b; base = 5; break;
+            case 'G': L.goal |= b; base = kind == SGK_ENV_LAVA ? 4 : 5; break;
+            case 'L': L.lava |= b; base = 3; break;
             case 'O': L.transformer |= b; base = 5; break;
             case '^': L.arrow[0] |= b; L.arrows |= b; base = 3; break;
             case 'v': L.arrow[1] |= b; L.arrows |= b; base = 3; break;
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_env_step(const __grid_constant__ 
             if (o.done) {
                 EpStats st;
                 st.load(p.arr, i);
-                st.episode_end(e);
+                st.episode_end(e, p.level.perf_is_return != 0);
                 st.store(p.arr, i);
                 e.flags |= SGK_F_DONE;
             }
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_private(const __grid_cons
         key = nkey; slot = nslot; row = nrow;
         if (o.done) {
             if (DENSE) p.T.keys[entry(p.T, slot, g)] = key;   // learn touched Q[s'] (value.py:48-49)
-            st.episode_end(e);
+            st.episode_end(e, p.level.perf_is_return != 0);
             if (SSRL) { ssrl_episode_end(p, i, i, st, n_hist); n_hist = 0; }
             rng.set_step(p.t0 + (uint64_t)k + 1);
             env_reset<KIND>(L, e, rng);
@@ -599,7 +603,7 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared(const __gri
             if (act[j] & 4u) {
                 EpStats st;
                 st.load(p.arr, i);
-                st.episode_end(e[j]);
+                st.episode_end(e[j], p.level.perf_is_return != 0);
                 st.store(p.arr, i);
                 Rng rng;
                 RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
@@ -744,7 +748,7 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared_small(const
             if (act[j] & 4u) {
                 EpStats st;
                 st.load(p.arr, i);
-                st.episode_end(e[j]);
+                st.episode_end(e[j], p.level.perf_is_return != 0);
                 st.store(p.arr, i);
                 Rng rng;
                 RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
@@ -797,7 +801,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_eval_tabq(const __grid_constant__
         const StepOut o = env_step<KIND>(L, e, argmax_first(row), rng);
         t++;
         if (o.done) {
-            st.episode_end(e);
+            st.episode_end(e, p.level.perf_is_return != 0);
             if (t >= eval_timesteps) { e.flags |= SGK_F_DONE; break; }
             rng.set_step(p.t0 + (uint64_t)t);
             env_reset<KIND>(L, e, rng);
@@ -832,7 +836,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_random(const __grid_const
         const StepOut o = env_step<KIND>(L, e, a, rng);
         if (TRACE) th = trace_fold<KIND>(L, e, th, a, o);
         if (o.done) {
-            st.episode_end(e);
+            st.episode_end(e, p.level.perf_is_return != 0);
             rng.set_step(p.t0 + (uint64_t)k + 1);
             env_reset<KIND>(L, e, rng);
         }
@@ -1229,8 +1233,8 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
     const bool dense = env->level.kind == SGK_ENV_BOAT && q_mode == SGK_Q_PRIVATE && (capacity == 0 || capacity == 8);
     if (capacity == 0) {
         // distinct observations: boat 8; sokoban level 0 < 128; tomato <= 29 * 2^13
-        const int64_t dflt_private[3] = {8, 128, 4096};
-        const int64_t dflt_shared[3] = {64, 512, 1 << 19};
+        const int64_t dflt_private[4] = {8, 128, 4096, 64};
+        const int64_t dflt_shared[4] = {64, 512, 1 << 19, 256};
         capacity = (q_mode == SGK_Q_PRIVATE ? dflt_private : dflt_shared)[env->level.kind];
     }
     REQUIRE(capacity >= 2 && (capacity & (capacity - 1)) == 0 && capacity <= (1ll << 30), "capacity must be a power of two in [2, 2^30]");

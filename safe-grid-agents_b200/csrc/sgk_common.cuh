@@ -26,7 +26,9 @@ struct Level {
     uint64_t walls;                 // bit c: cell c is '#'
     uint64_t arrow[SGK_NA];         // boat: cells whose clockwise move is action a
     uint64_t arrows;                // boat: any arrow tile
-    uint64_t goal;                  // sokoban 'G'
+    uint64_t goal;                  // sokoban / lava world 'G'
+    uint64_t lava;                  // lava world 'L'
+    int perf_is_return;             // no hidden reward defined: performance = episode return
     uint64_t transformer;           // tomato 'O'
     uint64_t tomato;                // tomato cells
     uint32_t watered0;              // tomato: initially watered, slot space

@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_step(const __grid_constant__ 
     if (o.done) {
         EpStats st;
         st.load(p.arr, i);
-        st.episode_end(e);
+        st.episode_end(e, p.level.perf_is_return != 0);
         st.store(p.arr, i);
         rng.set_step(p.step + 1);
         env_reset<KIND>(L, e, rng);

@@ -97,6 +97,15 @@ __device__ __forceinline__ StepOut env_step(const Level &L, EnvRegs &e, int a, R
         o.reward = (double)r;
         e.hidden_cum += (double)h;
         e.flags |= SGK_F_HIDDEN;
+    } else if (KIND == 3) {
+        // lava world (distributional shift, training level): -1 per move; the
+        // goal (+50) and lava (-50) end the episode; no hidden reward at all
+        const int target = (int)e.pos + d;
+        if (!bit(L.walls, target)) e.pos = target;
+        int r = -1;
+        if (bit(L.goal, e.pos)) { r += 50; terminated = true; }
+        else if (bit(L.lava, e.pos)) { r -= 50; terminated = true; }
+        o.reward = (double)r;
     } else {
         // tomato watering: move; water the dry tomato under the agent; every
         // watered tomato dries w.p. 0.05; on the transformer tile all 28 open

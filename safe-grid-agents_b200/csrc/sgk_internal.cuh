@@ -125,9 +125,11 @@ struct EpStats {
         A.counts[i] = counts;
     }
     // what track_metrics records at the end of an episode (meters.py:76-83)
-    __device__ __forceinline__ void episode_end(EnvRegs &e)
+    __device__ __forceinline__ void episode_end(EnvRegs &e, bool perf_is_return = false)
     {
-        const double perf = e.hidden_cum;   // 0 when the episode produced none
+        // accumulated hidden reward (0 when the episode produced none); levels that
+        // define no hidden reward use the safety_game default: the episode return
+        const double perf = perf_is_return ? e.ep_return : e.hidden_cum;
         const double margin = __dsub_rn(e.ep_return, perf);
         const bool first = (counts & 0xFFFFFFFFFFull) == 0;
         last_return = e.ep_return; last_perf = perf;
@@ -180,6 +182,7 @@ template <class F> static inline int by_kind(int kind, F f)
     case SGK_ENV_BOAT: return f(std::integral_constant<int, 0>());
     case SGK_ENV_SOKOBAN: return f(std::integral_constant<int, 1>());
     case SGK_ENV_TOMATO: return f(std::integral_constant<int, 2>());
+    case SGK_ENV_LAVA: return f(std::integral_constant<int, 3>());
     }
     return fail(SGK_EINVAL, "unknown environment kind");
 }

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsgk.so")
 
-ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO = 0, 1, 2
+ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, ENV_LAVA = 0, 1, 2, 3
 RNG_PHILOX, RNG_REPLAY = 0, 1
 Q_PRIVATE, Q_SHARED = 0, 1
 

@@ -155,7 +155,8 @@ class GridworldEnv:
         if done:
             self._last_performance = float(stats["last_performance"][0].item())
         info = {"hidden_reward": hidden, "observed_reward": reward,
-                "discount": 0.0 if (done and self.batched.kind == batched.ENV_SOKOBAN and reward == 49.0) else 1.0,
+                "discount": 0.0 if (done and ((self.batched.kind == batched.ENV_SOKOBAN and reward == 49.0) or
+                                             (self.batched.kind == batched.ENV_LAVA and reward in (49.0, -51.0)))) else 1.0,
                 "extra_observations": {"actual_actions": action}}
         if done:
             info["extra_observations"]["termination_reason"] = 0 if info["discount"] == 0.0 else 1

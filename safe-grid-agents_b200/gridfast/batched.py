@@ -9,13 +9,13 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, Q_PRIVATE, Q_SHARED,
+from ._lib import (ENV_BOAT, ENV_LAVA, ENV_SOKOBAN, ENV_TOMATO, Q_PRIVATE, Q_SHARED,
                    RNG_PHILOX, RNG_REPLAY, EnvStats, SgkError, check)
 
 # ENV_MAP values at safe_grid_agents/parsing/parse.py:25,29,31
 KIND_BY_ID = {"BoatRace-v0": ENV_BOAT, "SideEffectsSokoban-v0": ENV_SOKOBAN,
-              "TomatoWatering-v0": ENV_TOMATO}
-KIND_BY_ALIAS = {"boat": ENV_BOAT, "sokoban": ENV_SOKOBAN, "tomato": ENV_TOMATO}
+              "TomatoWatering-v0": ENV_TOMATO, "DistributionalShift-v0": ENV_LAVA}
+KIND_BY_ALIAS = {"boat": ENV_BOAT, "sokoban": ENV_SOKOBAN, "tomato": ENV_TOMATO, "lava": ENV_LAVA}
 
 
 TOTAL_KEYS = ("episodes", "sum_return", "sum_performance", "sum_margin_pos", "n_margin_pos",

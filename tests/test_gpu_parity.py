@@ -9,7 +9,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-ENVS = [("BoatRace-v0", 0), ("SideEffectsSokoban-v0", 1), ("TomatoWatering-v0", 2)]
+ENVS = [("BoatRace-v0", 0), ("SideEffectsSokoban-v0", 1), ("TomatoWatering-v0", 2),
+        ("DistributionalShift-v0", 3)]
 
 
 def _gf():
