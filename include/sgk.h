@@ -300,6 +300,14 @@ int sgk_dqn_set_tensor_cores(sgk_dqn *d, int enabled);
  * random-policy warm-up that only fills the ring (common/warmup.py:8-23). */
 int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64_t t0, int learn, void *stream);
 
+/* get_discounted_returns (common/agents/policy_base.py:179-186) for a block of
+ * n_steps lock-steps collected from `env`: reward / done are device
+ * [n_steps][n_envs], frame0 [n_envs] the in-episode index of row 0; returns
+ * float32 [n_steps][n_envs].  Used by the batched rollout collector that feeds
+ * policy-gradient agents (gather_rollout, policy_base.py:133-177). */
+int sgk_discounted_returns(const sgk_env *env, const double *reward, const uint8_t *done, const int32_t *frame0,
+                           int64_t n_steps, double discount, float *returns_out, void *stream);
+
 /* Raw environment state words, device [n_envs] (checkpoint / e2e path). */
 int sgk_env_get_core(const sgk_env *env, uint64_t *core_out, void *stream);
 int sgk_env_set_core(sgk_env *env, const uint64_t *core_in, void *stream);

@@ -997,6 +997,33 @@ __global__ void k_delta_apply(const TableView T, const uint64_t *keys_in, const 
     }
 }
 
+// PPO-style returns over a collected [T][N] trajectory block
+// (get_discounted_returns, common/agents/policy_base.py:179-186): within an
+// episode returns[t] = sum_{k >= t} discount^k * reward_k with k counted from
+// the episode's first step (the reference does NOT renormalise by discount^t).
+// One thread per environment walks its column backwards; `frame0` is the
+// in-episode index of row 0.  Episodes cut by the end of the block are summed
+// up to the cut.
+__global__ void k_discounted_returns(const double *reward, const uint8_t *done, const int32_t *frame0, int64_t T, int64_t n,
+                                     double discount, float *returns)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // forward: the in-episode index of every row, parked in the output buffer
+    int k = frame0[i];
+    for (int64_t t = 0; t < T; t++) {
+        returns[t * n + i] = (float)k;
+        k = done[t * n + i] ? 0 : k + 1;
+    }
+    // backward: suffix sums that restart at every episode end
+    double acc = 0.0;
+    for (int64_t t = T - 1; t >= 0; t--) {
+        if (done[t * n + i]) acc = 0.0;
+        acc += pow(discount, (double)returns[t * n + i]) * reward[t * n + i];
+        returns[t * n + i] = (float)acc;
+    }
+}
+
 // ===================================================================== C ABI: environments
 static EnvKernelArgs env_args(const sgk_env *env, uint64_t step)
 {
@@ -1195,6 +1222,15 @@ extern "C" int sgk_env_totals_host(const sgk_env *env, double totals[SGK_N_TOTAL
     CU(cudaMemcpyAsync(totals, env->totals, SGK_N_TOTALS * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return SGK_OK;
+}
+
+extern "C" int sgk_discounted_returns(const sgk_env *env, const double *reward, const uint8_t *done, const int32_t *frame0,
+                                      int64_t n_steps, double discount, float *returns_out, void *stream)
+{
+    REQUIRE(env != nullptr && reward && done && frame0 && returns_out && n_steps > 0, "bad argument");
+    DeviceGuard g(env->device);
+    k_discounted_returns<<<grid_for(env->n, 128), 128, 0, (cudaStream_t)stream>>>(reward, done, frame0, n_steps, env->n, discount, returns_out);
+    return launch_check("k_discounted_returns");
 }
 
 extern "C" int sgk_env_get_core(const sgk_env *env, uint64_t *core_out, void *stream)

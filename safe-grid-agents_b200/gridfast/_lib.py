@@ -82,6 +82,7 @@ SYMBOLS = [
     ("sgk_dqn_last_scalars", _i32, [_vp, _vp, _vp]),
     ("sgk_dqn_set_tensor_cores", _i32, [_vp, _i32]),
     ("sgk_rollout_dqn", _i32, [_vp, _vp, _i64, _u64, _i32, _vp]),
+    ("sgk_discounted_returns", _i32, [_vp, _vp, _vp, _vp, _i64, _dbl, _vp, _vp]),
     ("sgk_env_get_core", _i32, [_vp, _vp, _vp]),
     ("sgk_env_set_core", _i32, [_vp, _vp, _vp]),
     ("sgk_env_set_trace", _i32, [_vp, _i32]),

@@ -177,3 +177,51 @@ def test_deepq_adapter_runs_the_reference_loop_shape():
     assert isinstance(greedy, __import__("torch").Tensor) and greedy.numel() == 1
     assert len(agent.replay) == args.replay_capacity
     assert np.mean(returns[-10:]) > np.mean(warm_returns[1:]) - 5
+
+
+def test_batched_rollout_collection_matches_reference_returns():
+    """gridfast.rollouts.collect against gather_rollout semantics
+    (policy_base.py:133-186): same trajectories as stepping the oracle with the
+    same actions, and returns[t] = sum_{k>=t} discount^k r_k per episode with
+    k counted from the episode start (the reference's formula)."""
+    import torch
+    import gridfast
+    from gridfast import rollouts
+    from oracle import cgrid
+
+    n, T, discount = 300, 230, 0.97
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", n, seed=4)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    table = torch.randint(0, 4, (T, n), dtype=torch.uint8, device="cuda", generator=gen)
+    step = {"t": 0}
+
+    def policy(boards):
+        a = table[step["t"]]
+        step["t"] += 1
+        return a
+
+    out = rollouts.collect(env, policy, T, discount=discount)
+    sim = cgrid.Sim(cgrid.SOKOBAN, n, seed=4)
+    acts = table.cpu().numpy()
+    rewards, dones = [], []
+    for t in range(T):
+        boards_before = sim.boards()
+        assert np.array_equal(out["states"][t].cpu().numpy(), boards_before)
+        _, r, _, d = sim.step(acts[t])
+        rewards.append(r)
+        dones.append(d)
+    rewards, dones = np.array(rewards), np.array(dones)
+    assert np.array_equal(out["rewards"].cpu().numpy(), rewards)
+    assert np.array_equal(out["dones"].cpu().numpy(), dones)
+    # the reference's get_discounted_returns, episode by episode
+    want = np.zeros((T, n), np.float64)
+    for i in range(n):
+        start = 0
+        for t in range(T):
+            if dones[t, i] or t == T - 1:
+                seg = rewards[start:t + 1, i]
+                disc = np.array([discount ** k * r for k, r in enumerate(seg)])
+                want[start:t + 1, i] = [disc[k:].sum() for k in range(len(seg))]
+                start = t + 1
+    got = out["returns"].cpu().numpy()
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-4)
