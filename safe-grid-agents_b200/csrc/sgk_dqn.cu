@@ -244,7 +244,7 @@ __global__ void k_u8_to_f32(const uint8_t *in, float *out, int64_t n)
 __global__ void k_replay_sample(uint64_t seed, uint64_t step, int64_t fill, int64_t batch, int hw,
                                 const uint8_t *r_s, const uint8_t *r_s2, const uint8_t *r_a, const float *r_r,
                                 const uint8_t *r_term, float *x, float *x2, uint8_t *xb, uint8_t *xb2, uint8_t *b_a, float *b_r,
-                                uint8_t *b_term, int64_t *b_idx)
+                                uint8_t *b_term, int64_t *b_idx, int copy_boards)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
@@ -254,7 +254,7 @@ __global__ void k_replay_sample(uint64_t seed, uint64_t step, int64_t fill, int6
     const uint64_t u = ((uint64_t)w[0] << 32) | w[1];
     const int64_t idx = (int64_t)(u % (uint64_t)fill);
     b_idx[b] = idx;
-    for (int c = 0; c < hw; c++) {
+    for (int c = 0; copy_boards && c < hw; c++) {
         const uint8_t v = r_s[idx * hw + c], v2 = r_s2[idx * hw + c];
         x[b * hw + c] = (float)v; x2[b * hw + c] = (float)v2;
         xb[b * hw + c] = v; xb2[b * hw + c] = v2;
@@ -262,6 +262,23 @@ __global__ void k_replay_sample(uint64_t seed, uint64_t step, int64_t fill, int6
     b_a[b] = r_a[idx];
     b_r[b] = r_r[idx];
     b_term[b] = r_term[idx];
+}
+
+// second stage of the sample for boards whose size is a multiple of 4 bytes:
+// one thread per (sample, 4-byte word) -- coalesced word copies instead of a
+// per-thread byte loop.  b_idx holds the ring index of every sample.
+__global__ void k_replay_gather_words(const int64_t *b_idx, int64_t batch, int words, const uint32_t *r_s, const uint32_t *r_s2,
+                                      uint32_t *xb, uint32_t *xb2, float4 *x, float4 *x2)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= batch * words) return;
+    const int64_t b = e / words;
+    const int w = (int)(e - b * words);
+    const int64_t idx = b_idx[b];
+    const uint32_t v = r_s[idx * words + w], v2 = r_s2[idx * words + w];
+    xb[e] = v; xb2[e] = v2;
+    x[e] = make_float4((float)(v & 0xFF), (float)((v >> 8) & 0xFF), (float)((v >> 16) & 0xFF), (float)(v >> 24));
+    x2[e] = make_float4((float)(v2 & 0xFF), (float)((v2 >> 8) & 0xFF), (float)((v2 >> 16) & 0xFF), (float)(v2 >> 24));
 }
 
 __global__ void k_replay_add(int64_t cap, int64_t pos0, int64_t n, int hw, const uint8_t *s, const uint8_t *a,
@@ -594,7 +611,10 @@ static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
     tc::BwdParams bp;
     bp.w2 = P0 + d->w_off[1]; bp.w3 = P0 + d->w_off[2]; bp.n_hidden = H; bp.n_out = A;
     bp.dq = dq; bp.h1 = d->act[0]; bp.h2 = d->act[1]; bp.dh1 = dh1; bp.dh2 = dh2; bp.rows = B;
-    tc::k_mlp_backward_data_tc<<<grid, tc::TILE_M, tc::SmemBwd::TOTAL, st>>>(bp);
+    // 107 KB of shared memory and 256 TMEM columns per CTA: two CTAs fit on an SM,
+    // so one CTA's epilogue overlaps the other's MMAs
+    const unsigned grid_bwd = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)d->sm_count);
+    tc::k_mlp_backward_data_tc<<<grid_bwd, tc::TILE_M, tc::SmemBwd::TOTAL, st>>>(bp);
     int rc = launch_check("k_mlp_backward_data_tc");
     if (rc != SGK_OK) return rc;
     const int64_t need = (int64_t)d->sm_count * tc::TILE_M * tc::N_HID;
@@ -849,7 +869,14 @@ extern "C" int sgk_dqn_learn(sgk_dqn *d, uint64_t step, float *loss_out, void *s
     int rc = ensure_rows(d, B);
     if (rc != SGK_OK) return rc;
     k_replay_sample<<<grid_for(B, 128), 128, 0, st>>>(d->seed, step, fill, B, d->hw, d->r_s, d->r_s2, d->r_a, d->r_r, d->r_term,
-                                                      d->x, d->x2, d->xb, d->xb2, d->b_a, d->b_r, d->b_term, d->b_idx);
+                                                      d->x, d->x2, d->xb, d->xb2, d->b_a, d->b_r, d->b_term, d->b_idx, (d->hw & 3) != 0);
+    if ((d->hw & 3) == 0) {
+        const int words = d->hw / 4;
+        k_replay_gather_words<<<grid_for(B * words, 256), 256, 0, st>>>(
+            d->b_idx, B, words, reinterpret_cast<const uint32_t *>(d->r_s), reinterpret_cast<const uint32_t *>(d->r_s2),
+            reinterpret_cast<uint32_t *>(d->xb), reinterpret_cast<uint32_t *>(d->xb2), reinterpret_cast<float4 *>(d->x),
+            reinterpret_cast<float4 *>(d->x2));
+    }
     if ((rc = launch_check("k_replay_sample"))) return rc;
     return learn_staged(d, B, loss_out, st);
 }
