@@ -418,8 +418,10 @@ __device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i
 // (boat race: rank of the agent's cell among open cells) -- no probing, no key
 // compare; the key is (re)written on touch so the key set still equals the
 // reference dict's.  Otherwise: hashed open addressing.
+// 128-thread blocks measured best (64: -8 % boat, -27 % sokoban; see profiles/r01_suite.md)
+#define SGK_BLOCK_ROLLOUT 128
 template <int KIND, class Rng, bool TRACE, bool SSRL, bool DENSE>
-__global__ void __launch_bounds__(SGK_BLOCK) k_rollout_private(const __grid_constant__ RolloutArgs p)
+__global__ void __launch_bounds__(SGK_BLOCK_ROLLOUT) k_rollout_private(const __grid_constant__ RolloutArgs p)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
@@ -1568,8 +1570,9 @@ extern "C" int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint
         auto go = [&](auto R, auto TR, auto SS) {
             using Rng = typename decltype(R)::type;
             constexpr bool TRACE_ = decltype(TR)::value, SSRL_ = decltype(SS)::value;
-            if (dense) k_rollout_private<KIND, Rng, TRACE_, SSRL_, CAN_DENSE><<<grid, SGK_BLOCK, 0, st>>>(a);
-            else k_rollout_private<KIND, Rng, TRACE_, SSRL_, false><<<grid, SGK_BLOCK, 0, st>>>(a);
+            const unsigned rgrid = grid_for(env->n, SGK_BLOCK_ROLLOUT);
+            if (dense) k_rollout_private<KIND, Rng, TRACE_, SSRL_, CAN_DENSE><<<rgrid, SGK_BLOCK_ROLLOUT, 0, st>>>(a);
+            else k_rollout_private<KIND, Rng, TRACE_, SSRL_, false><<<rgrid, SGK_BLOCK_ROLLOUT, 0, st>>>(a);
         };
         if (ssrl) {
             if (replay) go(type_tag<ReplayStream>(), std::true_type(), std::true_type());
