@@ -92,9 +92,13 @@ class ClockSampler:
             pass
 
     def _run(self):
+        # NVML queries take a driver-wide lock: with one sampler per rank, poll
+        # gently (and not at all when SGK_BENCH_NO_CLOCKS is set)
+        if os.environ.get("SGK_BENCH_NO_CLOCKS"):
+            return
         while not self._stop.is_set():
             self._once()
-            self._stop.wait(0.02)
+            self._stop.wait(0.02 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 0.05)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -220,10 +224,16 @@ def run_ours(args, out):
         agent.rollout(T)                      # 2 launches: thresholds + fused rollout
         env.totals_device(buf)                # 2 launches: partial + final reduction
 
+    def sync_stats(block):                   # sums, and maxima for the max_* columns
+        if world > 1:
+            maxima = block[:, MAX_COLS].clone()
+            dist.all_reduce(block)
+            dist.all_reduce(maxima, op=dist.ReduceOp.MAX)
+            block[:, MAX_COLS] = maxima
+
     for _ in range(W):
         one_step(totals)
-    if world > 1:
-        dist.all_reduce(totals)
+    sync_stats(torch.zeros(K, 9, dtype=torch.float64, device=dev))   # same collectives as the timed ones
     agent.check()
     barrier()
 
@@ -243,15 +253,12 @@ def run_ours(args, out):
             env.totals_device(stats[k])
             ends[k].record()
         starts[K].record()                    # sync interval ends: one all-reduce of all K rows
-        if world > 1:                         # sums, and maxima for the max_* columns
-            maxima = stats[:, MAX_COLS].clone()
-            dist.all_reduce(stats)
-            dist.all_reduce(maxima, op=dist.ReduceOp.MAX)
-            stats[:, MAX_COLS] = maxima
+        sync_stats(stats)
         ends[K].record()
         barrier()
     agent.check()
     step_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    drain_ms = starts[K].elapsed_time(ends[K])
     kernel_ms = sum(s.elapsed_time(e) for s, e in zip(kstart, kend))
     t = torch.tensor([step_ms, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -300,7 +307,7 @@ def run_ours(args, out):
                          "algorithmic_bytes_per_env_step": B_ALG, "peak_source": peak_src,
                          "kernel_ms_per_launch": kernel_ms / K},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": 4 * K,
+            "gpu_launches": 4 * K, "stats_allreduce_ms": drain_ms,
             "clocks": clocks.summary(),
         }
         if world == 1:

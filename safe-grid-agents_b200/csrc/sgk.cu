@@ -679,9 +679,10 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared_small(const
             if (k == 0ull) break;
             s = (s + 1) & (cap - 1);
         }
-        s = find_shared(p.T, key, &status);
-        keys_s[s] = key;          // benign race: every writer stores the same value
-        return s;
+        // not in the snapshot (first seen this lock-step, possibly by another
+        // block): the global table decides; the snapshot learns the key at the
+        // refresh after the barrier
+        return find_shared(p.T, key, &status);
     };
     __syncthreads();
     for (int64_t k = 0; k < p.n_steps; k++) {

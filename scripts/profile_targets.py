@@ -30,6 +30,12 @@ elif what == "mlp":
     boards = torch.randint(0, 6, (1 << 20, env.hw), dtype=torch.uint8, device="cuda")
     for _ in range(4):
         agent.q_values(boards)
+elif what == "learn":
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", 4096, seed=0)
+    agent = gridfast.BatchedDeepQ(env, replay_capacity=100 * 4096, batch_size=262144)
+    agent.set_tensor_cores(True)
+    agent.warmup(100)
+    agent.rollout(2)
 elif what == "shared":
     env = gridfast.BatchedEnv("BoatRace-v0", 65536, seed=0)
     agent = gridfast.BatchedTabularQ(env, gridfast.Q_SHARED)
