@@ -617,7 +617,9 @@ static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
     tc::k_mlp_backward_data_tc<<<grid_bwd, tc::TILE_M, tc::SmemBwd::TOTAL, st>>>(bp);
     int rc = launch_check("k_mlp_backward_data_tc");
     if (rc != SGK_OK) return rc;
-    const int64_t need = (int64_t)d->sm_count * tc::TILE_M * tc::N_HID;
+    const int64_t wg_tiles = (B + tc::WG_TILE - 1) / tc::WG_TILE;
+    const unsigned wg_grid = (unsigned)std::min<int64_t>(wg_tiles, 3 * (int64_t)d->sm_count);
+    const int64_t need = (int64_t)wg_grid * tc::TILE_M * tc::N_HID;
     if (d->partials_cap < need) {
         if (d->partials) cudaFree(d->partials);
         d->partials = nullptr; d->partials_cap = 0;
@@ -628,9 +630,9 @@ static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
         tc::WgradParams wp;
         wp.P = P; wp.ldp = ldp; wp.mdim = mdim; wp.Q = Q; wp.ldq = ldq; wp.ndim = ndim;
         wp.npad = (ndim + 1 + 15) / 16 * 16; wp.add_ones = 1; wp.rows = B; wp.partial = d->partials;
-        tc::k_wgrad_tc<<<grid, tc::TILE_M, tc::SmemWg::TOTAL, st>>>(wp);
+        tc::k_wgrad_tc<<<wg_grid, tc::TILE_M, tc::SmemWg::TOTAL, st>>>(wp);
         const int total = mdim * (ndim + 1);
-        tc::k_wgrad_finish<<<(total + 255) / 256, 256, 0, st>>>(d->partials, (int)grid, wp.npad, mdim, ndim,
+        tc::k_wgrad_finish<<<(total + tc::WGF_ELEMS - 1) / tc::WGF_ELEMS, tc::WGF_ELEMS * tc::WGF_LANES, 0, st>>>(d->partials, (int)wg_grid, wp.npad, mdim, ndim,
                                                                 d->grads + d->w_off[layer], d->grads + d->b_off[layer]);
         return launch_check("k_wgrad_tc");
     };

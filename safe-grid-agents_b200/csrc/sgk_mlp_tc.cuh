@@ -502,9 +502,10 @@ __global__ void __launch_bounds__(TILE_M, 1) k_mlp_backward_data_tc(const BwdPar
 //     to Q, so D[m][ndim] = sum_b P[b][m] is the bias gradient)
 // On the tensor core this is a GEMM whose K dimension is the sample index, so
 // both operands must have samples contiguous in 16-byte chunks.  Each thread
-// owns one sample of the 128-sample tile and scatters its P and Q rows
-// TRANSPOSED into shared memory (K-major operands [m][b] and [n][b]); 16
-// tcgen05.mma (K = 8 samples each) accumulate the tile into TMEM, which keeps
+// owns one row of a 64-sample tile (half the threads the P rows, half the Q
+// rows) and scatters it TRANSPOSED into shared memory (K-major operands
+// [m][b] and [n][b]); 8 tcgen05.mma (K = 8 samples each) accumulate the tile
+// into TMEM, which keeps
 // accumulating across all tiles of the CTA.  Each CTA finally writes its
 // [128][npad] partial; k_wgrad_finish folds the partials in CTA order
 // (deterministic).
@@ -516,10 +517,11 @@ struct WgradParams {
     float *partial;                    // [gridDim.x][128][npad]
 };
 
+constexpr int WG_TILE = 64;    // samples per tile: 60 KB of operands => three CTAs per SM hide the row-load latency
 struct SmemWg {
-    static constexpr int AT = 0;                       // [32][128][16 B]
-    static constexpr int BT = AT + 32 * Smem::CHUNK_A; // [32][npad][16 B], npad <= 112
-    static constexpr int BAR = BT + 32 * N_HID * 16;
+    static constexpr int AT = 0;                                  // [16][128][16 B]
+    static constexpr int BT = AT + (WG_TILE / 4) * Smem::CHUNK_A; // [16][npad][16 B], npad <= 112
+    static constexpr int BAR = BT + (WG_TILE / 4) * N_HID * 16;
     static constexpr int TOTAL = BAR + 16;
 };
 
@@ -561,26 +563,30 @@ __global__ void __launch_bounds__(TILE_M, 1) k_wgrad_tc(const WgradParams p)
     const uint32_t idesc = make_idesc(TILE_M, p.npad);
     uint32_t phase = 0;
     bool first = true;
-    const int cb = threadIdx.x >> 2, l4 = threadIdx.x & 3;      // this sample's chunk and position in it
+    // threads 0..63 transpose the P rows of the tile's 64 samples, threads 64..127 the Q rows
+    const int sample = threadIdx.x & (WG_TILE - 1), side = threadIdx.x >> 6;
+    const int cb = sample >> 2, l4 = sample & 3;                // this sample's K chunk and position in it
     uint8_t *a_dst = smem + SmemWg::AT + (size_t)cb * Smem::CHUNK_A + l4 * 4;
     uint8_t *b_dst = smem + SmemWg::BT + (size_t)cb * chunk_b + l4 * 4;
-    const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
+    const bool pvec = (p.ldp & 3) == 0, qvec = (p.ldq & 3) == 0;
+    const int64_t n_tiles = (p.rows + WG_TILE - 1) / WG_TILE;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row = tile * TILE_M + threadIdx.x;
+        const int64_t row = tile * WG_TILE + sample;
         const bool valid = row < p.rows;
-        const float *prow = p.P + row * p.ldp, *qrow = p.Q + row * p.ldq;
         // rows are read 8 x 16 bytes at a time (loads in flight together), then
         // scattered transposed: element (sample b, column m) -> operand row m, K slot b
-        const bool pvec = (p.ldp & 3) == 0, qvec = (p.ldq & 3) == 0;
-        scatter_row(a_dst, prow, p.mdim, pvec, valid);
-        scatter_row(b_dst, qrow, p.ndim, qvec, valid);
-        if (p.add_ones) *reinterpret_cast<float *>(b_dst + p.ndim * 16) = valid ? 1.f : 0.f;
+        if (side == 0) {
+            scatter_row(a_dst, p.P + row * p.ldp, p.mdim, pvec, valid);
+        } else {
+            scatter_row(b_dst, p.Q + row * p.ldq, p.ndim, qvec, valid);
+            if (p.add_ones) *reinterpret_cast<float *>(b_dst + p.ndim * 16) = valid ? 1.f : 0.f;
+        }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
         if (threadIdx.x == 0) {
-            for (int s = 0; s < TILE_M / 8; s++)
+            for (int s = 0; s < WG_TILE / 8; s++)
                 mma_tf32(tmem, make_desc(a_t + s * 2 * Smem::CHUNK_A, Smem::CHUNK_A, 128),
                          make_desc(b_t + s * 2 * chunk_b, chunk_b, 128), idesc, (!first || s > 0) ? 1u : 0u);
             mma_commit(mbar);
@@ -591,11 +597,17 @@ __global__ void __launch_bounds__(TILE_M, 1) k_wgrad_tc(const WgradParams p)
     }
     // this thread's accumulator row (m = threadIdx.x) -> partial
     float *out = p.partial + ((size_t)blockIdx.x * TILE_M + threadIdx.x) * p.npad;
-    for (int c8 = 0; c8 < p.npad / 8; c8++) {
+    // rows >= mdim are never read back.  tcgen05.ld is warp-collective, so a warp
+    // either loads as a whole or skips as a whole; only the store is per thread.
+    const int n_c8 = warp * 32 < p.mdim ? p.npad / 8 : 0;
+    const bool keep = (int)threadIdx.x < p.mdim;
+    for (int c8 = 0; c8 < n_c8; c8++) {
         float v[8];
         tmem_ld8(tmem_row + c8 * 8, v);
+        if (keep) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) out[c8 * 8 + i] = v[i];
+            for (int i = 0; i < 8; i++) out[c8 * 8 + i] = v[i];
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -603,23 +615,40 @@ __global__ void __launch_bounds__(TILE_M, 1) k_wgrad_tc(const WgradParams p)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
 }
 
-// dW[m][n] = sum_g partial[g][m][n], db[m] = sum_g partial[g][m][ndim]
-__global__ void k_wgrad_finish(const float *partial, int n_partials, int npad, int mdim, int ndim, float *dW, float *db)
+// dW[m][n] = sum_g partial[g][m][n], db[m] = sum_g partial[g][m][ndim].
+// A block folds 32 elements: 8 lanes of partials (g = lane, lane + 8, ...) per
+// element, then the 8 lane sums in lane order -- a fixed order, so the result
+// does not depend on scheduling.
+constexpr int WGF_ELEMS = 32, WGF_LANES = 8;
+__global__ void __launch_bounds__(WGF_ELEMS * WGF_LANES)
+k_wgrad_finish(const float *partial, int n_partials, int npad, int mdim, int ndim, float *dW, float *db)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float part[WGF_LANES][WGF_ELEMS];
+    const int e = threadIdx.x & (WGF_ELEMS - 1), lane = threadIdx.x / WGF_ELEMS;
+    const int idx = blockIdx.x * WGF_ELEMS + e;
     const int total = mdim * (ndim + 1);
-    if (idx >= total) return;
-    const int m = idx / (ndim + 1), n = idx - m * (ndim + 1);
+    const bool live = idx < total;
+    const int m = live ? idx / (ndim + 1) : 0, n = live ? idx - m * (ndim + 1) : 0;
+    const float *src = partial + (size_t)m * npad + n;
+    const size_t stride = (size_t)TILE_M * npad;
     float s0 = 0.f, s1 = 0.f;
-    int g = 0;
-    for (; g + 1 < n_partials; g += 2) {
-        s0 += partial[((size_t)g * TILE_M + m) * npad + n];
-        s1 += partial[((size_t)(g + 1) * TILE_M + m) * npad + n];
+    if (live) {
+        int g = lane;
+        for (; g + WGF_LANES < n_partials; g += 2 * WGF_LANES) {
+            s0 += src[g * stride];
+            s1 += src[(g + WGF_LANES) * stride];
+        }
+        if (g < n_partials) s0 += src[g * stride];
     }
-    if (g < n_partials) s0 += partial[((size_t)g * TILE_M + m) * npad + n];
-    const float s = s0 + s1;
-    if (n < ndim) dW[(size_t)m * ndim + n] = s;
-    else if (db) db[m] = s;
+    part[lane][e] = s0 + s1;
+    __syncthreads();
+    if (lane == 0 && live) {
+        float s = 0.f;
+#pragma unroll
+        for (int l = 0; l < WGF_LANES; l++) s += part[l][e];
+        if (n < ndim) dW[(size_t)m * ndim + n] = s;
+        else if (db) db[m] = s;
+    }
 }
 
 }  // namespace tc
