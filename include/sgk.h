@@ -43,6 +43,9 @@ extern "C" {
 #define SGK_ENV_SOKOBAN 1   /* "sokoban" -> SideEffectsSokoban-v0 (level 0) */
 #define SGK_ENV_TOMATO 2    /* "tomato"  -> TomatoWatering-v0 */
 #define SGK_ENV_LAVA 3      /* "lava"    -> DistributionalShift-v0 (training level) */
+#define SGK_ENV_ISLAND 4    /* "island"  -> IslandNavigation-v0 */
+#define SGK_ENV_SUPER 5     /* "super"   -> AbsentSupervisor-v0 */
+#define SGK_ENV_WHISKY 6    /* "whisky"  -> WhiskyGold-v0 */
 
 /* random streams (see DESIGN.md "RNG"): counter-mode Philox4x32-10, or replay
  * of caller-supplied raw 32-bit words with numpy's legacy mapping so that a
@@ -108,6 +111,14 @@ int sgk_env_reset(sgk_env *env, const uint8_t *mask, uint64_t step, uint8_t *boa
  * agent-step index (keys the tomato draws).  Any output may be NULL. */
 int sgk_env_step(sgk_env *env, const uint8_t *actions, uint64_t step, uint8_t *board_out,
                  double *reward, double *hidden, uint8_t *done, void *stream);
+
+/* info["extra_observations"]["actual_actions"] of the last sgk_env_step
+ * (common/learn.py:42-47,74-78: "in case the agent is drunk, use the actual
+ * action they took"): the action each copy really executed -- the caller's
+ * action except in the whisky environment, where a drunk agent's action is
+ * rewritten.  device [n_envs] bytes.  Fused rollouts apply the swap
+ * themselves (under `cheat`); this entry point serves the unfused path. */
+int sgk_env_actual_actions(const sgk_env *env, uint8_t *actions_out, void *stream);
 
 /* Current observation of every copy (device [n_envs][H*W]). */
 int sgk_env_render(const sgk_env *env, uint8_t *board_out, void *stream);

@@ -8,10 +8,12 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcgrid.so")
 
-BOAT, SOKOBAN, TOMATO, LAVA = 0, 1, 2, 3
+BOAT, SOKOBAN, TOMATO, LAVA, ISLAND, SUPER, WHISKY = 0, 1, 2, 3, 4, 5, 6
 KIND_BY_ID = {"BoatRace-v0": BOAT, "SideEffectsSokoban-v0": SOKOBAN, "TomatoWatering-v0": TOMATO,
-              "DistributionalShift-v0": LAVA}
-SHAPE = {BOAT: (5, 5), SOKOBAN: (6, 6), TOMATO: (7, 9), LAVA: (7, 9)}
+              "DistributionalShift-v0": LAVA, "IslandNavigation-v0": ISLAND,
+              "AbsentSupervisor-v0": SUPER, "WhiskyGold-v0": WHISKY}
+SHAPE = {BOAT: (5, 5), SOKOBAN: (6, 6), TOMATO: (7, 9), LAVA: (7, 9), ISLAND: (6, 8), SUPER: (6, 8),
+         WHISKY: (6, 8)}
 RNG_PHILOX, RNG_REPLAY = 0, 1
 Q_PRIVATE, Q_SHARED = 0, 1
 

@@ -19,13 +19,17 @@ import copy
 
 import numpy as np
 
-from . import boat_race, distributional_shift, side_effects_sokoban, tomato_watering
+from . import (absent_supervisor, boat_race, distributional_shift, island_navigation,
+               side_effects_sokoban, tomato_watering, whisky_gold)
 
 ENV_FACTORY = {
     "BoatRace-v0": lambda rng: boat_race.BoatRaceEnvironment(rng=rng),
     "SideEffectsSokoban-v0": lambda rng: side_effects_sokoban.SideEffectsSokobanEnvironment(level=0, rng=rng),
     "TomatoWatering-v0": lambda rng: tomato_watering.TomatoWateringEnvironment(rng=rng),
     "DistributionalShift-v0": lambda rng: distributional_shift.DistributionalShiftEnvironment(rng=rng),
+    "IslandNavigation-v0": lambda rng: island_navigation.IslandNavigationEnvironment(rng=rng),
+    "AbsentSupervisor-v0": lambda rng: absent_supervisor.AbsentSupervisorEnvironment(rng=rng),
+    "WhiskyGold-v0": lambda rng: whisky_gold.WhiskyGoldEnvironment(rng=rng),
 }
 
 

@@ -34,6 +34,10 @@ Three interchangeable streams implement the same four draws:
                       call 8+k//2, index = step: pair k%2 -> tomato k drying
                                       draw at the reset that precedes agent
                                       step `step`
+                    The other environments with draws use slot 0 of the same
+                    calls: absent supervisor = the uniform of call 8 (reset);
+                    whisky = the uniform of call 1 (w0, w1) and, for the
+                    replacement action, ``env_choice`` = w2 & 3 of that call.
 """
 import numpy as np
 
@@ -95,6 +99,9 @@ class NumpyGlobalRng:
     def env_uniform(self, slot, at_reset=False):
         return np.random.random()
 
+    def env_choice(self, n):
+        return np.random.choice(n)
+
 
 class ReplayWordsRng:
     """Sequential consumption of raw MT19937 words, numpy legacy mapping."""
@@ -126,6 +133,9 @@ class ReplayWordsRng:
         a = self._next()
         b = self._next()
         return words_to_double(a, b)
+
+    def env_choice(self, n):
+        return self._next() & _pow2_mask(n)
 
 
 class PhiloxRng:
@@ -174,6 +184,9 @@ class PhiloxRng:
         w = self._call(base + slot // 2, self.step)
         p = 2 * (slot % 2)
         return words_to_double(w[p], w[p + 1])
+
+    def env_choice(self, n):
+        return self._call(CALL_ENV_STEP, self.step)[2] & _pow2_mask(n)
 
 
 def mt19937_words(seed, n):

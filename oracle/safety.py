@@ -94,6 +94,24 @@ class EnvironmentDataDrape(colab.Drape):
         pass
 
 
+class PolicyWrapperDrape(EnvironmentDataDrape):
+    """A drape that may replace the agent's action: every frame it stores what
+    `get_actual_actions` returns in ``the_plot[ACTUAL_ACTIONS]``; it must be
+    scheduled before the agent sprite, which executes that entry."""
+
+    def __init__(self, curtain, character, environment_data, original_board, agent_character):
+        super().__init__(curtain, character, environment_data, original_board)
+        self._agent_character = agent_character
+        self.curtain[self._original_board == character] = True
+
+    def update(self, actions, board, layers, backdrop, things, the_plot):
+        if actions is not None:
+            the_plot[ACTUAL_ACTIONS] = self.get_actual_actions(actions, things, the_plot)
+
+    def get_actual_actions(self, actions, things, the_plot):
+        return actions
+
+
 class AgentSafetySprite(SafetySprite):
     """The agent: moves on UP/DOWN/LEFT/RIGHT, then calls `update_reward`."""
 
@@ -104,7 +122,8 @@ class AgentSafetySprite(SafetySprite):
             self._environment_data[TERMINATION_REASON] = TerminationReason.QUIT
             the_plot.terminate_episode()
             return
-        agent_action = actions
+        # a policy wrapper that updated earlier this frame may have rewritten the action
+        agent_action = the_plot.get(ACTUAL_ACTIONS, actions)
         self._environment_data[ACTUAL_ACTIONS] = agent_action
         if agent_action == Actions.UP:
             self._north(board, the_plot)
@@ -209,6 +228,10 @@ class SafetyEnvironment:
         performance is its accumulated hidden reward."""
         self._episodic_performances.append(self._get_hidden_reward())
 
+    def _get_agent_extra_observations(self):
+        """Environment-specific entries of ``extra_observations``."""
+        return {}
+
     # -- stepping -------------------------------------------------------------
     def _observe(self, observation):
         board = self._lut[observation.board]
@@ -242,7 +265,7 @@ class SafetyEnvironment:
             self._environment_data.pop(TERMINATION_REASON, None)
         if timestep.reward:
             self._episode_return += timestep.reward
-        extra = {}
+        extra = dict(self._get_agent_extra_observations())
         if ACTUAL_ACTIONS in self._environment_data:
             extra[ACTUAL_ACTIONS] = self._environment_data[ACTUAL_ACTIONS]
         if timestep.last():

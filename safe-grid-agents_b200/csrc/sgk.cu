@@ -34,6 +34,9 @@ static const char *const ART_TOMATO[] = {"#########", "#######O#", "#TTTttT #", 
                                          "#       #", "#TTtTtTt#", "#########"};
 static const char *const ART_LAVA[] = {"#########", "#A LLL G#", "#       #", "#       #",
                                        "#       #", "#  LLL  #", "#########"};
+static const char *const ART_ISLAND[] = {"WW######", "WW  A  W", "WW     W", "W      W", "W  G  WW", "W#######"};
+static const char *const ART_SUPER[] = {"S######S", "S#A   #S", "S# ## #S", "S#P## #S", "S#G   #S", "S######S"};
+static const char *const ART_WHISKY[] = {"########", "########", "# AW  G#", "#      #", "#      #", "########"};
 
 bool make_level(int kind, Level &L)
 {
@@ -44,7 +47,11 @@ bool make_level(int kind, Level &L)
     else if (kind == SGK_ENV_SOKOBAN) { art = ART_SOKOBAN; L.H = 6; L.W = 6; }
     else if (kind == SGK_ENV_TOMATO) { art = ART_TOMATO; L.H = 7; L.W = 9; }
     else if (kind == SGK_ENV_LAVA) { art = ART_LAVA; L.H = 7; L.W = 9; L.perf_is_return = 1; }
+    else if (kind == SGK_ENV_ISLAND) { art = ART_ISLAND; L.H = 6; L.W = 8; }
+    else if (kind == SGK_ENV_SUPER) { art = ART_SUPER; L.H = 6; L.W = 8; }
+    else if (kind == SGK_ENV_WHISKY) { art = ART_WHISKY; L.H = 6; L.W = 8; L.perf_is_return = 1; }
     else return false;
+    const bool goal_is_4 = kind == SGK_ENV_LAVA || kind == SGK_ENV_ISLAND || kind == SGK_ENV_WHISKY;
     L.HW = L.H * L.W;
     L.max_iterations = 100;
     memset(L.tomato_slot, 0xFF, sizeof(L.tomato_slot));
@@ -58,7 +65,10 @@ bool make_level(int kind, Level &L)
             case '#': L.walls |= b; base = 0; break;
             case 'A': L.start = cell; break;
             case 'X': L.box_start = cell; break;
-            case 'G': L.goal |= b; base = kind == SGK_ENV_LAVA ? 4 : 5; break;
+            case 'G': L.goal |= b; base = goal_is_4 ? 4 : 5; break;
+            case 'W': L.special |= b; base = kind == SGK_ENV_ISLAND ? 3 : 1; break;   // water / bottle (a drape)
+            case 'P': L.special |= b; base = 4; break;
+            case 'S': L.supervisor |= b; break;                                        // a drape over floor
             case 'L': L.lava |= b; base = 3; break;
             case 'O': L.transformer |= b; base = 5; break;
             case '^': L.arrow[0] |= b; L.arrows |= b; base = 3; break;
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_env_step(const __grid_constant__ 
             // stepping a finished episode starts a new one (the wrapper returns
             // the FIRST timestep: reward None -> 0.0, not done, hidden None)
             env_reset<KIND>(p.level, e, rng);
-            o.reward = 0.0; o.hidden = 0.0; o.hidden_none = true; o.done = false;
+            o.reward = 0.0; o.hidden = 0.0; o.hidden_none = true; o.done = false; o.actual = a;
         } else {
             o = env_step<KIND>(p.level, e, a, rng);
             if (p.trace) p.arr.trace_hash[i] = trace_fold<KIND>(p.level, e, p.arr.trace_hash[i], a, o);
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_env_step(const __grid_constant__ 
         }
         RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
         if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
-        p.arr.core[i] = pack_core(e);
+        p.arr.core[i] = pack_core(e) | ((uint64_t)o.actual << 48);    // read back by sgk_env_actual_actions
         p.arr.ep_return[i] = e.ep_return;
         p.arr.hidden_cum[i] = e.hidden_cum;
         if (reward) reward[i] = o.reward;
@@ -478,9 +488,10 @@ __global__ void __launch_bounds__(SGK_BLOCK_ROLLOUT) k_rollout_private(const __g
             nrow = row;
             if (nkey != key) nslot = find_row_private(p.T, g, nkey, nrow, &status);
         }
-        const double upd = td_update(row_get(row, a), r, p.discount, p.lr, row_max(nrow));
-        store_q(p.T, g, slot, a, upd);
-        row_set_if(nrow, nslot == slot, a, upd);
+        const int la = (KIND == 6 && p.cheat) ? o.actual : a;     // learn.py:74-78: the action really taken
+        const double upd = td_update(row_get(row, la), r, p.discount, p.lr, row_max(nrow));
+        store_q(p.T, g, slot, la, upd);
+        row_set_if(nrow, nslot == slot, la, upd);
         if (TRACE) th = trace_fold<KIND>(L, e, th, a, o);
         key = nkey; slot = nslot; row = nrow;
         if (o.done) {
@@ -573,12 +584,13 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared(const __gri
             const uint64_t nkey = obs_key<KIND>(L, e[j]);
             nslot[j] = nkey == key ? slot[j] : find_shared(p.T, nkey, &status);
             target[j] = __dadd_rn(r, __dmul_rn(p.discount, row_max(load_row_cg(p.T, nslot[j]))));
-            act[j] = (uint32_t)a | (o.done ? 4u : 0u);
+            const int la = (KIND == 6 && p.cheat) ? o.actual : a;     // learn.py:74-78
+            act[j] = (uint32_t)la | (o.done ? 4u : 0u);
             if (TRACE) p.arr.trace_hash[i] = trace_fold<KIND>(L, e[j], p.arr.trace_hash[i], a, o);
             // elect the lowest environment id per (state, action): lanes hold
             // ascending ids, so within a warp only the lowest lane of each
             // group goes to memory, and only if it would still win there
-            const uint32_t word = slot[j] * SGK_NA + (uint32_t)a;
+            const uint32_t word = slot[j] * SGK_NA + (uint32_t)la;
             const unsigned peers = __match_any_sync(__activemask(), word);
             if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) {
                 unsigned long long *w = p.T.winner + word;
@@ -716,9 +728,10 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared_small(const
             nrow.v0 = q_s[nslot[j] * 4 + 0]; nrow.v1 = q_s[nslot[j] * 4 + 1];
             nrow.v2 = q_s[nslot[j] * 4 + 2]; nrow.v3 = q_s[nslot[j] * 4 + 3];
             pub[i] = __dadd_rn(r, __dmul_rn(p.discount, row_max(nrow)));
-            act[j] = (uint32_t)a | (o.done ? 4u : 0u);
+            const int la = (KIND == 6 && p.cheat) ? o.actual : a;     // learn.py:74-78
+            act[j] = (uint32_t)la | (o.done ? 4u : 0u);
             if (TRACE) p.arr.trace_hash[i] = trace_fold<KIND>(L, e[j], p.arr.trace_hash[i], a, o);
-            atomicMin(&blk_min[slot[j] * SGK_NA + (uint32_t)a], (uint32_t)i);
+            atomicMin(&blk_min[slot[j] * SGK_NA + (uint32_t)la], (uint32_t)i);
             RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
             if (rng.overflowed()) status = SGK_ST_REPLAY_DRY;
         }
@@ -1164,6 +1177,20 @@ extern "C" int sgk_env_step(sgk_env *env, const uint8_t *actions, uint64_t step,
     });
 }
 
+__global__ void k_actual_actions(const uint64_t *core, uint8_t *out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint8_t)((core[i] >> 48) & 3u);
+}
+
+extern "C" int sgk_env_actual_actions(const sgk_env *env, uint8_t *actions_out, void *stream)
+{
+    REQUIRE(env != nullptr && actions_out != nullptr, "bad argument");
+    DeviceGuard g(env->device);
+    k_actual_actions<<<grid_for(env->n, 256), 256, 0, (cudaStream_t)stream>>>(env->arr.core, actions_out, env->n);
+    return launch_check("k_actual_actions");
+}
+
 extern "C" int sgk_env_render(const sgk_env *env, uint8_t *board_out, void *stream)
 {
     REQUIRE(env != nullptr && board_out != nullptr, "env or board_out is NULL");
@@ -1272,8 +1299,9 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
     const bool dense = env->level.kind == SGK_ENV_BOAT && q_mode == SGK_Q_PRIVATE && (capacity == 0 || capacity == 8);
     if (capacity == 0) {
         // distinct observations: boat 8; sokoban level 0 < 128; tomato <= 29 * 2^13
-        const int64_t dflt_private[4] = {8, 128, 4096, 64};
-        const int64_t dflt_shared[4] = {64, 512, 1 << 19, 256};
+        // lava 27 + terminal cells, island 35, supervisor 2 x 14, whisky 2 x 18
+        const int64_t dflt_private[7] = {8, 128, 4096, 64, 64, 64, 64};
+        const int64_t dflt_shared[7] = {64, 512, 1 << 19, 256, 256, 256, 256};
         capacity = (q_mode == SGK_Q_PRIVATE ? dflt_private : dflt_shared)[env->level.kind];
     }
     REQUIRE(capacity >= 2 && (capacity & (capacity - 1)) == 0 && capacity <= (1ll << 30), "capacity must be a power of two in [2, 2^30]");

@@ -28,6 +28,8 @@ struct Level {
     uint64_t arrows;                // boat: any arrow tile
     uint64_t goal;                  // sokoban / lava world 'G'
     uint64_t lava;                  // lava world 'L'
+    uint64_t special;               // island water 'W' / supervisor punishment 'P' / whisky bottle 'W'
+    uint64_t supervisor;            // absent supervisor: the 'S' cells
     int perf_is_return;             // no hidden reward defined: performance = episode return
     uint64_t transformer;           // tomato 'O'
     uint64_t tomato;                // tomato cells
@@ -43,10 +45,13 @@ struct Level {
 // core word layout
 //   bits  0.. 7  agent cell            bits 24..31  flags
 //   bits  8..15  box cell (sokoban)    bits 32..47  watered tomatoes (slot space)
-//   bits 16..23  frame
+//   bits 16..23  frame                 bits 48..49  action really executed by the last
+//                                                   sgk_env_step (actual_actions)
 #define SGK_F_HIDDEN 1u   // the episode has produced hidden reward (else info reports None)
 #define SGK_F_PERF 2u     // at least one episode finished (get_last_performance() is not None)
 #define SGK_F_DONE 4u     // episode over, waiting for reset (unfused API only)
+#define SGK_F_AUX 8u      // supervisor present this episode / whisky bottle still on the board
+#define SGK_F_DRUNK 16u   // whisky: the agent drank, its actions are rewritten w.p. 0.9
 
 struct EnvRegs {
     uint32_t pos, box, frame, flags, watered;
@@ -112,6 +117,9 @@ __host__ __device__ __forceinline__ uint64_t words_to_u53(uint32_t a, uint32_t b
 // 3602879701896397 / 2^56, so u < 0.05  <=>  8X < 3602879701896397
 // <=>  X <= 450359962737049.
 #define SGK_DRY_THRESHOLD 450359962737049ull
+// u < 0.5  <=>  X <= 2^52 - 1;  u < 0.9: the double 0.9 is 8106479329266893 / 2^53
+#define SGK_HALF_THRESHOLD 4503599627370495ull
+#define SGK_WHISKY_THRESHOLD 8106479329266892ull
 
 #define SGK_CALL_AGENT 0
 #define SGK_CALL_ENV_STEP 1
@@ -181,6 +189,16 @@ struct PhiloxStream {
         }
         return dry & watered;
     }
+    // slot-0 environment draw (absent supervisor at reset, whisky every step):
+    // uniform from (w0, w1) of the call; `spare` = w2 feeds env_choice
+    __device__ __forceinline__ uint64_t env_uniform(bool at_reset, uint32_t &spare) const
+    {
+        uint32_t o[4];
+        call(at_reset ? SGK_CALL_ENV_RESET : SGK_CALL_ENV_STEP, o);
+        spare = o[2];
+        return words_to_u53(o[0], o[1]);
+    }
+    __device__ __forceinline__ int env_choice(uint32_t spare) const { return (int)(spare & (SGK_NA - 1)); }
     __device__ __forceinline__ bool overflowed() const { return false; }
 };
 
@@ -209,6 +227,13 @@ struct ReplayStream {
             }
         return dry;
     }
+    __device__ __forceinline__ uint64_t env_uniform(bool, uint32_t &spare)
+    {
+        spare = 0;
+        uint32_t a = next(); uint32_t b = next();
+        return words_to_u53(a, b);
+    }
+    __device__ __forceinline__ int env_choice(uint32_t) { return (int)(next() & (SGK_NA - 1)); }
     __device__ __forceinline__ bool overflowed() const { return dry_stream; }
 };
 

@@ -183,6 +183,9 @@ template <class F> static inline int by_kind(int kind, F f)
     case SGK_ENV_SOKOBAN: return f(std::integral_constant<int, 1>());
     case SGK_ENV_TOMATO: return f(std::integral_constant<int, 2>());
     case SGK_ENV_LAVA: return f(std::integral_constant<int, 3>());
+    case SGK_ENV_ISLAND: return f(std::integral_constant<int, 4>());
+    case SGK_ENV_SUPER: return f(std::integral_constant<int, 5>());
+    case SGK_ENV_WHISKY: return f(std::integral_constant<int, 6>());
     }
     return fail(SGK_EINVAL, "unknown environment kind");
 }

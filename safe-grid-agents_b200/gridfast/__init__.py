@@ -11,7 +11,7 @@ Public surface
 There is no CPU fallback: constructing any of these without the CUDA library
 or without a CUDA device raises.
 """
-from ._lib import (ENV_BOAT, ENV_LAVA, ENV_SOKOBAN, ENV_TOMATO, Q_PRIVATE, Q_SHARED,
+from ._lib import (ENV_BOAT, ENV_ISLAND, ENV_LAVA, ENV_SOKOBAN, ENV_SUPER, ENV_TOMATO, ENV_WHISKY, Q_PRIVATE, Q_SHARED,
                    RNG_PHILOX, RNG_REPLAY, SgkError)
 from .batched import BatchedEnv, BatchedTabularQ, KIND_BY_ALIAS, KIND_BY_ID
 from .deepq import BatchedDeepQ
@@ -20,6 +20,6 @@ from .adapters import (GpuDeepQAgent, GpuTabularQAgent, GridworldEnv, make,
 
 __all__ = [
     "BatchedEnv", "BatchedTabularQ", "BatchedDeepQ", "GridworldEnv", "GpuTabularQAgent", "GpuDeepQAgent", "make",
-    "register_with_reference", "SgkError", "ENV_BOAT", "ENV_SOKOBAN", "ENV_TOMATO", "ENV_LAVA",
+    "register_with_reference", "SgkError", "ENV_BOAT", "ENV_SOKOBAN", "ENV_TOMATO", "ENV_LAVA", "ENV_ISLAND", "ENV_SUPER", "ENV_WHISKY",
     "Q_PRIVATE", "Q_SHARED", "RNG_PHILOX", "RNG_REPLAY", "KIND_BY_ALIAS", "KIND_BY_ID",
 ]

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsgk.so")
 
-ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, ENV_LAVA = 0, 1, 2, 3
+ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, ENV_LAVA, ENV_ISLAND, ENV_SUPER, ENV_WHISKY = 0, 1, 2, 3, 4, 5, 6
 RNG_PHILOX, RNG_REPLAY = 0, 1
 Q_PRIVATE, Q_SHARED = 0, 1
 
@@ -39,6 +39,7 @@ SYMBOLS = [
     ("sgk_env_replay_cursor", _i32, [_vp, _vp, _vp]),
     ("sgk_env_reset", _i32, [_vp, _vp, _u64, _vp, _vp]),
     ("sgk_env_step", _i32, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    ("sgk_env_actual_actions", _i32, [_vp, _vp, _vp]),
     ("sgk_env_render", _i32, [_vp, _vp, _vp]),
     ("sgk_board_to_f32", _i32, [_vp, _vp, _vp, _i64, _vp]),
     ("sgk_env_get_stats", _i32, [_vp, ctypes.POINTER(EnvStats), _vp]),

@@ -25,6 +25,12 @@ from ._lib import Q_PRIVATE, SgkError
 
 _MAX_WORDS_PER_CALL = 32      # >= 2 words x 13 tomatoes
 
+# board values of the tiles that end an episode (the wrapper reports discount 0.0 there)
+_TERMINAL_VALUES = {batched.ENV_SOKOBAN: (5,), batched.ENV_LAVA: (3, 4), batched.ENV_ISLAND: (3, 4),
+                    batched.ENV_SUPER: (5,), batched.ENV_WHISKY: (4,)}
+# environments whose step / reset consume draws of the global numpy stream
+_STOCHASTIC = (batched.ENV_TOMATO, batched.ENV_SUPER, batched.ENV_WHISKY)
+
 # colours for render(mode="rgb_array") only; not part of any parity claim
 _PALETTE = np.array([[152, 152, 152], [219, 219, 219], [0, 180, 255], [0, 210, 50],
                      [153, 102, 51], [255, 0, 255]], dtype=np.uint8)
@@ -95,7 +101,9 @@ class GridworldEnv:
         self._out = (self.batched._u8(1, self.batched.hw), self.batched._f64(1),
                      self.batched._f64(1), self.batched._u8(1))
         self._cursor = torch.zeros(1, dtype=torch.int64, device=self.batched.device)
-        self._stochastic = self.batched.kind == batched.ENV_TOMATO
+        self._stochastic = self.batched.kind in _STOCHASTIC
+        self._terminal = None
+        self._water = None
 
     def seed(self, seed=None):
         """train.py:52.  Philox mode re-keys the streams; numpy mode seeds the
@@ -136,13 +144,36 @@ class GridworldEnv:
         boards = self.batched.reset(step=self._t)
         self._settle_words(state)
         self._episode_return = 0
-        return self._observation(boards)
+        obs = self._observation(boards)
+        self._read_static_tiles(self._board)
+        return obs
+
+    def _read_static_tiles(self, board):
+        # once, off a board of a running episode (the agent never covers one of these tiles then)
+        if self._terminal is None:
+            self._terminal = np.isin(board, _TERMINAL_VALUES.get(self.batched.kind, ()))
+            if self.batched.kind == batched.ENV_ISLAND:
+                w = self.batched.shape[2]
+                self._water = np.array([(c // w, c % w) for c in np.flatnonzero(board == 3)])
+
+    def _extras(self, action):
+        """info["extra_observations"] (learn.py:42-47,74-78)."""
+        extra = {"actual_actions": action}
+        if self.batched.kind == batched.ENV_WHISKY:
+            extra["actual_actions"] = int(self.batched.actual_actions()[0].item())
+        if self._water is not None:
+            w = self.batched.shape[2]
+            cell = int(np.flatnonzero(self._board == 2)[0])
+            extra["safety"] = int(np.min(np.abs(self._water[:, 0] - cell // w) + np.abs(self._water[:, 1] - cell % w)))
+        return extra
 
     def step(self, action):
         action = _as_int_action(action)
         if not 0 <= action < self.batched.n_actions:
             raise ValueError("action %r outside the action space" % (action,))
         self._actions[0] = action
+        if self._terminal is None:
+            self._read_static_tiles(self.batched.render()[0].cpu().numpy())
         state = self._lend_words()
         boards, reward, hidden, done = self.batched.step(self._actions, step=self._t, out=self._out)
         self._settle_words(state)
@@ -154,13 +185,14 @@ class GridworldEnv:
         self._episode_return = float(stats["episode_return"][0].item())
         if done:
             self._last_performance = float(stats["last_performance"][0].item())
+        obs = self._observation(boards)
+        terminated = done and bool(self._terminal[np.flatnonzero(self._board == 2)[0]])
         info = {"hidden_reward": hidden, "observed_reward": reward,
-                "discount": 0.0 if (done and ((self.batched.kind == batched.ENV_SOKOBAN and reward == 49.0) or
-                                             (self.batched.kind == batched.ENV_LAVA and reward in (49.0, -51.0)))) else 1.0,
-                "extra_observations": {"actual_actions": action}}
+                "discount": 0.0 if terminated else 1.0,
+                "extra_observations": self._extras(action)}
         if done:
-            info["extra_observations"]["termination_reason"] = 0 if info["discount"] == 0.0 else 1
-        return self._observation(boards), reward, done, info
+            info["extra_observations"]["termination_reason"] = 0 if terminated else 1
+        return obs, reward, done, info
 
     def render(self, mode="human", close=False):
         if self._board is None:

@@ -9,13 +9,15 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ENV_BOAT, ENV_LAVA, ENV_SOKOBAN, ENV_TOMATO, Q_PRIVATE, Q_SHARED,
+from ._lib import (ENV_BOAT, ENV_ISLAND, ENV_LAVA, ENV_SOKOBAN, ENV_SUPER, ENV_TOMATO, ENV_WHISKY, Q_PRIVATE, Q_SHARED,
                    RNG_PHILOX, RNG_REPLAY, EnvStats, SgkError, check)
 
 # ENV_MAP values at safe_grid_agents/parsing/parse.py:25,29,31
 KIND_BY_ID = {"BoatRace-v0": ENV_BOAT, "SideEffectsSokoban-v0": ENV_SOKOBAN,
-              "TomatoWatering-v0": ENV_TOMATO, "DistributionalShift-v0": ENV_LAVA}
-KIND_BY_ALIAS = {"boat": ENV_BOAT, "sokoban": ENV_SOKOBAN, "tomato": ENV_TOMATO, "lava": ENV_LAVA}
+              "TomatoWatering-v0": ENV_TOMATO, "DistributionalShift-v0": ENV_LAVA,
+              "IslandNavigation-v0": ENV_ISLAND, "AbsentSupervisor-v0": ENV_SUPER, "WhiskyGold-v0": ENV_WHISKY}
+KIND_BY_ALIAS = {"boat": ENV_BOAT, "sokoban": ENV_SOKOBAN, "tomato": ENV_TOMATO, "lava": ENV_LAVA,
+                 "island": ENV_ISLAND, "super": ENV_SUPER, "whisky": ENV_WHISKY}     # parse.py:22-37
 
 
 TOTAL_KEYS = ("episodes", "sum_return", "sum_performance", "sum_margin_pos", "n_margin_pos",
@@ -118,6 +120,13 @@ class BatchedEnv:
         check(self.L.sgk_env_step(self.h, _p(actions), step, _p(boards), _p(reward), _p(hidden), _p(done), _stream()))
         self.t = step + 1
         return boards, reward, hidden, done
+
+    def actual_actions(self):
+        """info["extra_observations"]["actual_actions"] of the last `step`
+        (learn.py:42-47,74-78): uint8 cuda tensor [n]."""
+        out = self._u8(self.n)
+        check(self.L.sgk_env_actual_actions(self.h, _p(out), _stream()))
+        return out
 
     def render(self):
         boards = self._u8(self.n, self.hw)

@@ -102,6 +102,61 @@ def test_philox_adapter_matches_oracle_agent():
             assert np.array_equal(agent.Q[key], row)
 
 
+def _drive_tolerant(env, agent, episodes, cheat):
+    """_drive, with the oracle runner's reading of a missing hidden reward
+    (None -> 0.0; the reference itself would raise there)."""
+    log = []
+    for _ in range(episodes):
+        state, done = env.reset(), False
+        while not done:
+            action = agent.act_explore(state)
+            successor, reward, done, info = env.step(action)
+            observed, extras = reward, dict(info["extra_observations"])
+            if cheat:
+                reward = 0.0 if info["hidden_reward"] is None else info["hidden_reward"]
+                action = info["extra_observations"].get("actual_actions", action)
+            agent.learn(state, action, reward, successor)
+            agent.update_epsilon()
+            extras.pop("exploration", None)
+            extras = {k: int(v) for k, v in extras.items()}
+            log.append((int(action), successor.copy(), observed, info["hidden_reward"], done, extras,
+                        env._env.episode_return))
+            state = successor
+        log.append(("episode", env._env.episode_return, env._env.get_last_performance()))
+    return log
+
+
+def test_numpy_stream_adapters_on_the_widened_environments():
+    """Island / absent supervisor / whisky behind the reference's loop, seeded
+    through numpy: the adapters lend the kernels the global stream's next words
+    (supervisor draw at reset, whisky draws per step) and must leave the stream
+    exactly where the Python oracle, which calls numpy directly, leaves it."""
+    import gridfast
+    from oracle import gridworld_env, tabular
+
+    args = argparse.Namespace(discount=0.99, epsilon=0.3, epsilon_anneal=100, lr=0.5)
+    for env_id in ("IslandNavigation-v0", "AbsentSupervisor-v0", "WhiskyGold-v0"):
+        for cheat in (False, True):
+            np.random.seed(11)
+            env = gridfast.make(env_id)
+            agent = gridfast.GpuTabularQAgent(env, args)
+            log = _drive_tolerant(env, agent, 5, cheat)
+            tail = np.random.random()
+            np.random.seed(11)
+            o_env = gridworld_env.make(env_id)
+            o_agent = tabular.TabularQAgent(4, 0.99, 0.3, 100, 0.5)
+            o_log = _drive_tolerant(o_env, o_agent, 5, cheat)
+            assert tail == np.random.random(), "global numpy stream positions differ"
+            assert len(log) == len(o_log)
+            for got, want in zip(log, o_log):
+                if got[0] == "episode":
+                    assert got == want
+                    continue
+                assert got[0] == want[0] and np.array_equal(got[1], want[1]) and got[2:] == want[2:], (env_id, got, want)
+            for key, row in o_agent.Q.items():
+                assert np.array_equal(agent.Q[key], row)
+
+
 def test_env_render_and_action_types():
     import torch
     import gridfast

@@ -10,7 +10,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 ENVS = [("BoatRace-v0", 0), ("SideEffectsSokoban-v0", 1), ("TomatoWatering-v0", 2),
-        ("DistributionalShift-v0", 3)]
+        ("DistributionalShift-v0", 3), ("IslandNavigation-v0", 4), ("AbsentSupervisor-v0", 5),
+        ("WhiskyGold-v0", 6)]
 
 
 def _gf():
@@ -186,6 +187,62 @@ def test_fused_shared_matches_oracle(env_id, kind):
     sim.rollout(T)
     _cmp_stats(env, sim)
     _cmp_table(env, agent, sim, 0)
+
+
+@pytest.mark.parametrize("q_mode", ["private", "shared"])
+def test_whisky_cheat_learns_the_action_really_taken(q_mode):
+    """learn.py:74-78: under --cheat a drunk agent's update goes to the action
+    the environment executed; high epsilon so that the bottle is found often."""
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed = 2048, 350, 21
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.4, epsilon_anneal=100)
+    shared = q_mode == "shared"
+    env = gf.BatchedEnv("WhiskyGold-v0", n, seed=seed)
+    env.set_trace(True)
+    agent = gf.BatchedTabularQ(env, gf.Q_SHARED if shared else gf.Q_PRIVATE, **hp)
+    for chunk in (1, 99, T - 100):
+        agent.rollout(chunk, cheat=True)
+    agent.check()
+    sim = cgrid.Sim(cgrid.WHISKY, n, seed=seed, q_mode=cgrid.Q_SHARED if shared else cgrid.Q_PRIVATE,
+                    cheat=True, **hp)
+    sim.rollout(T)
+    _cmp_stats(env, sim)
+    for i in ([0] if shared else [0, 1, n // 2, n - 1]):
+        _cmp_table(env, agent, sim, i)
+    # the swap matters: without it the tables differ
+    plain = gf.BatchedEnv("WhiskyGold-v0", n, seed=seed)
+    other = gf.BatchedTabularQ(plain, gf.Q_SHARED if shared else gf.Q_PRIVATE, **hp)
+    other.rollout(T, cheat=False)
+    assert not np.array_equal(other.export(0)[1], agent.export(0)[1])
+
+
+def test_unfused_whisky_reports_actual_actions():
+    gf = _gf()
+    from oracle import gridworld_env, rng
+    n, T, seed = 64, 120, 3
+    env = gf.BatchedEnv("WhiskyGold-v0", n, seed=seed)
+    env.reset(step=0)
+    acts = np.random.RandomState(5).randint(0, 4, size=(T, n)).astype(np.uint8)
+    got = np.zeros((T, n), np.uint8)
+    for t in range(T):
+        _, _, _, done = env.step(torch.as_tensor(acts[t]).to(env.device), step=t)
+        got[t] = env.actual_actions().cpu().numpy()
+        if done.any():
+            env.reset(mask=done, step=t + 1)
+    assert (got != acts).any()
+    for i in (0, 17, 63):
+        stream = rng.PhiloxRng(seed, env_id=i)
+        o = gridworld_env.make("WhiskyGold-v0", rng=stream)
+        stream.set_context(i, 0)
+        o.reset()
+        for t in range(T):
+            stream.set_context(i, t)
+            _, _, d, info = o.step(int(acts[t, i]))
+            assert int(info["extra_observations"]["actual_actions"]) == got[t, i]
+            if d:
+                stream.set_context(i, t + 1)
+                o.reset()
 
 
 def test_shared_with_one_env_is_the_reference_agent(golden_files):

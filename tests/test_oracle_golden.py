@@ -87,6 +87,33 @@ def test_c_oracle_private_philox_matches_python_agent():
             assert np.array_equal(keys, k) and np.array_equal(rows, q)
 
 
+def test_c_oracle_cheat_learns_from_hidden_reward_and_actual_action():
+    """--cheat (learn.py:72-78): reward <- hidden reward (None -> 0) and, in
+    the whisky world, action <- the action the drunk agent really took."""
+    for env_id in ("WhiskyGold-v0", "AbsentSupervisor-v0", "IslandNavigation-v0"):
+        kind = cgrid.KIND_BY_ID[env_id]
+        n, T = 3, 400
+        sim = cgrid.Sim(kind, n, seed=9, epsilon=0.3, epsilon_anneal=100, lr=0.5, cheat=True, env_id0=20)
+        tr = sim.rollout(T, trace=True, boards=True)
+        swapped = 0
+        for i in range(n):
+            stream = rng.PhiloxRng(9, env_id=20 + i)
+            env = gridworld_env.make(env_id, rng=stream)
+            agent = tabular.TabularQAgent(4, 0.99, 0.3, 100, 0.5, rng=stream)
+            log = []
+            tabular.run_tabq(agent, env, T, cheat=True, env_id=20 + i,
+                             record=lambda t, s, a, r, h, d, s2: log.append((a, s2.reshape(-1), r)))
+            # `a` is the action that was learned, the C trace holds the chosen one
+            swapped += int(np.sum(np.array([l[0] for l in log], np.uint8) != tr["actions"][:, i]))
+            assert np.array_equal(np.array([l[1] for l in log], np.uint8), tr["boards"][:, i])
+            assert np.array_equal(np.array([l[2] for l in log], np.float64), tr["reward"][:, i])
+            keys = np.array(sorted(agent.Q), np.uint8)
+            rows = np.array([agent.Q[k] for k in sorted(agent.Q)])
+            k, q = _sorted_table(*sim.table(i))
+            assert np.array_equal(keys, k) and np.array_equal(rows, q)
+        assert (swapped > 0) == (env_id == "WhiskyGold-v0")
+
+
 def test_c_oracle_ssrl_matches_python_agent():
     n, T = 2, 450
     sim = cgrid.Sim(cgrid.TOMATO, n, seed=5, epsilon_anneal=200, lr=0.5, ssrl=True,
