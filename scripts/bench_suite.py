@@ -18,7 +18,12 @@ for p in (ROOT, os.path.join(ROOT, "safe-grid-agents_b200")):
 import gridfast  # noqa: E402
 
 HP = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=100000)
-B_ALG = {"BoatRace-v0": 132, "SideEffectsSokoban-v0": 158, "TomatoWatering-v0": 208}
+# SURVEY 8(d) contract: 2 x board + 2 x scalars + 52 (Q traffic) + 10 (outputs)
+B_ALG = {"BoatRace-v0": 132, "SideEffectsSokoban-v0": 158, "TomatoWatering-v0": 208,
+         "DistributionalShift-v0": 208, "IslandNavigation-v0": 178, "AbsentSupervisor-v0": 180,
+         "WhiskyGold-v0": 180}
+BASE_ENVS = ("BoatRace-v0", "SideEffectsSokoban-v0", "TomatoWatering-v0")
+WIDENED_ENVS = ("DistributionalShift-v0", "IslandNavigation-v0", "AbsentSupervisor-v0", "WhiskyGold-v0")
 PEAK = 6550.7
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -162,6 +167,10 @@ def main():
         fused("TomatoWatering-v0", 65536, 1000, P, capacity=8192, reps=3, warm=1, label="C4 tomato private")
         fused("TomatoWatering-v0", 65536, 1000, P, capacity=8192, reps=3, warm=1, ssrl=True, label="C4 tomato private + SSRL")
         fused("TomatoWatering-v0", 65536, 1000, S, label="C4 tomato shared")
+    if "widened" in which:
+        for env_id in WIDENED_ENVS:
+            fused(env_id, 65536, 5000, P, label="8(f3) private")
+            fused(env_id, 65536, 1000, S, label="8(f3) shared")
     if "large" in which:
         fused("BoatRace-v0", 1 << 24, 200, P, reps=3, label="large-N boat private 2^24 x 200")
         fused("SideEffectsSokoban-v0", 1 << 22, 200, P, reps=3, label="large-N sokoban private 2^22 x 200")
@@ -172,7 +181,7 @@ def main():
             dqn(4096, 4096, 200, use_tc, label="C5 sokoban DQN 4096 envs, batch 4096")
             dqn(4096, 64 * 4096, 50, use_tc, label="C5 sokoban DQN 4096 envs, batch 64 per env-step")
     if "unfused" in which:
-        for env_id in B_ALG:
+        for env_id in BASE_ENVS:
             unfused_step(env_id, 1 << 24)
         unfused_agent("BoatRace-v0", 1 << 24)
 
