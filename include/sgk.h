@@ -290,6 +290,11 @@ int sgk_dqn_qvalues(sgk_dqn *d, int which, const uint8_t *boards, int64_t n, flo
 /* ReplayBuffer.add for n transitions (contain.py:15-17) */
 int sgk_dqn_replay_add(sgk_dqn *d, const uint8_t *s, const uint8_t *a, const double *r, const uint8_t *s2,
                        const uint8_t *term, int64_t n, void *stream);
+/* Rows [first, first + n) of the ring, i.e. ReplayBuffer.buffer entries in
+ * insertion order modulo capacity (contain.py:8-17): device arrays, any may be
+ * NULL.  Inspection / checkpointing; not on the hot path. */
+int sgk_dqn_replay_get(const sgk_dqn *d, int64_t first, int64_t n, uint8_t *s, uint8_t *a, float *r,
+                       uint8_t *s2, uint8_t *term, void *stream);
 /* DeepQAgent.learn after replay.add (value.py:115-136): sample batch_size
  * transitions with replacement, loss, backward, clip_grad_norm_(10), Adam.
  * loss_out (device float[3], may be NULL) = loss, gradient norm, clip factor. */
@@ -307,9 +312,14 @@ int sgk_dqn_last_scalars(const sgk_dqn *d, float *out3, void *stream);
 int sgk_dqn_set_tensor_cores(sgk_dqn *d, int enabled);
 /* n_steps lock-steps of the dqn_learn body (common/learn.py:29-58) for every
  * environment: act_explore, env.step, replay.add, learn, update_epsilon,
- * target sync every sync_every steps, reset when done.  learn == 0 runs the
- * random-policy warm-up that only fills the ring (common/warmup.py:8-23). */
-int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64_t t0, int learn, void *stream);
+ * target sync every sync_every steps, reset when done.  `mode` is a bit set:
+ * without SGK_DQN_LEARN the random-policy warm-up that only fills the ring
+ * runs (common/warmup.py:8-23); SGK_DQN_CHEAT is args.cheat (learn.py:39-47):
+ * the transition stores info["hidden_reward"] (None -> 0) as its reward and
+ * the action the environment really executed ("actual_actions"). */
+#define SGK_DQN_LEARN 1
+#define SGK_DQN_CHEAT 2
+int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64_t t0, int mode, void *stream);
 
 /* get_discounted_returns (common/agents/policy_base.py:179-186) for a block of
  * n_steps lock-steps collected from `env`: reward / done are device

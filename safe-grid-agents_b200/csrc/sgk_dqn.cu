@@ -423,6 +423,7 @@ struct DqnStepArgs {
     const float *q;
     unsigned long long thr;
     int random_policy;
+    int cheat;              // learn.py:39-47: store the hidden reward and the action really taken
     int64_t cap, pos0;
     uint8_t *r_s, *r_s2, *r_a, *r_term;
     float *r_r;
@@ -457,8 +458,8 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_step(const __grid_constant__ 
     for (int c = 0; c < L.HW; c++) s[c] = render_cell<KIND>(L, e, c);
     const StepOut o = env_step<KIND>(L, e, a, rng);
     for (int c = 0; c < L.HW; c++) s2[c] = render_cell<KIND>(L, e, c);
-    p.r_a[slot] = (uint8_t)a;
-    p.r_r[slot] = (float)o.reward;
+    p.r_a[slot] = (uint8_t)(p.cheat ? o.actual : a);
+    p.r_r[slot] = (float)(p.cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward);
     p.r_term[slot] = o.done ? 1 : 0;
     if (o.done) {
         EpStats st;
@@ -781,6 +782,21 @@ extern "C" int sgk_dqn_replay_add(sgk_dqn *d, const uint8_t *s, const uint8_t *a
     return launch_check("k_replay_add");
 }
 
+extern "C" int sgk_dqn_replay_get(const sgk_dqn *d, int64_t first, int64_t n, uint8_t *s, uint8_t *a, float *r,
+                                  uint8_t *s2, uint8_t *term, void *stream)
+{
+    REQUIRE(d != nullptr && first >= 0 && n > 0 && first + n <= d->cap, "rows outside the ring");
+    DeviceGuard g(d->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t hw = (size_t)d->hw;
+    if (s) CU(cudaMemcpyAsync(s, d->r_s + (size_t)first * hw, (size_t)n * hw, cudaMemcpyDeviceToDevice, st));
+    if (s2) CU(cudaMemcpyAsync(s2, d->r_s2 + (size_t)first * hw, (size_t)n * hw, cudaMemcpyDeviceToDevice, st));
+    if (a) CU(cudaMemcpyAsync(a, d->r_a + first, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    if (r) CU(cudaMemcpyAsync(r, d->r_r + first, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (term) CU(cudaMemcpyAsync(term, d->r_term + first, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    return SGK_OK;
+}
+
 // loss, backward, clip, Adam on the batch already staged in x / x2 / b_a / b_r / b_term
 static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
 {
@@ -883,9 +899,11 @@ extern "C" int sgk_dqn_learn(sgk_dqn *d, uint64_t step, float *loss_out, void *s
     return learn_staged(d, B, loss_out, st);
 }
 
-extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64_t t0, int learn, void *stream)
+extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64_t t0, int mode, void *stream)
 {
     REQUIRE(env != nullptr && d != nullptr && n_steps > 0, "bad argument");
+    REQUIRE((mode & ~(SGK_DQN_LEARN | SGK_DQN_CHEAT)) == 0, "unknown mode bits");
+    const bool learn = (mode & SGK_DQN_LEARN) != 0;
     REQUIRE(env->device == d->device && env->level.kind == d->kind, "agent was created for a different environment kind");
     REQUIRE(env->n <= d->cap, "replay capacity is smaller than one lock-step of transitions");
     DeviceGuard g(env->device);
@@ -905,6 +923,7 @@ extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64
         a.level = env->level; a.arr = env->arr; a.n = env->n; a.env_id0 = env->env_id0; a.seed = env->seed; a.step = t;
         a.words = env->replay_words; a.wpe = env->words_per_env; a.status = env->status;
         a.random_policy = learn ? 0 : 1;
+        a.cheat = (mode & SGK_DQN_CHEAT) ? 1 : 0;
         a.cap = d->cap; a.pos0 = d->count % d->cap;
         a.r_s = d->r_s; a.r_s2 = d->r_s2; a.r_a = d->r_a; a.r_term = d->r_term; a.r_r = d->r_r;
         a.q = d->q_env; a.thr = 0;

@@ -78,6 +78,7 @@ SYMBOLS = [
     ("sgk_dqn_sync_target", _i32, [_vp, _vp]),
     ("sgk_dqn_qvalues", _i32, [_vp, _i32, _vp, _i64, _vp, _vp]),
     ("sgk_dqn_replay_add", _i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    ("sgk_dqn_replay_get", _i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("sgk_dqn_learn", _i32, [_vp, _u64, _vp, _vp]),
     ("sgk_dqn_learn_batch", _i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     ("sgk_dqn_last_scalars", _i32, [_vp, _vp, _vp]),

@@ -84,6 +84,17 @@ class BatchedDeepQ:
     def replay_add(self, s, a, r, s2, term):
         check(self.L.sgk_dqn_replay_add(self.h, _p(s), _p(a), _p(r), _p(s2), _p(term), s.shape[0], _stream()))
 
+    def replay_rows(self, first, n):
+        """Ring rows [first, first + n): (s u8 [n,HW], a u8 [n], r f32 [n], s2 u8 [n,HW], term u8 [n])."""
+        dev = self.env.device
+        s = torch.empty(n, self.env.hw, dtype=torch.uint8, device=dev)
+        s2 = torch.empty_like(s)
+        a = torch.empty(n, dtype=torch.uint8, device=dev)
+        term = torch.empty_like(a)
+        r = torch.empty(n, dtype=torch.float32, device=dev)
+        check(self.L.sgk_dqn_replay_get(self.h, first, n, _p(s), _p(a), _p(r), _p(s2), _p(term), _stream()))
+        return s, a, r, s2, term
+
     @property
     def replay_count(self):
         return self.L.sgk_dqn_replay_count(self.h)
@@ -104,9 +115,11 @@ class BatchedDeepQ:
         check(self.L.sgk_rollout_dqn(self.env.h, self.h, n_steps, self.env.t, 0, _stream()))
         self.env.t += n_steps
 
-    def rollout(self, n_steps):
-        """n_steps lock-steps of act_explore / step / replay.add / learn / sync."""
-        check(self.L.sgk_rollout_dqn(self.env.h, self.h, n_steps, self.env.t, 1, _stream()))
+    def rollout(self, n_steps, cheat=False):
+        """n_steps lock-steps of act_explore / step / replay.add / learn / sync;
+        `cheat` = args.cheat (learn.py:39-47): learn from the hidden reward and
+        the action really executed."""
+        check(self.L.sgk_rollout_dqn(self.env.h, self.h, n_steps, self.env.t, 1 | (2 if cheat else 0), _stream()))
         self.env.t += n_steps
 
     def last_scalars(self):

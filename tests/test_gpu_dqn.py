@@ -101,6 +101,41 @@ def test_warmup_fills_ring_with_oracle_random_walk():
     assert np.array_equal(env.render().cpu().numpy(), sim.boards())
 
 
+@pytest.mark.parametrize("env_id", ["IslandNavigation-v0", "WhiskyGold-v0"])
+def test_rollout_cheat_stores_hidden_reward_and_actual_action(env_id):
+    """args.cheat in dqn_learn (learn.py:39-47).  With lr = 0 the network never
+    changes, so a plain and a cheating run act identically; their rings must
+    then differ exactly by reward <- hidden reward (None -> 0) and action <-
+    the action the environment executed, as the unfused environment reports
+    them when it is fed the plain run's actions."""
+    import gridfast
+    n, T = 512, 60
+    rings = {}
+    for cheat in (False, True):
+        env = gridfast.BatchedEnv(env_id, n, seed=13)
+        agent = gridfast.BatchedDeepQ(env, replay_capacity=n * T, batch_size=64, lr=0.0, epsilon=0.3,
+                                      epsilon_anneal=10, seed=2)
+        agent.rollout(T, cheat=cheat)
+        rings[cheat] = [x.cpu().numpy().reshape(T, n, -1) for x in agent.replay_rows(0, n * T)]
+    (s0, a0, r0, n0, t0), (s1, a1, r1, n1, t1) = rings[False], rings[True]
+    assert np.array_equal(s0, s1) and np.array_equal(n0, n1) and np.array_equal(t0, t1)
+    env = gridfast.BatchedEnv(env_id, n, seed=13)
+    env.reset(step=0)
+    swapped = 0
+    for t in range(T):
+        boards, reward, hidden, done = env.step(torch.as_tensor(a0[t, :, 0]).to(env.device), step=t)
+        actual = env.actual_actions().cpu().numpy()
+        assert np.array_equal(boards.cpu().numpy(), n0[t])
+        assert np.array_equal(reward.cpu().numpy().astype(np.float32), r0[t, :, 0])
+        assert np.array_equal(np.nan_to_num(hidden.cpu().numpy(), nan=0.0).astype(np.float32), r1[t, :, 0])
+        assert np.array_equal(actual, a1[t, :, 0])
+        swapped += int((actual != a0[t, :, 0]).sum())
+        if done.any():
+            env.reset(mask=done, step=t + 1)
+    assert (swapped > 0) == (env_id == "WhiskyGold-v0")
+    assert not np.array_equal(r0, r1)
+
+
 def _train_and_score(agent, env, train_steps=1500, score_steps=300):
     agent.warmup(40)
     base = env.totals()
