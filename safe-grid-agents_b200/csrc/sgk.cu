@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -108,6 +109,7 @@ struct sgk_tabq {
     int64_t n_tables, cap, n_envs;
     int log_cap;
     uint32_t dense_open;       // boat race, private tables: minimal perfect hash
+    int table_major;           // hashed private tables: [table][slot] instead of [slot][table]
     unsigned long long *keys;
     double *q;
     double *c;
@@ -140,6 +142,8 @@ static TableView view_of(const sgk_tabq *q)
     TableView T;
     T.keys = q->keys; T.q = q->q; T.c = q->c; T.winner = q->winner;
     T.n_tables = (uint32_t)q->n_tables; T.cap = (uint32_t)q->cap; T.log_cap = (uint32_t)q->log_cap;
+    T.slot_stride = q->table_major ? 1u : (uint32_t)q->n_tables;
+    T.table_stride = q->table_major ? (uint32_t)q->cap : 1u;
     T.dense_open = q->dense_open;
     return T;
 }
@@ -430,8 +434,13 @@ __device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i
 // reference dict's.  Otherwise: hashed open addressing.
 // 128-thread blocks measured best (64: -8 % boat, -27 % sokoban; see profiles/r01_suite.md)
 #define SGK_BLOCK_ROLLOUT 128
+// Sokoban (config 3: 131,072 environments per GPU = 1,024 blocks) must fit 7 blocks
+// per SM -- at 6 the grid needs a second wave and the rollout loses a quarter
+// of its rate (measured 4.6e10 -> 3.3e10 env-steps/s when the kernel grew from
+// 72 to 77 registers).  7 x 128 threads => at most 72 registers.
 template <int KIND, class Rng, bool TRACE, bool SSRL, bool DENSE>
-__global__ void __launch_bounds__(SGK_BLOCK_ROLLOUT) k_rollout_private(const __grid_constant__ RolloutArgs p)
+__global__ void __launch_bounds__(SGK_BLOCK_ROLLOUT, (KIND == 1 && !SSRL) ? 7 : 1)
+k_rollout_private(const __grid_constant__ RolloutArgs p)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
@@ -1312,6 +1321,10 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
     q->device = env->device; q->kind = env->level.kind; q->q_mode = q_mode;
     q->n_envs = env->n;
     q->n_tables = q_mode == SGK_Q_PRIVATE ? env->n : 1;
+    // large hashed private tables are laid out table-major (measured: tomato, capacity 8192,
+    // +29 %; +42 % with SSRL); small ones stay slot-major (lock-step neighbours share slots:
+    // sokoban / lava / island lose 5-25 % table-major) -- profiles/r01_suite.md
+    q->table_major = (q_mode == SGK_Q_PRIVATE && !dense && capacity > 512) ? 1 : 0;
     q->cap = capacity;
     q->log_cap = 0;
     while ((1ll << q->log_cap) < capacity) q->log_cap++;

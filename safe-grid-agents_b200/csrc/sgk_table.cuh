@@ -6,12 +6,17 @@
 // observation code (sgk_envs.cuh obs_key): exact keys, so lookups can never
 // alias two boards -- same semantics as the dict.
 //
-// Layout in HBM: slot-major across tables,
-//     keys[slot][table]        u64   (0 = empty)
-//     q   [slot][table][4]     f64
-// so that when the 32 environments of a warp (32 private tables) sit in the
-// same state, their probes and row loads are one contiguous 256 B / 1 KB
-// access; a shared table is the n_tables == 1 case of the same layout.
+// Two layouts in HBM, chosen per table set at creation (TableView strides):
+//   slot-major   keys[slot][table] u64 (0 = empty), q[slot][table][4] f64
+//       the dense boat-race tables: 8 slots, and the 32 environments of a
+//       warp mostly sit in neighbouring slots, so a warp's probe / row load is
+//       a few contiguous 256 B / 1 KB runs; a shared table is its
+//       n_tables == 1 case;
+//   table-major  keys[table][slot], q[table][slot][4]
+//       hashed private tables: every environment probes a different random
+//       slot, so nothing coalesces either way, but each table is one
+//       contiguous 40 * cap byte region -- a warp's 32 accesses fall into a
+//       handful of 2 MB pages instead of 64 (TLB reach, DRAM page locality).
 #pragma once
 #include "sgk_common.cuh"
 
@@ -25,6 +30,7 @@ struct TableView {
     double *c;                    // SSRL corruption estimate per slot (or null)
     unsigned long long *winner;   // shared mode: [cap][4] election words
     uint32_t n_tables;            // cap * n_tables < 2^32 (checked at creation)
+    uint32_t slot_stride, table_stride;   // entry index = slot * slot_stride + table * table_stride
     uint32_t cap, log_cap;
     uint32_t dense_open;          // != 0: minimal perfect hash (boat race), see dense_slot
 };
@@ -45,7 +51,7 @@ __device__ __forceinline__ uint32_t dense_slot(uint32_t open32, uint32_t pos)
 
 __device__ __forceinline__ size_t entry(const TableView &T, uint32_t slot, uint32_t g)
 {
-    return (size_t)(slot * T.n_tables + g);
+    return (size_t)(slot * T.slot_stride + g * T.table_stride);
 }
 
 // find-or-insert in a table only this thread touches

@@ -41,4 +41,11 @@ elif what == "shared":
     agent = gridfast.BatchedTabularQ(env, gridfast.Q_SHARED)
     for _ in range(3):
         agent.rollout(200)
+elif what == "tomato":
+    # C4 shape at a quarter of the environments (tables 5 GB instead of 21 GB: ncu replays)
+    env = gridfast.BatchedEnv("TomatoWatering-v0", 16384, seed=0)
+    agent = gridfast.BatchedTabularQ(env, gridfast.Q_PRIVATE, capacity=8192)
+    for _ in range(3):
+        agent.rollout(500)
+    agent.check()
 torch.cuda.synchronize()
