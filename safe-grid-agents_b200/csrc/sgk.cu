@@ -54,6 +54,7 @@ bool make_level(int kind, Level &L)
     else return false;
     const bool goal_is_4 = kind == SGK_ENV_LAVA || kind == SGK_ENV_ISLAND || kind == SGK_ENV_WHISKY;
     L.HW = L.H * L.W;
+    if (L.HW != by_kind(kind, [](auto K) { return KindCells<decltype(K)::value>::value; })) return false;
     L.max_iterations = 100;
     memset(L.tomato_slot, 0xFF, sizeof(L.tomato_slot));
     for (int r = 0; r < L.H; r++)
@@ -249,10 +250,11 @@ __global__ void k_board_to_f32(const uint8_t *boards, float *out, int64_t total)
         out[k] = (float)boards[k];
 }
 
+template <int KIND>
 __global__ void k_board_to_key(const __grid_constant__ Level L, const uint8_t *boards, uint64_t *keys, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = board_key(L, boards + i * L.HW);
+    if (i < n) keys[i] = board_key<KIND>(L, boards + i * KindCells<KIND>::value);
 }
 
 // ===================================================================== unfused agent kernels
@@ -272,7 +274,7 @@ struct AgentArgs {
     int ssrl;
 };
 
-template <class Rng>
+template <int KIND, class Rng>
 __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_act(const __grid_constant__ AgentArgs p, const uint8_t *boards,
                                                         int explore, uint8_t *actions)
 {
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_act(const __grid_constant__ 
     }
     if (greedy) {
         // np.argmax(Q[key]) -- the defaultdict inserts a zero row on a miss
-        const uint64_t key = board_key(p.level, boards + i * p.level.HW);
+        const uint64_t key = board_key<KIND>(p.level, boards + i * KindCells<KIND>::value);
         const long long g = p.q_mode == SGK_Q_PRIVATE ? i : 0;
         const uint32_t slot = p.q_mode == SGK_Q_PRIVATE ? find_private(p.T, g, key, p.status) : find_shared(p.T, key, p.status);
         a = argmax_first(load_row(p.T, g, slot));
@@ -299,14 +301,15 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_act(const __grid_constant__ 
 }
 
 // private tables: the whole of TabularQAgent.learn in one pass
+template <int KIND>
 __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_private(const __grid_constant__ AgentArgs p, const uint8_t *boards,
                                                                   const uint8_t *actions, const double *rewards,
                                                                   const uint8_t *successors)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    const uint64_t skey = board_key(p.level, boards + i * p.level.HW);
-    const uint64_t nkey = board_key(p.level, successors + i * p.level.HW);
+    const uint64_t skey = board_key<KIND>(p.level, boards + i * KindCells<KIND>::value);
+    const uint64_t nkey = board_key<KIND>(p.level, successors + i * KindCells<KIND>::value);
     const uint32_t nslot = find_private(p.T, i, nkey, p.status);
     const uint32_t slot = find_private(p.T, i, skey, p.status);
     const int a = actions[i] & 3;
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_private(const __grid_c
 }
 
 // shared table, phase A: targets from the table as it is, elect lowest index
+template <int KIND>
 __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_shared_a(const __grid_constant__ AgentArgs p, const uint8_t *boards,
                                                                    const uint8_t *actions, const double *rewards,
                                                                    const uint8_t *successors, uint32_t *scr_slot,
@@ -325,8 +329,8 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_shared_a(const __grid_
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
-    const uint64_t skey = board_key(p.level, boards + i * p.level.HW);
-    const uint64_t nkey = board_key(p.level, successors + i * p.level.HW);
+    const uint64_t skey = board_key<KIND>(p.level, boards + i * KindCells<KIND>::value);
+    const uint64_t nkey = board_key<KIND>(p.level, successors + i * KindCells<KIND>::value);
     const uint32_t nslot = find_shared(p.T, nkey, p.status);
     const uint32_t slot = find_shared(p.T, skey, p.status);
     const int a = actions[i] & 3;
@@ -439,7 +443,10 @@ __device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i
 // of its rate (measured 4.6e10 -> 3.3e10 env-steps/s when the kernel grew from
 // 72 to 77 registers).  7 x 128 threads => at most 72 registers.
 template <int KIND, class Rng, bool TRACE, bool SSRL, bool DENSE>
-__global__ void __launch_bounds__(SGK_BLOCK_ROLLOUT, (KIND == 1 && !SSRL) ? 7 : 1)
+#ifndef SGK_BOAT_MINBLOCKS
+#define SGK_BOAT_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(SGK_BLOCK_ROLLOUT, (KIND == 1 && !SSRL) ? 7 : (KIND == 0 && !SSRL) ? SGK_BOAT_MINBLOCKS : 1)
 k_rollout_private(const __grid_constant__ RolloutArgs p)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1230,8 +1237,10 @@ extern "C" int sgk_board_to_key(const sgk_env *env, const uint8_t *boards, uint6
     REQUIRE(env != nullptr && boards != nullptr && keys_out != nullptr && n >= 0, "bad argument");
     if (n == 0) return SGK_OK;
     DeviceGuard g(env->device);
-    k_board_to_key<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(env->level, boards, keys_out, n);
-    return launch_check("k_board_to_key");
+    return by_kind(env->level.kind, [&](auto K) {
+        k_board_to_key<decltype(K)::value><<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(env->level, boards, keys_out, n);
+        return launch_check("k_board_to_key");
+    });
 }
 
 extern "C" int sgk_env_get_stats(const sgk_env *env, const sgk_env_stats *out, void *stream)
@@ -1419,11 +1428,14 @@ extern "C" int sgk_tabq_act(sgk_tabq *q, sgk_env *env, const uint8_t *boards, in
     REQUIRE(!explore || n <= env->n, "n exceeds the environment count");
     DeviceGuard g(q->device);
     const AgentArgs a = agent_args(q, env, n, step);
-    if (explore && env->rng_mode == SGK_RNG_REPLAY)
-        k_tabq_act<ReplayStream><<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, (cudaStream_t)stream>>>(a, boards, explore, actions_out);
-    else
-        k_tabq_act<PhiloxStream><<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, (cudaStream_t)stream>>>(a, boards, explore, actions_out);
-    return launch_check("k_tabq_act");
+    return by_kind(q->kind, [&](auto K) {
+        constexpr int KIND = decltype(K)::value;
+        if (explore && env->rng_mode == SGK_RNG_REPLAY)
+            k_tabq_act<KIND, ReplayStream><<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, (cudaStream_t)stream>>>(a, boards, explore, actions_out);
+        else
+            k_tabq_act<KIND, PhiloxStream><<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, (cudaStream_t)stream>>>(a, boards, explore, actions_out);
+        return launch_check("k_tabq_act");
+    });
 }
 
 extern "C" int sgk_tabq_learn(sgk_tabq *q, const uint8_t *boards, const uint8_t *actions, const double *rewards,
@@ -1435,8 +1447,10 @@ extern "C" int sgk_tabq_learn(sgk_tabq *q, const uint8_t *boards, const uint8_t 
     cudaStream_t st = (cudaStream_t)stream;
     if (q->q_mode == SGK_Q_PRIVATE) {
         const AgentArgs a = agent_args(q, nullptr, n, 0);
-        k_tabq_learn_private<<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a, boards, actions, rewards, successors);
-        return launch_check("k_tabq_learn_private");
+        return by_kind(q->kind, [&](auto K) {
+            k_tabq_learn_private<decltype(K)::value><<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a, boards, actions, rewards, successors);
+            return launch_check("k_tabq_learn_private");
+        });
     }
     REQUIRE(n < (1ll << 32), "batch too large");
     if (q->scr_cap < n) {
@@ -1449,7 +1463,11 @@ extern "C" int sgk_tabq_learn(sgk_tabq *q, const uint8_t *boards, const uint8_t 
     }
     q->epoch += 1;
     const AgentArgs a = agent_args(q, nullptr, n, 0);
-    k_tabq_learn_shared_a<<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a, boards, actions, rewards, successors, q->scr_slot, q->scr_target);
+    const int rc = by_kind(q->kind, [&](auto K) {
+        k_tabq_learn_shared_a<decltype(K)::value><<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a, boards, actions, rewards, successors, q->scr_slot, q->scr_target);
+        return launch_check("k_tabq_learn_shared_a");
+    });
+    if (rc != SGK_OK) return rc;
     k_tabq_learn_shared_b<<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a, actions, q->scr_slot, q->scr_target);
     return launch_check("k_tabq_learn_shared");
 }

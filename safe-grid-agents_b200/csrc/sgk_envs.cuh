@@ -202,19 +202,24 @@ __device__ __forceinline__ uint64_t obs_key(const Level &L, const EnvRegs &e)
     return k;
 }
 
-// The same code computed from board bytes (API boundary).
+// The same code computed from board bytes (API boundary).  KindCells (cells per
+// board of a kind) is compile-time so the scan unrolls.
+template <int KIND> struct KindCells { static constexpr int value = KIND == 0 ? 25 : KIND == 1 ? 36 : KIND <= 3 ? 63 : 48; };
+
+template <int KIND>
 __device__ __forceinline__ uint64_t board_key(const Level &L, const uint8_t *board)
 {
     uint64_t k = 1ull << 63;
     uint32_t seen = 0;
-    for (int c = 0; c < L.HW; c++) {
+#pragma unroll
+    for (int c = 0; c < KindCells<KIND>::value; c++) {
         const uint8_t v = board[c];
         if (v == 2) k |= (uint64_t)c;
-        if (L.kind == 1 && v == 4) k |= (uint64_t)c << 8;
-        if (L.kind == 2 && v == 4 && L.tomato_slot[c] != 0xFFu) seen |= 1u << L.tomato_slot[c];
-        if ((L.kind == 5 || L.kind == 6) && v == 3) k |= 1ull << 8;
+        if (KIND == 1 && v == 4) k |= (uint64_t)c << 8;
+        if (KIND == 2 && v == 4 && L.tomato_slot[c] != 0xFFu) seen |= 1u << L.tomato_slot[c];
+        if ((KIND == 5 || KIND == 6) && v == 3) k |= 1ull << 8;
     }
-    if (L.kind == 2) k |= (uint64_t)seen << 8;
+    if (KIND == 2) k |= (uint64_t)seen << 8;
     return k;
 }
 

@@ -146,13 +146,18 @@ struct EpStats {
 
 // Block-cooperative coalesced store of one board per thread: render into
 // shared memory, then write the block's contiguous byte range as 16 B words.
+// KindCells<KIND> (== Level::HW, checked in make_level) is compile-time: the
+// render loop unrolls and backdrop bytes become constant-bank operands.
 template <int KIND>
 __device__ __forceinline__ void store_boards(const Level &L, const EnvRegs &e, bool valid, uint8_t *board_out,
                                              int64_t n, uint8_t *smem)
 {
-    const int hw = L.HW;
-    if (valid)
-        for (int c = 0; c < hw; c++) smem[threadIdx.x * hw + c] = render_cell<KIND>(L, e, c);
+    constexpr int hw = KindCells<KIND>::value;
+    if (valid) {
+        uint8_t *mine = smem + threadIdx.x * hw;
+#pragma unroll
+        for (int c = 0; c < hw; c++) mine[c] = render_cell<KIND>(L, e, c);
+    }
     __syncthreads();
     const int64_t first = (int64_t)blockIdx.x * blockDim.x;
     const int64_t count = min((int64_t)blockDim.x, n - first);
