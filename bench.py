@@ -148,6 +148,25 @@ def cpu_port_rate(n_procs, n_steps):
     return sum(r[0] for r in res) / wall
 
 
+def c_port_rate():
+    """The plain-C restatement (oracle/cgrid.c, pthreads over environments) on
+    all host cores: a stronger CPU yardstick than the Python port, reported
+    beside it.  None if the oracle library is not built."""
+    try:
+        from oracle import cgrid
+        n, T = 65536, 100
+        sim = cgrid.Sim(cgrid.BOAT, n, seed=0, lr=HP["lr"], discount=HP["discount"], epsilon=HP["epsilon"],
+                        epsilon_anneal=HP["epsilon_anneal"])
+        sim.rollout(10)
+        t = time.perf_counter()
+        sim.rollout(T)
+        dt = time.perf_counter() - t
+        return {"value": n * T / dt, "unit": "env-steps/s", "cores": min(os.cpu_count() or 1, 64),
+                "sample": "%d envs x %d lock-steps of boat-race tabular-Q, C oracle (pthreads), %.2f s" % (n, T, dt)}
+    except Exception as exc:      # the C yardstick is optional; the Python port below is the contract value
+        return {"unavailable": repr(exc)[:200]}
+
+
 def run_reference(args, out):
     """--impl reference: the CPU implementation of the path on all host cores.
     /root/reference is pure Python whose env half is an absent third-party
@@ -179,7 +198,8 @@ def run_reference(args, out):
         "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "reference_sample": sample},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "c_port": c_port_rate()},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=out, flush=True)
@@ -316,7 +336,8 @@ def run_ours(args, out):
             rate = cpu_port_rate(1, 150000)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                "sample": "150000 env-steps of boat-race tabular-Q, python oracle port, 1 process (%.1f s)" % (time.perf_counter() - t)}
+                "sample": "150000 env-steps of boat-race tabular-Q, python oracle port, 1 process (%.1f s)" % (time.perf_counter() - t),
+                "c_port": c_port_rate()}
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
