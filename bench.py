@@ -279,6 +279,7 @@ def run_ours(args, out):
     agent.check()
     step_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     drain_ms = starts[K].elapsed_time(ends[K])
+    kernel_ms_by_step = [round(s.elapsed_time(e), 4) for s, e in zip(kstart, kend)]    # this rank's
     kernel_ms = sum(s.elapsed_time(e) for s, e in zip(kstart, kend))
     t = torch.tensor([step_ms, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -325,7 +326,10 @@ def run_ours(args, out):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
                          "algorithmic_bytes_per_env_step": B_ALG, "peak_source": peak_src,
-                         "kernel_ms_per_launch": kernel_ms / K},
+                         "kernel_ms_per_launch": kernel_ms / K,
+                         # epsilon anneals over the first 100,000 agent steps: early launches explore
+                         # (environments of a warp spread over the states), later ones run greedy
+                         "kernel_ms_by_launch": kernel_ms_by_step},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": 4 * K, "stats_allreduce_ms": drain_ms,
             "clocks": clocks.summary(),
