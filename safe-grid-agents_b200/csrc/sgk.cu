@@ -473,12 +473,25 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     // The dict of the reference gains a key when act/learn first touch it
     // (value.py:35,46-52), not when the environment resets: look the start
     // state up without inserting; it is inserted by the step that leaves it.
+    // DENSE: this thread's whole table (cap rows) lives in shared memory for
+    // the rollout, column `threadIdx.x` of q_sm[cap * 4][block] (conflict-free),
+    // so row reads are LDS whatever states the warp's environments are in; the
+    // rows and the keys of the slots touched go back to HBM when the kernel ends.
+    extern __shared__ double q_sm[];
+    auto qs = [&](uint32_t s, int a) -> double & { return q_sm[(s * SGK_NA + a) * SGK_BLOCK_ROLLOUT + threadIdx.x]; };
+    auto row_s = [&](uint32_t s) { QRow r; r.v0 = qs(s, 0); r.v1 = qs(s, 1); r.v2 = qs(s, 2); r.v3 = qs(s, 3); return r; };
+    uint32_t touched = 0;
+    if (DENSE)
+        for (uint32_t s = 0; s < p.T.cap; s++) {
+            const QRow r = load_row(p.T, g, s);
+            qs(s, 0) = r.v0; qs(s, 1) = r.v1; qs(s, 2) = r.v2; qs(s, 3) = r.v3;
+        }
     uint64_t key = obs_key<KIND>(L, e);
     uint32_t slot = SGK_NOSLOT;
     QRow row = {0.0, 0.0, 0.0, 0.0};
     if (DENSE) {
         slot = dense_slot(L.open32, e.pos);
-        row = load_row(p.T, g, slot);
+        row = row_s(slot);
     } else if (lookup(p.T, g, key, slot)) {
         row = load_row(p.T, g, slot);
     }
@@ -491,7 +504,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         // act_explore (value.py:37-42)
         int a = greedy;
         if (rng.agent_uniform() < __ldg(p.thr + k)) a = rng.agent_choice();
-        if (DENSE) p.T.keys[entry(p.T, slot, g)] = key;
+        if (DENSE) touched |= 1u << slot;
         else if (slot == SGK_NOSLOT) slot = find_private(p.T, g, key, &status);
         if (SSRL) { p.ssrl_hist[(size_t)n_hist * p.n + i] = slot; n_hist++; }
         // env.step
@@ -504,7 +517,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         QRow nrow;
         if (DENSE) {
             nslot = dense_slot(L.open32, e.pos);
-            nrow = load_row(p.T, g, nslot);          // memory is current: same-thread stores are ordered
+            nrow = row_s(nslot);
         } else {
             nslot = slot;
             nrow = row;
@@ -512,12 +525,13 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         }
         const int la = (KIND == 6 && p.cheat) ? o.actual : a;     // learn.py:74-78: the action really taken
         const double upd = td_update(row_get(row, la), r, p.discount, p.lr, row_max(nrow));
-        store_q(p.T, g, slot, la, upd);
+        if (DENSE) qs(slot, la) = upd;
+        else store_q(p.T, g, slot, la, upd);
         row_set_if(nrow, nslot == slot, la, upd);
         if (TRACE) th = trace_fold<KIND>(L, e, th, a, o);
         key = nkey; slot = nslot; row = nrow;
         if (o.done) {
-            if (DENSE) p.T.keys[entry(p.T, slot, g)] = key;   // learn touched Q[s'] (value.py:48-49)
+            if (DENSE) touched |= 1u << slot;                  // learn touched Q[s'] (value.py:48-49)
             st.episode_end(e, p.level.perf_is_return != 0);
             if (SSRL) { ssrl_episode_end(p, i, i, st, n_hist); n_hist = 0; }
             rng.set_step(p.t0 + (uint64_t)k + 1);
@@ -527,7 +541,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             row = QRow{0.0, 0.0, 0.0, 0.0};
             if (DENSE) {
                 slot = dense_slot(L.open32, e.pos);
-                row = load_row(p.T, g, slot);
+                row = row_s(slot);
             } else if (lookup(p.T, g, key, slot)) {
                 row = load_row(p.T, g, slot);
             }
@@ -535,7 +549,16 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         greedy = argmax_first(row);
         fresh = o.done;
     }
-    if (DENSE && !fresh) p.T.keys[entry(p.T, slot, g)] = key;   // the last learn touched Q[s']
+    if (DENSE) {
+        if (!fresh) touched |= 1u << slot;                      // the last learn touched Q[s']
+        for (uint32_t s = 0; s < p.T.cap; s++) {
+            double2 *dst = reinterpret_cast<double2 *>(p.T.q + entry(p.T, s, g) * SGK_NA);
+            dst[0] = make_double2(qs(s, 0), qs(s, 1));
+            dst[1] = make_double2(qs(s, 2), qs(s, 3));
+            // the key of slot s: the s-th open cell under the agent
+            if ((touched >> s) & 1u) p.T.keys[entry(p.T, s, g)] = (1ull << 63) | (uint64_t)__fns(L.open32, 0, (int)s + 1);
+        }
+    }
     p.arr.core[i] = pack_core(e);
     p.arr.ep_return[i] = e.ep_return;
     p.arr.hidden_cum[i] = e.hidden_cum;
@@ -1637,7 +1660,8 @@ extern "C" int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint
             using Rng = typename decltype(R)::type;
             constexpr bool TRACE_ = decltype(TR)::value, SSRL_ = decltype(SS)::value;
             const unsigned rgrid = grid_for(env->n, SGK_BLOCK_ROLLOUT);
-            if (dense) k_rollout_private<KIND, Rng, TRACE_, SSRL_, CAN_DENSE><<<rgrid, SGK_BLOCK_ROLLOUT, 0, st>>>(a);
+            const size_t dense_smem = (size_t)q->cap * SGK_NA * sizeof(double) * SGK_BLOCK_ROLLOUT;    // 32 KB
+            if (dense) k_rollout_private<KIND, Rng, TRACE_, SSRL_, CAN_DENSE><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a);
             else k_rollout_private<KIND, Rng, TRACE_, SSRL_, false><<<rgrid, SGK_BLOCK_ROLLOUT, 0, st>>>(a);
         };
         if (ssrl) {

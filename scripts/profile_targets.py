@@ -41,6 +41,13 @@ elif what == "shared":
     agent = gridfast.BatchedTabularQ(env, gridfast.Q_SHARED)
     for _ in range(3):
         agent.rollout(200)
+elif what == "rollout":
+    # the bench.py workload: boat, 65,536 envs, 10,000 lock-steps per launch
+    env = gridfast.BatchedEnv("BoatRace-v0", 65536, seed=0)
+    agent = gridfast.BatchedTabularQ(env, gridfast.Q_PRIVATE)
+    for _ in range(3):
+        agent.rollout(10000)
+    agent.check()
 elif what == "tomato":
     # C4 shape at a quarter of the environments (tables 5 GB instead of 21 GB: ncu replays)
     env = gridfast.BatchedEnv("TomatoWatering-v0", 16384, seed=0)
