@@ -48,6 +48,13 @@ elif what == "rollout":
     for _ in range(3):
         agent.rollout(10000)
     agent.check()
+elif what == "sokoban":
+    # config 3, one GPU's share: 131,072 envs, hashed private tables (capacity 128)
+    env = gridfast.BatchedEnv("SideEffectsSokoban-v0", 131072, seed=0)
+    agent = gridfast.BatchedTabularQ(env, gridfast.Q_PRIVATE)
+    for _ in range(3):
+        agent.rollout(5000)
+    agent.check()
 elif what == "tomato":
     # C4 shape at a quarter of the environments (tables 5 GB instead of 21 GB: ncu replays)
     env = gridfast.BatchedEnv("TomatoWatering-v0", 16384, seed=0)
