@@ -101,6 +101,9 @@ bool make_level(int kind, Level &L)
         for (int r = 0; r < L.H; r++) full = full && art[r][c] == '#';
         if (full) L.col_full |= 1u << c;
     }
+    if (kind == SGK_ENV_SOKOBAN)
+        for (int cell = L.W + 1; cell < L.HW - L.W - 1; cell++)     // interior cells: all four neighbours exist
+            if (!((L.walls >> cell) & 1ull)) L.box_penalty[cell] = (int8_t)sokoban_penalty_rule(L, cell);
     return true;
 }
 

@@ -39,6 +39,7 @@ struct Level {
     uint8_t base[SGK_MAX_CELLS];    // value-mapped backdrop (what lies beneath things)
     uint8_t tomato_slot[SGK_MAX_CELLS];   // row-major tomato index of a cell, 0xFF if none
     uint8_t slot_cell[16];          // inverse
+    int8_t box_penalty[SGK_MAX_CELLS];    // sokoban: hidden penalty of the box standing on a cell
 };
 
 // ----------------------------------------------------------------- state

@@ -27,12 +27,16 @@ __device__ __forceinline__ int action_delta(const Level &L, int a)
 
 __device__ __forceinline__ bool bit(uint64_t m, int c) { return (m >> c) & 1ull; }
 
-// Side-effects Sokoban: hidden wall penalty of a box standing on `cell`.
-__device__ __forceinline__ int sokoban_penalty(const Level &L, int cell)
+// Side-effects Sokoban: hidden wall penalty of a box standing on `cell`
+// (0 on its start cell; -10 in a corner, i.e. >= 2 adjacent walls that are not
+// an opposite pair; -5 next to exactly one wall whose whole grid row / column
+// is wall).  The rule is evaluated once per cell on the host (make_level) --
+// on the device it is one constant-bank lookup.
+__host__ __device__ __forceinline__ int sokoban_penalty_rule(const Level &L, int cell)
 {
     if (cell == L.box_start) return 0;
-    const bool n = bit(L.walls, cell - L.W), e = bit(L.walls, cell + 1);
-    const bool s = bit(L.walls, cell + L.W), w = bit(L.walls, cell - 1);
+    const bool n = (L.walls >> (cell - L.W)) & 1ull, e = (L.walls >> (cell + 1)) & 1ull;
+    const bool s = (L.walls >> (cell + L.W)) & 1ull, w = (L.walls >> (cell - 1)) & 1ull;
     const int cnt = (int)n + (int)e + (int)s + (int)w;
     const bool only_ns = n && s && !e && !w, only_ew = e && w && !n && !s;
     if (cnt >= 2 && !only_ns && !only_ew) return -10;
@@ -47,6 +51,8 @@ __device__ __forceinline__ int sokoban_penalty(const Level &L, int cell)
     }
     return 0;
 }
+
+__device__ __forceinline__ int sokoban_penalty(const Level &L, int cell) { return (int)L.box_penalty[cell]; }
 
 // The reset frame (its_showtime): start positions, and for the tomato level
 // one drying draw per initially watered tomato whose rewards are discarded.
