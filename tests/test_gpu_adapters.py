@@ -280,3 +280,22 @@ def test_batched_rollout_collection_matches_reference_returns():
                 start = t + 1
     got = out["returns"].cpu().numpy()
     assert np.allclose(got, want, rtol=1e-5, atol=1e-4)
+
+
+def test_integration_md_ctypes_stub_runs_as_written():
+    """The bare ctypes binding shown in INTEGRATION.md is executed verbatim."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "C.CDLL" in b]
+    assert len(blocks) == 1
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        scope = {}
+        exec(blocks[0], scope)
+    finally:
+        os.chdir(cwd)
+    totals = list(scope["totals"])
+    assert totals[0] == 65536 * 100          # episodes: 10,000 lock-steps / 100 frames, every environment

@@ -265,19 +265,22 @@ def test_shared_with_one_env_is_the_reference_agent(golden_files):
     assert np.array_equal(keys[og], gk[ow]) and np.array_equal(rows[og], g["q_rows"][ow])
 
 
-def test_fused_ssrl_matches_oracle():
+@pytest.mark.parametrize("env_id,kind", [("TomatoWatering-v0", 2), ("BoatRace-v0", 0), ("AbsentSupervisor-v0", 5)])
+def test_fused_ssrl_matches_oracle(env_id, kind):
+    """SSRL over hashed tables (tomato, supervisor) and over the dense boat
+    tables that live in shared memory during the rollout."""
     gf = _gf()
     from oracle import cgrid
     n, T, seed = 256, 650, 4
     hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=300)
-    env = gf.BatchedEnv("TomatoWatering-v0", n, seed=seed)
+    env = gf.BatchedEnv(env_id, n, seed=seed)
     env.set_trace(True)
     agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **hp)
     agent.enable_ssrl(c_prior=0.01, budget=4)
     agent.rollout(250)
     agent.rollout(T - 250)
     agent.check()
-    sim = cgrid.Sim(cgrid.TOMATO, n, seed=seed, ssrl=True, c_prior=0.01, budget=4, **hp)
+    sim = cgrid.Sim(kind, n, seed=seed, ssrl=True, c_prior=0.01, budget=4, **hp)
     sim.rollout(T)
     _cmp_stats(env, sim)
     for i in (0, 17, n - 1):
