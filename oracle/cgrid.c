@@ -154,15 +154,19 @@ static int rng_env_choice(cg_rng *g)
     return (int)(w[2] & (NA - 1));
 }
 
+/* environment draw `slot`: first word from call 1 + slot/4 (8 + slot/4 at a
+ * reset), second word from call 16 + slot/4 (24 + slot/4), word slot%4 of each
+ * (see oracle/rng.py) */
 static double rng_env_uniform(cg_rng *g, int slot, int at_reset)
 {
     if (g->mode == CG_RNG_REPLAY) {
         uint32_t a = rng_next_word(g), b = rng_next_word(g);
         return words_to_double(a, b);
     }
-    uint32_t w[4];
-    rng_call(g, (at_reset ? 8 : 1) + slot / 2, w);
-    return words_to_double(w[2 * (slot % 2)], w[2 * (slot % 2) + 1]);
+    uint32_t hi[4], lo[4];
+    rng_call(g, (at_reset ? 8 : 1) + slot / 4, hi);
+    rng_call(g, (at_reset ? 24 : 16) + slot / 4, lo);
+    return words_to_double(hi[slot % 4], lo[slot % 4]);
 }
 
 /* ------------------------------------------------------------------ env */

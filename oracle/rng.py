@@ -29,15 +29,20 @@ Three interchangeable streams implement the same four draws:
                                       uniform from (a, b), explore action
                                       a & 3, RandomAgent action b & 3 (low bits
                                       the 53-bit uniform does not use)
-                      call 1+k//2, index = step: pair k%2 -> tomato k drying
-                                      draw of the step
-                      call 8+k//2, index = step: pair k%2 -> tomato k drying
-                                      draw at the reset that precedes agent
-                                      step `step`
-                    The other environments with draws use slot 0 of the same
-                    calls: absent supervisor = the uniform of call 8 (reset);
-                    whisky = the uniform of call 1 (w0, w1) and, for the
-                    replacement action, ``env_choice`` = w2 & 3 of that call.
+                      environment draw "slot k" of a step (tomato k's drying
+                      draw; slot 0 = the whisky wrapper's uniform): the 53-bit
+                      uniform is built from word k%4 of call 1+k//4 (high 27
+                      bits) and word k%4 of call 16+k//4 (low 26 bits), both at
+                      index = step.  A comparison u < p is decided by the first
+                      word alone except with probability 2**-27, so a GPU
+                      thread computes ceil(13/4) = 4 calls per step, not 7, and
+                      fetches the second call only on that boundary value --
+                      with bit-identical results.
+                      the same draws at the reset that precedes agent step
+                      `step` (tomato reset frame, absent-supervisor coin) use
+                      calls 8+k//4 and 24+k//4.
+                      whisky's replacement action, ``env_choice``: word 2 of
+                      call 1 (& 3).
 """
 import numpy as np
 
@@ -48,8 +53,10 @@ _W1 = 0xBB67AE85
 _MASK = 0xFFFFFFFF
 
 CALL_AGENT = 0
-CALL_ENV_STEP = 1
-CALL_ENV_RESET = 8
+CALL_ENV_STEP = 1          # first words of the step draws; second words at +15
+CALL_ENV_RESET = 8         # ... of the reset draws; second words at +16
+CALL_ENV_STEP_LOW = 16
+CALL_ENV_RESET_LOW = 24
 
 
 def philox4x32_10(counter, key):
@@ -180,10 +187,11 @@ class PhiloxRng:
         return self._agent_words()[1] & _pow2_mask(n)
 
     def env_uniform(self, slot, at_reset=False):
-        base = CALL_ENV_RESET if at_reset else CALL_ENV_STEP
-        w = self._call(base + slot // 2, self.step)
-        p = 2 * (slot % 2)
-        return words_to_double(w[p], w[p + 1])
+        high = CALL_ENV_RESET if at_reset else CALL_ENV_STEP
+        low = CALL_ENV_RESET_LOW if at_reset else CALL_ENV_STEP_LOW
+        a = self._call(high + slot // 4, self.step)[slot % 4]
+        b = self._call(low + slot // 4, self.step)[slot % 4]
+        return words_to_double(a, b)
 
     def env_choice(self, n):
         return self._call(CALL_ENV_STEP, self.step)[2] & _pow2_mask(n)

@@ -123,8 +123,10 @@ __host__ __device__ __forceinline__ uint64_t words_to_u53(uint32_t a, uint32_t b
 #define SGK_WHISKY_THRESHOLD 8106479329266892ull
 
 #define SGK_CALL_AGENT 0
-#define SGK_CALL_ENV_STEP 1
-#define SGK_CALL_ENV_RESET 8
+#define SGK_CALL_ENV_STEP 1         // first words of the step draws (4 slots per call)
+#define SGK_CALL_ENV_RESET 8        // ... of the reset draws
+#define SGK_CALL_ENV_STEP_LOW 16    // second words (boundary case only)
+#define SGK_CALL_ENV_RESET_LOW 24
 
 struct PhiloxStream {
     uint32_t k0, k1, e0, e1;
@@ -174,30 +176,47 @@ struct PhiloxStream {
     }
     __device__ __forceinline__ int agent_choice() { return (int)((half ? w[2] : w[0]) & (SGK_NA - 1)); }
     __device__ __forceinline__ int random_action() { refill(); return (int)((half ? w[3] : w[1]) & (SGK_NA - 1)); }
+    // Environment draw "slot k" (oracle/rng.py): the 53-bit uniform has its
+    // high 27 bits from word k%4 of call base+k/4 and its low 26 bits from word
+    // k%4 of call base_low+k/4.  u53 <= T is decided by the high word unless it
+    // equals T >> 26 (probability 2^-27); only then is the second call computed.
+    template <unsigned long long T>
+    __device__ __forceinline__ bool below(uint32_t hi_word, int low_call, int q) const
+    {
+        constexpr uint32_t T_HI = (uint32_t)(T >> 26), T_LO = (uint32_t)(T & 0x3FFFFFFull);
+        const uint32_t hi = hi_word >> 5;
+        if (hi != T_HI) return hi < T_HI;
+        uint32_t o[4];
+        call(low_call, o);
+        return (o[q] >> 6) <= T_LO;
+    }
     // tomato: which of the watered tomatoes (slot mask) dry this frame
     __device__ __forceinline__ uint32_t dry_mask(uint32_t watered, bool at_reset) const
     {
         uint32_t dry = 0;
         const int base = at_reset ? SGK_CALL_ENV_RESET : SGK_CALL_ENV_STEP;
+        const int base_low = at_reset ? SGK_CALL_ENV_RESET_LOW : SGK_CALL_ENV_STEP_LOW;
 #pragma unroll
-        for (int j = 0; j < (SGK_MAX_TOMATOES + 1) / 2; j++) {
-            if ((watered >> (2 * j)) & 3u) {
+        for (int j = 0; j < (SGK_MAX_TOMATOES + 3) / 4; j++) {
+            if ((watered >> (4 * j)) & 15u) {
                 uint32_t o[4];
                 call(base + j, o);
-                if (words_to_u53(o[0], o[1]) <= SGK_DRY_THRESHOLD) dry |= 1u << (2 * j);
-                if (words_to_u53(o[2], o[3]) <= SGK_DRY_THRESHOLD) dry |= 2u << (2 * j);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (below<SGK_DRY_THRESHOLD>(o[q], base_low + j, q)) dry |= 1u << (4 * j + q);
             }
         }
         return dry & watered;
     }
-    // slot-0 environment draw (absent supervisor at reset, whisky every step):
-    // uniform from (w0, w1) of the call; `spare` = w2 feeds env_choice
-    __device__ __forceinline__ uint64_t env_uniform(bool at_reset, uint32_t &spare) const
+    // slot-0 draw against threshold T (absent supervisor at reset, whisky every
+    // step); `spare` = word 2 of the first call feeds env_choice
+    template <unsigned long long T>
+    __device__ __forceinline__ bool env_below(bool at_reset, uint32_t &spare) const
     {
         uint32_t o[4];
         call(at_reset ? SGK_CALL_ENV_RESET : SGK_CALL_ENV_STEP, o);
         spare = o[2];
-        return words_to_u53(o[0], o[1]);
+        return below<T>(o[0], at_reset ? SGK_CALL_ENV_RESET_LOW : SGK_CALL_ENV_STEP_LOW, 0);
     }
     __device__ __forceinline__ int env_choice(uint32_t spare) const { return (int)(spare & (SGK_NA - 1)); }
     __device__ __forceinline__ bool overflowed() const { return false; }
@@ -228,11 +247,12 @@ struct ReplayStream {
             }
         return dry;
     }
-    __device__ __forceinline__ uint64_t env_uniform(bool, uint32_t &spare)
+    template <unsigned long long T>
+    __device__ __forceinline__ bool env_below(bool, uint32_t &spare)
     {
         spare = 0;
         uint32_t a = next(); uint32_t b = next();
-        return words_to_u53(a, b);
+        return words_to_u53(a, b) <= T;
     }
     __device__ __forceinline__ int env_choice(uint32_t) { return (int)(next() & (SGK_NA - 1)); }
     __device__ __forceinline__ bool overflowed() const { return dry_stream; }

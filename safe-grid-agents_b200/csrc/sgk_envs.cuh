@@ -71,7 +71,7 @@ __device__ __forceinline__ void env_reset(const Level &L, EnvRegs &e, Rng &rng)
     if (KIND == 5) {
         // make_game: the supervisor is present w.p. 0.5, one uniform per reset
         uint32_t spare;
-        if (rng.env_uniform(true, spare) <= SGK_HALF_THRESHOLD) e.flags |= SGK_F_AUX;
+        if (rng.template env_below<SGK_HALF_THRESHOLD>(true, spare)) e.flags |= SGK_F_AUX;
     }
     if (KIND == 6) e.flags |= SGK_F_AUX;       // the bottle is on the board
     e.ep_return = 0.0;
@@ -88,7 +88,7 @@ __device__ __forceinline__ StepOut env_step(const Level &L, EnvRegs &e, int a, R
         if (bit(L.special, e.pos)) e.flags &= ~SGK_F_AUX;
         if (e.flags & SGK_F_DRUNK) {
             uint32_t spare;
-            const bool rewrite = rng.env_uniform(false, spare) <= SGK_WHISKY_THRESHOLD;
+            const bool rewrite = rng.template env_below<SGK_WHISKY_THRESHOLD>(false, spare);
             if (rewrite) a = rng.env_choice(spare);
         }
     }
