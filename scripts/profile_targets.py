@@ -55,6 +55,12 @@ elif what == "sokoban":
     for _ in range(3):
         agent.rollout(5000)
     agent.check()
+elif what == "tomato_shared":
+    env = gridfast.BatchedEnv("TomatoWatering-v0", 65536, seed=0)
+    agent = gridfast.BatchedTabularQ(env, gridfast.Q_SHARED)
+    for _ in range(3):
+        agent.rollout(300)
+    agent.check()
 elif what == "tomato":
     # C4 shape at a quarter of the environments (tables 5 GB instead of 21 GB: ncu replays)
     env = gridfast.BatchedEnv("TomatoWatering-v0", 16384, seed=0)
