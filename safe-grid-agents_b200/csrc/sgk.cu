@@ -527,10 +527,21 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             if (nkey != key) nslot = find_row_private(p.T, g, nkey, nrow, &status);
         }
         const int la = (KIND == 6 && p.cheat) ? o.actual : a;     // learn.py:74-78: the action really taken
-        const double upd = td_update(row_get(row, la), r, p.discount, p.lr, row_max(nrow));
-        if (DENSE) qs(slot, la) = upd;
-        else store_q(p.T, g, slot, la, upd);
-        row_set_if(nrow, nslot == slot, la, upd);
+        int next_greedy = 0;
+        if (DENSE) {
+            // one compare chain yields max Q(s', .) for the TD target AND the next
+            // greedy action; Q(s, a) comes from shared memory by index (no select
+            // tree), and the row is re-read only when the update hit it (s' == s)
+            double best;
+            next_greedy = argmax_first(nrow, best);
+            const double upd = td_update(qs(slot, la), r, p.discount, p.lr, best);
+            qs(slot, la) = upd;
+            if (nslot == slot) { nrow = row_s(nslot); next_greedy = argmax_first(nrow); }
+        } else {
+            const double upd = td_update(row_get(row, la), r, p.discount, p.lr, row_max(nrow));
+            store_q(p.T, g, slot, la, upd);
+            row_set_if(nrow, nslot == slot, la, upd);
+        }
         if (TRACE) th = trace_fold<KIND>(L, e, th, a, o);
         key = nkey; slot = nslot; row = nrow;
         if (o.done) {
@@ -545,11 +556,12 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             if (DENSE) {
                 slot = dense_slot(L.open32, e.pos);
                 row = row_s(slot);
+                next_greedy = argmax_first(row);
             } else if (lookup(p.T, g, key, slot)) {
                 row = load_row(p.T, g, slot);
             }
         }
-        greedy = argmax_first(row);
+        greedy = DENSE ? next_greedy : argmax_first(row);
         fresh = o.done;
     }
     if (DENSE) {

@@ -150,6 +150,16 @@ __device__ __forceinline__ int argmax_first(const QRow &r)
     return b;
 }
 
+// ... and the maximum itself (what learn bootstraps from, value.py:48-50)
+__device__ __forceinline__ int argmax_first(const QRow &r, double &m)
+{
+    int b = 0; m = r.v0;
+    if (r.v1 > m) { m = r.v1; b = 1; }
+    if (r.v2 > m) { m = r.v2; b = 2; }
+    if (r.v3 > m) { m = r.v3; b = 3; }
+    return b;
+}
+
 __device__ __forceinline__ double row_max(const QRow &r)
 {
     double m = r.v0;
