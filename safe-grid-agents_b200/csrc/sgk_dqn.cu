@@ -20,11 +20,23 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "sgk_internal.cuh"
 #include "sgk_mlp_tc.cuh"
 
 #define DQN_MAX_LAYERS 6   // linear layers
+
+// What changes from one lock-step to the next.  The direct path passes these by
+// value; the CUDA-graph path (sgk_rollout_dqn) uploads one entry per lock-step
+// up front and every replay of the captured graph reads entry `*cursor`.
+struct StepVars {
+    uint64_t step;             // agent step t
+    unsigned long long thr;    // explore threshold of step t
+    int64_t pos0;              // ring position the step's transitions are written at
+    int64_t fill;              // filled part of the ring when the step samples
+    float bc1, bc2_sqrt;       // Adam bias corrections of the step's update
+};
 
 // ===================================================================== object
 struct sgk_dqn {
@@ -56,6 +68,11 @@ struct sgk_dqn {
     int use_tc;                       // forward passes on tcgen05 (TF32) instead of fp32 FFMA
     uint8_t *xb, *xb2;                // uint8 copies of the staged batch (tensor-core input)
     int sm_count;
+    // graph replay of the lock-step: per-step variables on the device + cursor
+    StepVars *sv_table; int64_t sv_cap;
+    int *sv_cursor;
+    const StepVars *sv_use;           // non-null while a lock-step is being captured: kernels read sv_use[*sv_cursor]
+    cudaStream_t cap_stream;
 };
 
 static const int SPLITS = 256;   // upper bound of the batch splits of the weight-gradient GEMMs
@@ -244,10 +261,11 @@ __global__ void k_u8_to_f32(const uint8_t *in, float *out, int64_t n)
 __global__ void k_replay_sample(uint64_t seed, uint64_t step, int64_t fill, int64_t batch, int hw,
                                 const uint8_t *r_s, const uint8_t *r_s2, const uint8_t *r_a, const float *r_r,
                                 const uint8_t *r_term, float *x, float *x2, uint8_t *xb, uint8_t *xb2, uint8_t *b_a, float *b_r,
-                                uint8_t *b_term, int64_t *b_idx, int copy_boards)
+                                uint8_t *b_term, int64_t *b_idx, int copy_boards, const StepVars *sv, const int *cursor)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
+    if (sv) { step = sv[*cursor].step; fill = sv[*cursor].fill; }
     uint32_t w[4];
     philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)step, 0x40u | ((uint32_t)((step >> 32) & 0xFFFFFF) << 8),
                   (uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x5bd1e995u, w);
@@ -383,10 +401,11 @@ __global__ void __launch_bounds__(1024) k_grad_norm(const float *g, int64_t n, f
 // torch.optim.Adam(amsgrad=True) single-tensor update, defaults betas
 // (0.9, 0.999), eps 1e-8, no weight decay (value.py:87).
 __global__ void k_adam_amsgrad(float *p, const float *g, float *m, float *v, float *vmax, int64_t n, const float *scalars,
-                               float lr, float bc1, float bc2_sqrt)
+                               float lr, float bc1, float bc2_sqrt, const StepVars *sv, const int *cursor)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (sv) { bc1 = sv[*cursor].bc1; bc2_sqrt = sv[*cursor].bc2_sqrt; }
     const float grad = g[i] * scalars[2];
     const float mi = m[i] + (grad - m[i]) * (float)(1.0 - 0.9);    // exp_avg.lerp_(grad, 1 - beta1)
     const float vi = v[i] * 0.999f + (float)(1.0 - 0.999) * grad * grad;
@@ -424,6 +443,7 @@ struct DqnStepArgs {
     unsigned long long thr;
     int random_policy;
     int cheat;              // learn.py:39-47: store the hidden reward and the action really taken
+    const StepVars *sv; const int *cursor;     // graph replay: step, thr and pos0 come from sv[*cursor]
     int64_t cap, pos0;
     uint8_t *r_s, *r_s2, *r_a, *r_term;
     float *r_r;
@@ -439,9 +459,13 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_step(const __grid_constant__ 
     unpack_core(p.arr.core[i], e);
     e.ep_return = p.arr.ep_return[i];
     e.hidden_cum = p.arr.hidden_cum[i];
+    uint64_t step = p.step;
+    unsigned long long thr = p.thr;
+    int64_t pos0 = p.pos0;
+    if (p.sv) { const StepVars v = p.sv[*p.cursor]; step = v.step; thr = v.thr; pos0 = v.pos0; }
     Rng rng;
     RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
-    rng.set_step(p.step);
+    rng.set_step(step);
     int a;
     if (p.random_policy) {
         a = rng.random_action();
@@ -451,9 +475,9 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_step(const __grid_constant__ 
         if (q.y > m) { m = q.y; a = 1; }
         if (q.z > m) { m = q.z; a = 2; }
         if (q.w > m) { m = q.w; a = 3; }
-        if (rng.agent_uniform() < p.thr) a = rng.agent_choice();
+        if (rng.agent_uniform() < thr) a = rng.agent_choice();
     }
-    const int64_t slot = (p.pos0 + i) % p.cap;
+    const int64_t slot = (pos0 + i) % p.cap;
     uint8_t *s = p.r_s + slot * L.HW, *s2 = p.r_s2 + slot * L.HW;
     for (int c = 0; c < L.HW; c++) s[c] = render_cell<KIND>(L, e, c);
     const StepOut o = env_step<KIND>(L, e, a, rng);
@@ -466,7 +490,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_step(const __grid_constant__ 
         st.load(p.arr, i);
         st.episode_end(e, p.level.perf_is_return != 0);
         st.store(p.arr, i);
-        rng.set_step(p.step + 1);
+        rng.set_step(step + 1);
         env_reset<KIND>(L, e, rng);
     }
     RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
@@ -475,6 +499,10 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_step(const __grid_constant__ 
     p.arr.ep_return[i] = e.ep_return;
     p.arr.hidden_cum[i] = e.hidden_cum;
 }
+
+__global__ void k_advance_cursor(int *cursor) { *cursor += 1; }
+
+#define SGK_DQN_GRAPH_MIN_STEPS 16
 
 template <int KIND>
 __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_render_f32(const __grid_constant__ Level L, const uint64_t *core, int64_t n, float *x)
@@ -653,6 +681,9 @@ extern "C" int sgk_dqn_destroy(sgk_dqn *d)
                     d->b_idx, d->partials, d->q_env, d->boards_env, d->thr, d->status, d->xb, d->xb2, d->loss_partial};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < DQN_MAX_LAYERS; l++) { if (d->act[l]) cudaFree(d->act[l]); if (d->act_t[l]) cudaFree(d->act_t[l]); }
+    if (d->sv_table) cudaFree(d->sv_table);
+    if (d->sv_cursor) cudaFree(d->sv_cursor);
+    if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
     delete d;
     return SGK_OK;
 }
@@ -852,7 +883,8 @@ static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
     d->adam_step += 1;
     const double bc1 = 1.0 - pow(0.9, (double)d->adam_step), bc2 = 1.0 - pow(0.999, (double)d->adam_step);
     k_adam_amsgrad<<<grid_for(d->n_params, 256), 256, 0, st>>>(d->params[0], d->grads, d->adam_m, d->adam_v, d->adam_vmax,
-                                                               d->n_params, d->scalars, (float)d->lr, (float)bc1, (float)sqrt(bc2));
+                                                               d->n_params, d->scalars, (float)d->lr, (float)bc1, (float)sqrt(bc2),
+                                                               d->sv_use, d->sv_cursor);
     if ((rc = launch_check("k_adam_amsgrad"))) return rc;
     if (loss_out) CU(cudaMemcpyAsync(loss_out, d->scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return SGK_OK;
@@ -887,7 +919,8 @@ extern "C" int sgk_dqn_learn(sgk_dqn *d, uint64_t step, float *loss_out, void *s
     int rc = ensure_rows(d, B);
     if (rc != SGK_OK) return rc;
     k_replay_sample<<<grid_for(B, 128), 128, 0, st>>>(d->seed, step, fill, B, d->hw, d->r_s, d->r_s2, d->r_a, d->r_r, d->r_term,
-                                                      d->x, d->x2, d->xb, d->xb2, d->b_a, d->b_r, d->b_term, d->b_idx, (d->hw & 3) != 0);
+                                                      d->x, d->x2, d->xb, d->xb2, d->b_a, d->b_r, d->b_term, d->b_idx, (d->hw & 3) != 0,
+                                                      d->sv_use, d->sv_cursor);
     if ((d->hw & 3) == 0) {
         const int words = d->hw / 4;
         k_replay_gather_words<<<grid_for(B * words, 256), 256, 0, st>>>(
@@ -917,13 +950,24 @@ extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64
         d->env_rows = env->n;
     }
     const bool replay = env->rng_mode == SGK_RNG_REPLAY;
-    for (int64_t k = 0; k < n_steps; k++) {
-        const uint64_t t = t0 + (uint64_t)k;
+    // epsilon of agent-step t: DeepQAgent keeps entry 0 (value.py:72-76)
+    auto threshold_at = [&](uint64_t t) -> unsigned long long {
+        const int64_t last = d->anneal > 1 ? d->anneal - 1 : 0;
+        const int64_t idx = (int64_t)t < last ? (int64_t)t : last;
+        const volatile double scaled = (1 - d->epsilon) * (double)idx;
+        const volatile double frac = scaled / (double)d->anneal;
+        const double eps = 1.0 - frac;
+        return eps <= 0.0 ? 0ull : (unsigned long long)ceil(eps * 9007199254740992.0);
+    };
+    // one lock-step enqueued on `st`; host bookkeeping (ring count, Adam step) advances with it
+    auto lockstep = [&](uint64_t t, cudaStream_t st) -> int {
+        int rc;
         DqnStepArgs a;
         a.level = env->level; a.arr = env->arr; a.n = env->n; a.env_id0 = env->env_id0; a.seed = env->seed; a.step = t;
         a.words = env->replay_words; a.wpe = env->words_per_env; a.status = env->status;
         a.random_policy = learn ? 0 : 1;
         a.cheat = (mode & SGK_DQN_CHEAT) ? 1 : 0;
+        a.sv = d->sv_use; a.cursor = d->sv_cursor;
         a.cap = d->cap; a.pos0 = d->count % d->cap;
         a.r_s = d->r_s; a.r_s2 = d->r_s2; a.r_a = d->r_a; a.r_term = d->r_term; a.r_r = d->r_r;
         a.q = d->q_env; a.thr = 0;
@@ -943,13 +987,7 @@ extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64
                 if ((rc = forward(d, 0, d->x, env->n, d->act, st))) return rc;
                 CU(cudaMemcpyAsync(d->q_env, d->act[d->n_linear - 1], (size_t)env->n * d->n_actions * 4, cudaMemcpyDeviceToDevice, st));
             }
-            // epsilon of this agent-step: DeepQAgent keeps entry 0 (value.py:72-76)
-            const int64_t last = d->anneal > 1 ? d->anneal - 1 : 0;
-            const int64_t idx = (int64_t)t < last ? (int64_t)t : last;
-            const volatile double scaled = (1 - d->epsilon) * (double)idx;
-            const volatile double frac = scaled / (double)d->anneal;
-            const double eps = 1.0 - frac;
-            a.thr = eps <= 0.0 ? 0ull : (unsigned long long)ceil(eps * 9007199254740992.0);
+            a.thr = threshold_at(t);
         }
         rc = by_kind(env->level.kind, [&](auto K) {
             constexpr int KIND = decltype(K)::value;
@@ -959,11 +997,81 @@ extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64
         });
         if (rc != SGK_OK) return rc;
         d->count += env->n;
-        if (learn) {
-            if ((rc = sgk_dqn_learn(d, t, nullptr, stream))) return rc;
-            if (t % (uint64_t)d->sync_every == (uint64_t)d->sync_every - 1)   // learn.py:55-56
-                if ((rc = sgk_dqn_sync_target(d, stream))) return rc;
+        if (learn && (rc = sgk_dqn_learn(d, t, nullptr, st))) return rc;
+        return SGK_OK;
+    };
+    auto sync_if_due = [&](uint64_t t) -> int {
+        if (learn && t % (uint64_t)d->sync_every == (uint64_t)d->sync_every - 1)   // learn.py:55-56
+            return sgk_dqn_sync_target(d, stream);
+        return SGK_OK;
+    };
+
+    // Long learning rollouts replay ONE captured CUDA graph of the lock-step
+    // (about 20 kernels) instead of enqueueing every kernel again: the host
+    // cost per lock-step drops from ~160 us of launches to one graph launch.
+    // Per-step scalars are uploaded once and indexed by a device cursor.
+    int64_t k = 0;
+    const bool use_graph = learn && n_steps >= SGK_DQN_GRAPH_MIN_STEPS && getenv("SGK_DQN_NO_GRAPH") == nullptr;
+    if (use_graph) {
+        // first lock-step directly: settles every lazy allocation outside the capture
+        if ((rc = lockstep(t0, st))) return rc;
+        if ((rc = sync_if_due(t0))) return rc;
+        k = 1;
+        const int64_t m = n_steps - 1;
+        if (d->sv_cap < m) {
+            if (d->sv_table) cudaFree(d->sv_table);
+            d->sv_table = nullptr; d->sv_cap = 0;
+            CU(cudaMalloc(&d->sv_table, (size_t)m * sizeof(StepVars)));
+            d->sv_cap = m;
         }
+        if (!d->sv_cursor) CU(cudaMalloc(&d->sv_cursor, sizeof(int)));
+        if (!d->cap_stream) CU(cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking));
+        std::vector<StepVars> host((size_t)m);
+        for (int64_t j = 0; j < m; j++) {
+            StepVars &v = host[(size_t)j];
+            const int64_t count_before = d->count + j * env->n, count_after = count_before + env->n;
+            const int64_t adam = d->adam_step + j + 1;
+            v.step = t0 + (uint64_t)(j + 1);
+            v.thr = threshold_at(v.step);
+            v.pos0 = count_before % d->cap;
+            v.fill = count_after < d->cap ? count_after : d->cap;
+            v.bc1 = (float)(1.0 - pow(0.9, (double)adam));
+            v.bc2_sqrt = (float)sqrt(1.0 - pow(0.999, (double)adam));
+        }
+        CU(cudaMemcpyAsync(d->sv_table, host.data(), (size_t)m * sizeof(StepVars), cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(d->sv_cursor, 0, sizeof(int), st));
+        CU(cudaStreamSynchronize(st));            // `host` goes out of scope; the capture below is on another stream
+        // capture one lock-step reading sv_table[*sv_cursor]
+        const int64_t count0 = d->count, adam0 = d->adam_step;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        d->sv_use = d->sv_table;
+        CU(cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeRelaxed));
+        rc = lockstep(t0 + 1, d->cap_stream);
+        if (rc == SGK_OK) k_advance_cursor<<<1, 1, 0, d->cap_stream>>>(d->sv_cursor);
+        const cudaError_t end = cudaStreamEndCapture(d->cap_stream, &graph);
+        d->sv_use = nullptr;
+        d->count = count0; d->adam_step = adam0;      // the capture enqueued nothing
+        if (rc != SGK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (end != cudaSuccess) return fail(SGK_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(end));
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            cudaGraphDestroy(graph);
+            return fail(SGK_ECUDA, "cudaGraphInstantiate failed for the deep-Q lock-step");
+        }
+        for (; k < n_steps; k++) {
+            if (cudaGraphLaunch(exec, st) != cudaSuccess) { rc = fail(SGK_ECUDA, "cudaGraphLaunch failed"); break; }
+            d->count += env->n;
+            d->adam_step += 1;
+            if ((rc = sync_if_due(t0 + (uint64_t)k))) break;
+        }
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        return rc;
+    }
+    for (; k < n_steps; k++) {
+        const uint64_t t = t0 + (uint64_t)k;
+        if ((rc = lockstep(t, st))) return rc;
+        if ((rc = sync_if_due(t))) return rc;
     }
     return SGK_OK;
 }

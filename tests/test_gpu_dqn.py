@@ -136,6 +136,36 @@ def test_rollout_cheat_stores_hidden_reward_and_actual_action(env_id):
     assert not np.array_equal(r0, r1)
 
 
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_graph_replayed_lockstep_equals_direct_launches(use_tc):
+    """Rollouts of >= 16 lock-steps replay one captured CUDA graph whose
+    per-step scalars (step, epsilon threshold, ring position, ring fill, Adam
+    bias corrections) come from a device table; shorter calls launch every
+    kernel directly.  Both must produce the same network, ring and statistics,
+    bit for bit -- across a ring wrap and several target syncs."""
+    import gridfast
+    n, T = 256, 48
+    out = {}
+    for label, chunks in (("graph", [T]), ("direct", [8] * (T // 8))):
+        env = gridfast.BatchedEnv("SideEffectsSokoban-v0", n, seed=3)
+        agent = gridfast.BatchedDeepQ(env, replay_capacity=n * 20, batch_size=512, lr=1e-3, epsilon=0.05,
+                                      epsilon_anneal=30, sync_every=7, seed=5)
+        agent.set_tensor_cores(use_tc)
+        agent.warmup(10)
+        for c in chunks:
+            agent.rollout(c)
+        ring = [x.cpu().numpy() for x in agent.replay_rows(0, n * 20)]
+        out[label] = (agent.get_params(0).cpu().numpy(), agent.get_params(1).cpu().numpy(), ring,
+                      {k: v.cpu().numpy() for k, v in env.stats().items()}, env.render().cpu().numpy())
+    g, d = out["graph"], out["direct"]
+    assert np.array_equal(g[0], d[0]) and np.array_equal(g[1], d[1])
+    for a, b in zip(g[2], d[2]):
+        assert np.array_equal(a, b)
+    for k in g[3]:
+        assert np.array_equal(g[3][k], d[3][k], equal_nan=True), k
+    assert np.array_equal(g[4], d[4])
+
+
 def _train_and_score(agent, env, train_steps=1500, score_steps=300):
     agent.warmup(40)
     base = env.totals()
