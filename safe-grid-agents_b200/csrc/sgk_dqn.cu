@@ -73,6 +73,10 @@ struct sgk_dqn {
     int *sv_cursor;
     const StepVars *sv_use;           // non-null while a lock-step is being captured: kernels read sv_use[*sv_cursor]
     cudaStream_t cap_stream;
+    // tensor-core path: weights pre-packed into the kernels' shared-memory operand layout
+    uint8_t *w_image[2];              // forward image of Q / target_Q
+    uint8_t *w_image_bwd;             // W3^T | W2^T of Q
+    int w_image_dirty[2];             // parameters changed since the image was packed
 };
 
 static const int SPLITS = 256;   // upper bound of the batch splits of the weight-gradient GEMMs
@@ -600,6 +604,26 @@ static bool tc_supported(const sgk_dqn *d)
            d->n_actions <= 8;
 }
 
+// (re)pack network `which` into the operand images if its parameters changed
+static int ensure_packed(sgk_dqn *d, int which, cudaStream_t st)
+{
+    if (!d->w_image[which]) {
+        CU(cudaMalloc(&d->w_image[which], tc::FWD_IMAGE_BYTES));
+        CU(cudaMemsetAsync(d->w_image[which], 0, tc::FWD_IMAGE_BYTES, st));
+        d->w_image_dirty[which] = 1;
+    }
+    if (which == 0 && !d->w_image_bwd) {
+        CU(cudaMalloc(&d->w_image_bwd, tc::BWD_IMAGE_BYTES));
+        d->w_image_dirty[0] = 1;
+    }
+    if (!d->w_image_dirty[which]) return SGK_OK;
+    const float *P = d->params[which];
+    tc::k_pack_weights<<<which == 0 ? 5 : 3, 256, 0, st>>>(P + d->w_off[0], P + d->w_off[1], P + d->w_off[2], d->dims[0], d->dims[1],
+                                                         d->n_actions, d->w_image[which], which == 0 ? d->w_image_bwd : nullptr);
+    d->w_image_dirty[which] = 0;
+    return launch_check("k_pack_weights");
+}
+
 // the fused tensor-core forward: boards (uint8) -> Q, optionally H1 / H2 in fp32
 static int forward_tc(sgk_dqn *d, int which, const uint8_t *boards, int64_t rows, float *q_out, float *h1, float *h2,
                       cudaStream_t st)
@@ -609,7 +633,10 @@ static int forward_tc(sgk_dqn *d, int which, const uint8_t *boards, int64_t rows
         CU(cudaFuncSetAttribute(tc::k_mlp_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem::TOTAL));
         attr_set = true;
     }
+    int prc = ensure_packed(d, which, st);
+    if (prc != SGK_OK) return prc;
     tc::Params p;
+    p.w_image = d->w_image[which];
     const float *P = d->params[which];
     p.w1 = P + d->w_off[0]; p.b1 = P + d->b_off[0];
     p.w2 = P + d->w_off[1]; p.b2 = P + d->b_off[1];
@@ -640,6 +667,9 @@ static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
     tc::BwdParams bp;
     bp.w2 = P0 + d->w_off[1]; bp.w3 = P0 + d->w_off[2]; bp.n_hidden = H; bp.n_out = A;
     bp.dq = dq; bp.h1 = d->act[0]; bp.h2 = d->act[1]; bp.dh1 = dh1; bp.dh2 = dh2; bp.rows = B;
+    int prc = ensure_packed(d, 0, st);
+    if (prc != SGK_OK) return prc;
+    bp.w_image = d->w_image_bwd;
     // 107 KB of shared memory and 256 TMEM columns per CTA: two CTAs fit on an SM,
     // so one CTA's epilogue overlaps the other's MMAs
     const unsigned grid_bwd = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)d->sm_count);
@@ -681,6 +711,7 @@ extern "C" int sgk_dqn_destroy(sgk_dqn *d)
                     d->b_idx, d->partials, d->q_env, d->boards_env, d->thr, d->status, d->xb, d->xb2, d->loss_partial};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < DQN_MAX_LAYERS; l++) { if (d->act[l]) cudaFree(d->act[l]); if (d->act_t[l]) cudaFree(d->act_t[l]); }
+    for (uint8_t *img : {d->w_image[0], d->w_image[1], d->w_image_bwd}) if (img) cudaFree(img);
     if (d->sv_table) cudaFree(d->sv_table);
     if (d->sv_cursor) cudaFree(d->sv_cursor);
     if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
@@ -767,6 +798,7 @@ extern "C" int sgk_dqn_set_params(sgk_dqn *d, int which, const float *in, void *
     REQUIRE(d != nullptr && in != nullptr && (which == 0 || which == 1), "bad argument");
     DeviceGuard g(d->device);
     CU(cudaMemcpyAsync(d->params[which], in, (size_t)d->n_params * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    d->w_image_dirty[which] = 1;
     return SGK_OK;
 }
 
@@ -783,6 +815,9 @@ extern "C" int sgk_dqn_sync_target(sgk_dqn *d, void *stream)
     REQUIRE(d != nullptr, "d is NULL");
     DeviceGuard g(d->device);
     CU(cudaMemcpyAsync(d->params[1], d->params[0], (size_t)d->n_params * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    d->w_image_dirty[1] = 1;
+    // re-pack right away: the target image must never be stale inside a captured lock-step
+    if (d->use_tc) return ensure_packed(d, 1, (cudaStream_t)stream);
     return SGK_OK;
 }
 
@@ -885,6 +920,7 @@ static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
     k_adam_amsgrad<<<grid_for(d->n_params, 256), 256, 0, st>>>(d->params[0], d->grads, d->adam_m, d->adam_v, d->adam_vmax,
                                                                d->n_params, d->scalars, (float)d->lr, (float)bc1, (float)sqrt(bc2),
                                                                d->sv_use, d->sv_cursor);
+    d->w_image_dirty[0] = 1;
     if ((rc = launch_check("k_adam_amsgrad"))) return rc;
     if (loss_out) CU(cudaMemcpyAsync(loss_out, d->scalars, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return SGK_OK;
@@ -1054,12 +1090,14 @@ extern "C" int sgk_rollout_dqn(sgk_env *env, sgk_dqn *d, int64_t n_steps, uint64
         d->count = count0; d->adam_step = adam0;      // the capture enqueued nothing
         if (rc != SGK_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (end != cudaSuccess) return fail(SGK_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(end));
-        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        if (ie != cudaSuccess) {
             cudaGraphDestroy(graph);
-            return fail(SGK_ECUDA, "cudaGraphInstantiate failed for the deep-Q lock-step");
+            return fail(SGK_ECUDA, std::string("cudaGraphInstantiate (deep-Q lock-step): ") + cudaGetErrorString(ie));
         }
         for (; k < n_steps; k++) {
-            if (cudaGraphLaunch(exec, st) != cudaSuccess) { rc = fail(SGK_ECUDA, "cudaGraphLaunch failed"); break; }
+            const cudaError_t le = cudaGraphLaunch(exec, st);
+            if (le != cudaSuccess) { rc = fail(SGK_ECUDA, std::string("cudaGraphLaunch: ") + cudaGetErrorString(le)); break; }
             d->count += env->n;
             d->adam_step += 1;
             if ((rc = sync_if_due(t0 + (uint64_t)k))) break;

@@ -43,6 +43,7 @@ struct Params {
     int64_t rows;
     float *q_out;                               // [rows][n_out]
     float *h1_out, *h2_out;                     // [rows][n_hidden] or null
+    const uint8_t *w_image;                     // W1|W2|W3 already in the shared-memory operand layout (k_pack_weights), or null
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,6 +106,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity)
         :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
 }
 
+// One TMA bulk copy global -> shared (cp.async.bulk, no tensor map: the image is
+// contiguous), completion signalled on `mbar` as a byte count.  Issued by ONE
+// thread; `bytes` % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -134,6 +145,8 @@ struct Smem {
     static constexpr int BAR = BIAS + (2 * N_HID + N_OUT) * 4;
     static constexpr int TOTAL = BAR + 16;
 };
+
+constexpr uint32_t FWD_IMAGE_BYTES = Smem::X;    // W1 | W2 | W3 regions, contiguous from offset 0
 
 // W[out][in] (global, row-major) -> chunk-major TF32 operand with `rows_pad`
 // rows and `k_pad` columns, zero padded.  Consecutive threads take consecutive
@@ -219,9 +232,19 @@ __global__ void __launch_bounds__(TILE_M, 1) k_mlp_forward_tc(const Params p)
     const int k_in = (p.n_in + 7) & ~7;             // 36 -> 40, 25 -> 32, 63 -> 64
 
     // ---- one-time setup: weights, biases, barrier, TMEM
-    stage_weights(smem + Smem::W1, p.w1, p.n_hidden, p.n_in, N_HID, k_in);
-    stage_weights(smem + Smem::W2, p.w2, p.n_hidden, p.n_hidden, N_HID, K_HID);
-    stage_weights(smem + Smem::W3, p.w3, p.n_out, p.n_hidden, N_OUT, K_HID);
+    uint64_t *mbar_w = mbar + 1;                    // completion of the weight image's bulk copy
+    if (p.w_image) {
+        // the three matrices arrive as ONE TMA bulk copy of their pre-packed image
+        if (threadIdx.x == 0) {
+            mbar_init(mbar_w, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            bulk_load(smem + Smem::W1, p.w_image, FWD_IMAGE_BYTES, mbar_w);
+        }
+    } else {
+        stage_weights(smem + Smem::W1, p.w1, p.n_hidden, p.n_in, N_HID, k_in);
+        stage_weights(smem + Smem::W2, p.w2, p.n_hidden, p.n_hidden, N_HID, K_HID);
+        stage_weights(smem + Smem::W3, p.w3, p.n_out, p.n_hidden, N_OUT, K_HID);
+    }
     for (int i = threadIdx.x; i < 2 * N_HID + N_OUT; i += blockDim.x) {
         float b = 0.f;
         if (i < N_HID) b = i < p.n_hidden ? p.b1[i] : 0.f;
@@ -242,6 +265,7 @@ __global__ void __launch_bounds__(TILE_M, 1) k_mlp_forward_tc(const Params p)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.w_image) mbar_wait(mbar_w, 0);
     const uint32_t tmem = tmem_base_slot;
     const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 lanes
     const uint32_t d1 = tmem, d2 = tmem + 128, d3 = tmem;
@@ -348,6 +372,7 @@ struct BwdParams {
     const float *h1, *h2;          // [rows][n_hidden], post-ReLU
     float *dh1, *dh2;              // [rows][n_hidden]
     int64_t rows;
+    const uint8_t *w_image;        // W3^T|W2^T already in the operand layout, or null
 };
 
 struct SmemBwd {
@@ -358,6 +383,8 @@ struct SmemBwd {
     static constexpr int BAR = DH + (K_HID / 4) * Smem::CHUNK_A;
     static constexpr int TOTAL = BAR + 16;
 };
+
+constexpr uint32_t BWD_IMAGE_BYTES = SmemBwd::DQ;    // W3^T | W2^T regions, contiguous from offset 0
 
 // B operand holding W^T: row r = input index (< n_in), K index = output index (< n_out)
 __device__ __forceinline__ void stage_weights_T(uint8_t *dst, const float *w, int n_out, int n_in, int rows_pad, int k_pad)
@@ -400,13 +427,19 @@ __global__ void __launch_bounds__(TILE_M, 1) k_mlp_backward_data_tc(const BwdPar
     __shared__ uint32_t tmem_base_slot;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + SmemBwd::BAR);
     const int warp = threadIdx.x >> 5;
-    stage_weights_T(smem + SmemBwd::W3T, p.w3, p.n_out, p.n_hidden, N_HID, 8);
-    stage_weights_T(smem + SmemBwd::W2T, p.w2, p.n_hidden, p.n_hidden, N_HID, K_HID);
+    uint64_t *mbar_w = mbar + 1;
+    if (!p.w_image) {
+        stage_weights_T(smem + SmemBwd::W3T, p.w3, p.n_out, p.n_hidden, N_HID, 8);
+        stage_weights_T(smem + SmemBwd::W2T, p.w2, p.n_hidden, p.n_hidden, N_HID, K_HID);
+    }
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
+        mbar_init(mbar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (p.w_image) bulk_load(smem + SmemBwd::W3T, p.w_image, BWD_IMAGE_BYTES, mbar_w);
     }
     const uint32_t tmem = tmem_alloc_and_sync(&tmem_base_slot, warp, 256);
+    if (p.w_image) mbar_wait(mbar_w, 0);
     const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t d0 = tmem, d1 = tmem + 128;
     const uint32_t a_dq = smem_u32(smem + SmemBwd::DQ), a_dh = smem_u32(smem + SmemBwd::DH);
@@ -648,6 +681,22 @@ k_wgrad_finish(const float *partial, int n_partials, int npad, int mdim, int ndi
         for (int l = 0; l < WGF_LANES; l++) s += part[l][e];
         if (n < ndim) dW[(size_t)m * ndim + n] = s;
         else if (db) db[m] = s;
+    }
+}
+
+// Weights -> operand images in global memory, once per parameter update; the
+// MLP kernels then fetch an image with one bulk copy instead of re-staging the
+// matrices in every CTA.  Block b packs one matrix.
+__global__ void __launch_bounds__(256) k_pack_weights(const float *w1, const float *w2, const float *w3, int n_in, int n_hidden,
+                                                      int n_out, uint8_t *fwd_image, uint8_t *bwd_image)
+{
+    const int k_in = (n_in + 7) & ~7;
+    switch (blockIdx.x) {
+    case 0: stage_weights(fwd_image + Smem::W1, w1, n_hidden, n_in, N_HID, k_in); break;
+    case 1: stage_weights(fwd_image + Smem::W2, w2, n_hidden, n_hidden, N_HID, K_HID); break;
+    case 2: stage_weights(fwd_image + Smem::W3, w3, n_out, n_hidden, N_OUT, K_HID); break;
+    case 3: if (bwd_image) stage_weights_T(bwd_image + SmemBwd::W3T, w3, n_out, n_hidden, N_HID, 8); break;
+    default: if (bwd_image) stage_weights_T(bwd_image + SmemBwd::W2T, w2, n_hidden, n_hidden, N_HID, K_HID); break;
     }
 }
 
