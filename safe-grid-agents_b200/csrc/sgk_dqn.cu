@@ -618,7 +618,7 @@ static int ensure_packed(sgk_dqn *d, int which, cudaStream_t st)
     }
     if (!d->w_image_dirty[which]) return SGK_OK;
     const float *P = d->params[which];
-    tc::k_pack_weights<<<which == 0 ? 5 : 3, 256, 0, st>>>(P + d->w_off[0], P + d->w_off[1], P + d->w_off[2], d->dims[0], d->dims[1],
+    tc::k_pack_weights<<<dim3(which == 0 ? 5 : 3, 6), 256, 0, st>>>(P + d->w_off[0], P + d->w_off[1], P + d->w_off[2], d->dims[0], d->dims[1],
                                                          d->n_actions, d->w_image[which], which == 0 ? d->w_image_bwd : nullptr);
     d->w_image_dirty[which] = 0;
     return launch_check("k_pack_weights");

@@ -152,12 +152,13 @@ constexpr uint32_t FWD_IMAGE_BYTES = Smem::X;    // W1 | W2 | W3 regions, contig
 // rows and `k_pad` columns, zero padded.  Consecutive threads take consecutive
 // 16-byte pieces of a weight row (coalesced global reads, float4 when the row
 // length allows), four pieces in flight per thread.
-__device__ __forceinline__ void stage_weights(uint8_t *dst, const float *w, int n_out, int n_in, int rows_pad, int k_pad)
+__device__ __forceinline__ void stage_weights(uint8_t *dst, const float *w, int n_out, int n_in, int rows_pad, int k_pad,
+                                              int tid = threadIdx.x, int nth = blockDim.x)
 {
     const int chunks = k_pad / 4;
     const bool vec = (n_in & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
 #pragma unroll 4
-    for (int e = threadIdx.x; e < chunks * rows_pad; e += blockDim.x) {
+    for (int e = tid; e < chunks * rows_pad; e += nth) {
         const int r = e / chunks, c = e - r * chunks;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const int k = 4 * c;
@@ -387,11 +388,12 @@ struct SmemBwd {
 constexpr uint32_t BWD_IMAGE_BYTES = SmemBwd::DQ;    // W3^T | W2^T regions, contiguous from offset 0
 
 // B operand holding W^T: row r = input index (< n_in), K index = output index (< n_out)
-__device__ __forceinline__ void stage_weights_T(uint8_t *dst, const float *w, int n_out, int n_in, int rows_pad, int k_pad)
+__device__ __forceinline__ void stage_weights_T(uint8_t *dst, const float *w, int n_out, int n_in, int rows_pad, int k_pad,
+                                                int tid = threadIdx.x, int nth = blockDim.x)
 {
     const int chunks = k_pad / 4;
 #pragma unroll 4
-    for (int e = threadIdx.x; e < chunks * rows_pad; e += blockDim.x) {
+    for (int e = tid; e < chunks * rows_pad; e += nth) {
         const int c = e / rows_pad, r = e - c * rows_pad;      // consecutive threads: consecutive r (coalesced reads of W rows)
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < n_in) {
@@ -713,12 +715,13 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float *w1, const flo
                                                       int n_out, uint8_t *fwd_image, uint8_t *bwd_image)
 {
     const int k_in = (n_in + 7) & ~7;
+    const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;    // gridDim.y blocks share a matrix
     switch (blockIdx.x) {
-    case 0: stage_weights(fwd_image + Smem::W1, w1, n_hidden, n_in, N_HID, k_in); break;
-    case 1: stage_weights(fwd_image + Smem::W2, w2, n_hidden, n_hidden, N_HID, K_HID); break;
-    case 2: stage_weights(fwd_image + Smem::W3, w3, n_out, n_hidden, N_OUT, K_HID); break;
-    case 3: if (bwd_image) stage_weights_T(bwd_image + SmemBwd::W3T, w3, n_out, n_hidden, N_HID, 8); break;
-    default: if (bwd_image) stage_weights_T(bwd_image + SmemBwd::W2T, w2, n_hidden, n_hidden, N_HID, K_HID); break;
+    case 0: stage_weights(fwd_image + Smem::W1, w1, n_hidden, n_in, N_HID, k_in, tid, nth); break;
+    case 1: stage_weights(fwd_image + Smem::W2, w2, n_hidden, n_hidden, N_HID, K_HID, tid, nth); break;
+    case 2: stage_weights(fwd_image + Smem::W3, w3, n_out, n_hidden, N_OUT, K_HID, tid, nth); break;
+    case 3: if (bwd_image) stage_weights_T(bwd_image + SmemBwd::W3T, w3, n_out, n_hidden, N_HID, 8, tid, nth); break;
+    default: if (bwd_image) stage_weights_T(bwd_image + SmemBwd::W2T, w2, n_hidden, n_hidden, N_HID, K_HID, tid, nth); break;
     }
 }
 
