@@ -47,3 +47,29 @@ def test_epsilon_schedule_matches_list_popping():
             if future:
                 cur = future.pop(0)
             sched.advance()
+
+
+def test_environment_draw_layout_high_and_low_words_from_separate_calls():
+    """Slot k of a step: high 27 bits from word k%4 of call 1+k//4, low 26 bits
+    from word k%4 of call 16+k//4 (8+k//4 / 24+k//4 at a reset); the choice
+    word of the whisky wrapper is word 2 of call 1."""
+    seed, env_id, step = 0x1234_5678_9ABC_DEF0, 77, 4242
+    stream = rng.PhiloxRng(seed, env_id=env_id)
+    stream.set_context(env_id, step)
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+
+    def call(c):
+        return rng.philox4x32_10((env_id, 0, step, c), key)
+
+    for slot in range(13):
+        for at_reset, hi, lo in ((False, 1, 16), (True, 8, 24)):
+            a = call(hi + slot // 4)[slot % 4]
+            b = call(lo + slot // 4)[slot % 4]
+            assert stream.env_uniform(slot, at_reset) == rng.words_to_double(a, b)
+    assert stream.env_choice(4) == call(1)[2] & 3
+    # the decision u < p needs the low word only when the high 27 bits sit on the threshold
+    t = 450359962737049                       # u < 0.05  <=>  u53 <= t
+    for hi27, lo26, expect in ((t >> 26) - 1, 0x3FFFFFF, True), ((t >> 26) + 1, 0, False), \
+                              (t >> 26, t & 0x3FFFFFF, True), (t >> 26, (t & 0x3FFFFFF) + 1, False):
+        u = ((hi27 << 26) | lo26) / 2.0 ** 53
+        assert (u < 0.05) == expect
