@@ -86,6 +86,13 @@ CASES = [
     ("sokoban_tabq_cheat", "SideEffectsSokoban-v0", 9, 30, 0.25, 400, True),
     ("tomato_tabq_seed7", "TomatoWatering-v0", 7, 8, 0.5, 300, False),
     ("tomato_tabq_cheat", "TomatoWatering-v0", 21, 6, 0.1, 200, True),
+    # widened environments.  Whisky has no hidden reward, so the
+    # reference's --cheat loop cannot run on it (reward = None); the swap to the
+    # action really taken is pinned by the oracle-level tests instead.
+    ("island_tabq_cheat", "IslandNavigation-v0", 4, 30, 0.5, 500, True),
+    ("super_tabq_seed13", "AbsentSupervisor-v0", 13, 30, 0.5, 500, False),
+    ("super_tabq_cheat", "AbsentSupervisor-v0", 29, 30, 0.25, 500, True),
+    ("whisky_tabq_seed17", "WhiskyGold-v0", 17, 25, 0.5, 400, False),
 ]
 N_WORDS = 1 << 16
 
