@@ -196,6 +196,11 @@ int sgk_tabq_learn(sgk_tabq *q, const uint8_t *boards, const uint8_t *actions, c
 
 /* Lossless key of a board (what the table stores); device [n][H*W] -> [n]. */
 int sgk_board_to_key(const sgk_env *env, const uint8_t *boards, uint64_t *keys_out, int64_t n, void *stream);
+/* ... and back: the board a key stands for, i.e. the reference's dict key
+ * tuple(board.flatten()) (value.py:34) of a table entry.  device [n] -> [n][H*W]. */
+int sgk_key_to_board(const sgk_env *env, const uint64_t *keys, uint8_t *boards_out, int64_t n, void *stream);
+/* Frames per episode before the time limit ends it (safety_game max_iterations). */
+int sgk_env_max_iterations(const sgk_env *env);
 
 /* Dump table `table`: keys_out [capacity] (0 = empty slot), q_out
  * [capacity][4], corruption_out [capacity] or NULL; device pointers. */
@@ -203,6 +208,18 @@ int sgk_tabq_export(const sgk_tabq *q, int64_t table, uint64_t *keys_out, double
                     double *corruption_out, void *stream);
 /* Overwrite table `table` from the same layout (host-side merge / restore). */
 int sgk_tabq_import(sgk_tabq *q, int64_t table, const uint64_t *keys, const double *qrows, void *stream);
+
+/* The reference's dict never fills (value.py:31).  Hashed private tables
+ * therefore grow on demand: sgk_tabq_act / _learn / sgk_rollout_tabq* measure
+ * the fullest table when their bound on its key count nears the capacity and
+ * rehash every table into twice the capacity (host-side, synchronises, rare).
+ * sgk_tabq_set_auto_grow(q, 0) pins the capacity: an overflowing table then
+ * drops the update, treats the state as unseen and raises SGK_EFULL at the
+ * next sgk_check / *_host call.  sgk_tabq_max_fill: key count of the fullest
+ * table (synchronises); sgk_tabq_grow: explicit rehash to `new_capacity`. */
+int sgk_tabq_set_auto_grow(sgk_tabq *q, int enabled);
+int sgk_tabq_max_fill(sgk_tabq *q, int64_t *max_fill_out, void *stream);
+int sgk_tabq_grow(sgk_tabq *q, int64_t new_capacity, void *stream);
 
 /* Replica sync for shared tables on several GPUs: every
  * GPU keeps a replica; at a sync point each exports its change since the last
@@ -214,6 +231,17 @@ int sgk_tabq_delta_export(sgk_tabq *q, uint64_t *keys_out, double *delta_out, vo
 int sgk_tabq_delta_apply(sgk_tabq *q, const uint64_t *keys, const double *delta, double scale, void *stream);
 int sgk_tabq_rebase(sgk_tabq *q, void *stream);
 int sgk_tabq_restore_base(sgk_tabq *q, void *stream);
+/* The same sync as ONE all-reduce, for tables whose keys have a small canonical
+ * index (boat 25, sokoban 36 x 36, lava 63, island 48, supervisor / whisky
+ * 48 x 2; tomato has none: 0): sgk_tabq_dense_size entries of 5 doubles --
+ * delta-Q[4] and a presence count.  export writes this replica's change since
+ * the last sync; the caller all-reduces (sum) the array over the replicas
+ * (ncclAllReduce); apply restores the base, writes
+ * base + scale * sum for every key any replica holds, and makes the result the
+ * new base.  Replicas end bit-identical: they apply the same reduced array. */
+int64_t sgk_tabq_dense_size(const sgk_tabq *q);
+int sgk_tabq_delta_export_dense(sgk_tabq *q, double *delta_out, void *stream);
+int sgk_tabq_delta_apply_dense(sgk_tabq *q, const double *delta_sum, double scale, void *stream);
 
 /* ------------------------------------------------------------ SSRL agent --
  * TabularSSQAgent (ssrl/agents.py:9-86): per-state corruption estimate C with
@@ -221,6 +249,25 @@ int sgk_tabq_restore_base(sgk_tabq *q, void *stream);
  * end, while `budget` queries remain, query_H + learn_C over the states the
  * episode visited (loop defined in DESIGN.md; the reference ships none). */
 int sgk_tabq_enable_ssrl(sgk_tabq *q, double c_prior, int64_t budget, int64_t max_episode_steps);
+/* ssrl.random_warmup (ssrl/warmup.py:4-35): every environment plays
+ * `n_episodes` random-policy episodes (RandomAgent, dummy.py:15-16; reset at
+ * the start of each, like the reference's loop, and left un-reset after the
+ * last); after each, query_H (budget -= 1) and learn_C(return - safety > 0).
+ * As in the reference the warm-up never calls act_explore, so the agent's
+ * history is empty and only the episode / corrupt-episode counters move
+ * (ssrl/agents.py:50-82).  steps_done: device [n_envs] int64 or NULL. */
+int sgk_ssrl_warmup(sgk_env *env, sgk_tabq *q, int64_t n_episodes, uint64_t t0, int64_t *steps_done, void *stream);
+/* The same agent method by method, for callers that keep the episode's history
+ * on the host (the N = 1 adapter): optional query_H bookkeeping (budget -= 1,
+ * ssrl/agents.py:45-48), then learn_C(corrupt) over `boards` (device
+ * [n_boards][H*W], the states passed to act_explore this episode, in order;
+ * ssrl/agents.py:50-75), then reset_history(corrupt, increment_episode)
+ * (:77-82), all for table `table`. */
+int sgk_ssrl_learn_c(sgk_tabq *q, int64_t table, const uint8_t *boards, int64_t n_boards, int corrupt, int query,
+                     int increment_episode, void *stream);
+/* TabularSSQAgent.budget / .episodes / .corrupt_episodes per environment
+ * (device [n_envs] int64 each, any may be NULL). */
+int sgk_ssrl_get_counters(const sgk_tabq *q, int64_t *budget, int64_t *episodes, int64_t *corrupt_episodes, void *stream);
 
 /* ------------------------------------------------------ fused hot kernel --
  * `n_steps` lock-steps of the whole tabq_learn body (common/learn.py:61-85)
@@ -233,6 +280,21 @@ int sgk_tabq_enable_ssrl(sgk_tabq *q, double c_prior, int64_t budget, int64_t ma
  * passing the previous t0 + n_steps). */
 int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat, void *stream);
 
+/* The same body run EPISODE-wise, the shape of one reference call
+ * tabq_learn(agent, env, env_state, history, args) = whiler.stepbystep
+ * (common/learn.py:13-24): every environment runs until it has finished
+ * `max_episodes` episodes (at most `max_steps` lock-steps) and is NOT reset
+ * after its last one -- like the reference, whose caller resets at the top of
+ * the next episode (train.py:62-70); a finished environment is reset by its
+ * next step.  Private tables only.  Outputs (device [n_envs], any may be NULL):
+ * steps executed, and reward / info["hidden_reward"] (NaN = None) of the last
+ * step; its actual action is read with sgk_env_actual_actions.  Meant for the
+ * N = 1 adapters: with several environments the agent-step index (epsilon
+ * schedule, random streams) restarts from the common `t0` of the next call. */
+int sgk_rollout_tabq_episodes(sgk_env *env, sgk_tabq *q, int64_t max_episodes, int64_t max_steps, uint64_t t0,
+                              int cheat, int64_t *steps_done, double *last_reward, double *last_hidden,
+                              void *stream);
+
 /* Same as sgk_rollout_tabq but with a uniform random policy and no learning
  * (RandomAgent, common/agents/dummy.py:7-16; warm-up loops). */
 int sgk_rollout_random(sgk_env *env, int64_t n_steps, uint64_t t0, void *stream);
@@ -243,6 +305,15 @@ int sgk_rollout_random(sgk_env *env, int64_t n_steps, uint64_t t0, void *stream)
  * the first episode end at or after `eval_timesteps` steps.  Episode metrics
  * accumulate in eval_env (read them with sgk_env_totals*). */
 int sgk_eval_tabq(sgk_env *eval_env, const sgk_tabq *q, int64_t eval_timesteps, uint64_t t0, void *stream);
+/* ... with the two things the single-environment drop-in needs to be exact:
+ * insert_on_miss -- the reference evaluates through act(), whose defaultdict
+ * lookup inserts a zero row for every unseen board (value.py:31,35), so its key
+ * set grows during evaluation (private tables only); episode_log -- device
+ * [n_envs][log_cap][2] doubles receiving (return, performance) of every
+ * evaluation episode in order, what track_metrics feeds the meters one episode
+ * at a time (meters.py:76-83); NULL = not wanted. */
+int sgk_eval_tabq_ex(sgk_env *eval_env, sgk_tabq *q, int64_t eval_timesteps, uint64_t t0, int insert_on_miss,
+                     double *episode_log, int64_t log_cap, void *stream);
 
 /* Check the sticky device status word (table full, replay stream dry);
  * synchronises `stream`. */

@@ -189,6 +189,8 @@ typedef struct {
     double sum_return, sum_perf, sum_margin_pos, max_return, max_perf, max_margin;
     int64_t n_margin_pos;
     uint64_t trace_hash;
+    int pending_reset;  /* the episode ended and nobody has called env.reset() yet (train.py:62-70 resets at
+                           the top of the next episode; ssrl/warmup.py:12 likewise) */
     unsigned char board[MAXHW]; /* current observation, value-mapped 0..5 */
 } cg_env;
 
@@ -644,6 +646,7 @@ static void rollout_range(cg_job *j)
         cg_rng *g = &s->rng[i];
         cg_table *tab = &s->tab[s->q_mode == CG_Q_PRIVATE ? i : 0];
         g->step = (uint64_t)s->t;
+        if (e->pending_reset) { env_reset(L, e, g); e->pending_reset = 0; }
         unsigned char skey[MAXHW];
         memset(skey, 0, MAXHW);
         memcpy(skey, e->board, (size_t)L->HW);
@@ -759,6 +762,61 @@ int cg_rollout_random(cg_sim *s, int64_t n_steps)
             if (g->overflow) return -1;
         }
     return 0;
+}
+
+/* ssrl.random_warmup (safe_grid_agents/ssrl/warmup.py:4-35) for every
+ * environment: n_episodes random-policy episodes (RandomAgent, dummy.py:15-16),
+ * each begun by env.reset() unless the environment is still fresh, and after
+ * each: safety = query_H(env) (budget -= 1, ssrl/agents.py:45-48), corrupt =
+ * episode_return - safety > 0, learn_C(corrupt) -- over an EMPTY history,
+ * since the warm-up never calls act_explore (ssrl/agents.py:29-32,50-82), so
+ * only the episode counters move.  The environment is left finished and not
+ * reset, as the reference leaves it.  Lock-steps are indexed from t0 (the
+ * simulation clock s->t is not advanced).  steps_out [n_envs] or NULL. */
+int cg_ssrl_warmup(cg_sim *s, int64_t n_episodes, uint64_t t0, int64_t *steps_out)
+{
+    for (int64_t i = 0; i < s->n_envs; i++) {
+        cg_env *e = &s->env[i];
+        cg_rng *g = &s->rng[i];
+        int64_t k = 0;
+        for (int64_t ep = 0; ep < n_episodes; ep++) {
+            int done = 0;
+            while (!done) {
+                g->step = t0 + (uint64_t)k;
+                if (e->pending_reset) { env_reset(&s->L, e, g); e->pending_reset = 0; }
+                double r, h;
+                int action = rng_random_action(g);
+                env_step(&s->L, e, g, action, &r, &h, &done);
+                trace_fold(&s->L, e, action, r, h, done);
+                k++;
+                if (g->overflow) return -1;
+            }
+            e->pending_reset = 1;
+            s->budget[i] -= 1;                                       /* query_H */
+            if (e->last_return - e->last_perf > 0) s->ssrl_corrupt[i] += 1;   /* learn_C -> reset_history(corrupt) */
+            s->ssrl_episodes[i] += 1;
+        }
+        if (steps_out) steps_out[i] = k;
+    }
+    return 0;
+}
+
+void cg_get_ssrl_counters(const cg_sim *s, int64_t *budget, int64_t *episodes, int64_t *corrupt)
+{
+    for (int64_t i = 0; i < s->n_envs; i++) {
+        budget[i] = s->budget[i]; episodes[i] = s->ssrl_episodes[i]; corrupt[i] = s->ssrl_corrupt[i];
+    }
+}
+
+/* Forget all finished-episode statistics (the warm-up resets the meters, ssrl/warmup.py:30-33). */
+void cg_clear_stats(cg_sim *s)
+{
+    for (int64_t i = 0; i < s->n_envs; i++) {
+        cg_env *e = &s->env[i];
+        e->episodes = 0; e->n_margin_pos = 0;
+        e->sum_return = e->sum_perf = e->sum_margin_pos = e->max_return = e->max_perf = e->max_margin = 0;
+        e->last_return = e->last_perf = 0;
+    }
 }
 
 /* Externally chosen actions (the unfused env.step contract). */

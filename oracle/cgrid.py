@@ -59,6 +59,10 @@ def lib():
         L.cg_epsilon_at.argtypes = [dbl, i64, i64]
         L.cg_philox.argtypes = [vp, vp, vp]
         L.cg_set_threads.argtypes = [i32]
+        L.cg_ssrl_warmup.restype = i32
+        L.cg_ssrl_warmup.argtypes = [vp, i64, u64, vp]
+        L.cg_get_ssrl_counters.argtypes = [vp, vp, vp, vp]
+        L.cg_clear_stats.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -112,6 +116,21 @@ class Sim:
         if rc:
             raise RuntimeError("replay word stream exhausted")
         return out
+
+    def ssrl_warmup(self, n_episodes, t0=1 << 40):
+        """ssrl/warmup.py:4-35 for every environment; returns steps taken per environment."""
+        steps = np.zeros(self.n, np.int64)
+        if self.L.cg_ssrl_warmup(self.h, n_episodes, t0, _ptr(steps)):
+            raise RuntimeError("replay word stream exhausted")
+        return steps
+
+    def ssrl_counters(self):
+        out = [np.zeros(self.n, np.int64) for _ in range(3)]
+        self.L.cg_get_ssrl_counters(self.h, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]))
+        return tuple(out)
+
+    def clear_stats(self):
+        self.L.cg_clear_stats(self.h)
 
     def rollout_random(self, n_steps):
         if self.L.cg_rollout_random(self.h, n_steps):

@@ -154,6 +154,30 @@ class RandomAgent:
         return int(self.rng.random_action(self.action_n))
 
 
+def random_warmup(agent, env, n_episodes, rando=None, t0=1 << 40, env_id=0):
+    """ssrl/warmup.py:4-35 on the gym-style environment (the reference's drives
+    the raw pycolab API and cannot run as shipped):
+    `n_episodes` = int(args.budget * args.warmup) random-policy episodes, each
+    begun by env.reset(); after each, safety = agent.query_H(env), corrupt =
+    episode_return - safety > 0, agent.learn_C(corrupt).  The warm-up never
+    calls agent.act_explore, so agent._history is empty and learn_C only moves
+    the episode counters -- exactly as in the reference.  Returns steps taken."""
+    rando = rando or RandomAgent(agent.action_n, rng=agent.rng)
+    stream = agent.rng
+    t = t0
+    for _ in range(n_episodes):
+        stream.set_context(env_id, t)
+        env.reset()
+        done = False
+        while not done:
+            stream.set_context(env_id, t)
+            _, _, done, _ = env.step(rando.act(None))
+            t += 1
+        safety = agent.query_H(env._env)
+        agent.learn_C(env._env.episode_return - safety > 0)
+    return t - t0
+
+
 def run_tabq(agent, env, n_steps, cheat=False, t0=0, env_id=0, record=None,
              ssrl=False):
     """`n_steps` iterations of the tabq_learn body (learn.py:61-85) with the

@@ -139,6 +139,15 @@ struct sgk_tabq {
     uint32_t *ssrl_hist;       // [hist_len][n_envs] slots visited this episode
     int *ssrl_budget;          // [n_envs]
     unsigned long long *ssrl_counts;   // [n_envs] episodes | corrupt << 32
+    unsigned long long *ssrl_visits;   // [n_envs] dense tables: visit count of each of the 8 slots this episode (8 bits each)
+    // growth of hashed private tables (the reference's dict is unbounded): the host
+    // keeps an upper bound of the fullest table's key count and rehashes into a
+    // larger capacity before a launch could overflow (reserve_slots)
+    int64_t fill_ub;           // no table holds more keys than this
+    int64_t max_states;        // distinct observations of the level (0 = unknown)
+    const uint64_t *env_core;  // the environments' state words (SSRL history remap on growth)
+    int *fill_scratch;         // device, max-reduction target of k_table_fill
+    int auto_grow;             // default on; off = fixed capacity, overflow raises SGK_EFULL
 };
 
 static TableView view_of(const sgk_tabq *q)
@@ -266,6 +275,24 @@ __global__ void k_board_to_key(const __grid_constant__ Level L, const uint8_t *b
     if (i < n) keys[i] = board_key<KIND>(L, boards + i * KindCells<KIND>::value);
 }
 
+// The inverse of board_key: the board a key stands for (keys are lossless codes
+// of the observation).  Lets the host show the table as the reference's dict
+// {tuple(board.flatten()): row} without ever having seen the boards.
+template <int KIND>
+__global__ void k_key_to_board(const __grid_constant__ Level L, const uint64_t *keys, uint8_t *boards, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = keys[i];
+    EnvRegs e = {};
+    e.pos = (uint32_t)(k & 0xFFu);
+    if (KIND == 1) e.box = (uint32_t)((k >> 8) & 0xFFu);
+    if (KIND == 2) e.watered = (uint32_t)((k >> 8) & 0xFFFFu);
+    if ((KIND == 5 || KIND == 6) && ((k >> 8) & 1ull)) e.flags |= SGK_F_AUX;
+    uint8_t *out = boards + i * KindCells<KIND>::value;
+    for (int c = 0; c < KindCells<KIND>::value; c++) out[c] = k ? render_cell<KIND>(L, e, c) : 0;
+}
+
 // ===================================================================== unfused agent kernels
 struct AgentArgs {
     Level level;
@@ -321,6 +348,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_private(const __grid_c
     const uint64_t nkey = board_key<KIND>(p.level, successors + i * KindCells<KIND>::value);
     const uint32_t nslot = find_private(p.T, i, nkey, p.status);
     const uint32_t slot = find_private(p.T, i, skey, p.status);
+    if (slot == SGK_NOSLOT) return;      // table full (status raised): no row to update
     const int a = actions[i] & 3;
     double r = rewards[i];
     if (p.ssrl) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[entry(p.T, slot, (uint32_t)i)]));
@@ -342,11 +370,12 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_shared_a(const __grid_
     const uint64_t nkey = board_key<KIND>(p.level, successors + i * KindCells<KIND>::value);
     const uint32_t nslot = find_shared(p.T, nkey, p.status);
     const uint32_t slot = find_shared(p.T, skey, p.status);
+    scr_slot[i] = slot;
+    if (slot == SGK_NOSLOT) return;      // table full (status raised): takes no part in the election
     const int a = actions[i] & 3;
     double r = rewards[i];
     if (p.ssrl) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[slot]));
     const double best = row_max(load_row(p.T, 0, nslot));
-    scr_slot[i] = slot;
     scr_target[i] = __dadd_rn(r, __dmul_rn(p.discount, best));
     atomicMax(p.T.winner + (size_t)slot * SGK_NA + a, (p.epoch << 32) | (0xFFFFFFFFull - (unsigned long long)i));
 }
@@ -357,6 +386,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_shared_b(const __grid_
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
     const uint32_t slot = scr_slot[i];
+    if (slot == SGK_NOSLOT) return;
     const int a = actions[i] & 3;
     if (p.T.winner[(size_t)slot * SGK_NA + a] != ((p.epoch << 32) | (0xFFFFFFFFull - (unsigned long long)i))) return;
     double *q = p.T.q + (size_t)slot * SGK_NA + a;
@@ -417,11 +447,26 @@ struct RolloutArgs {
     int64_t ssrl_hist_len;
     int *ssrl_budget;
     unsigned long long *ssrl_counts;
+    unsigned long long *ssrl_visits;
+    // episodic mode (TRACE builds only): environments reset lazily -- an episode
+    // that ended stays ended (SGK_F_DONE) until the next step starts a new one,
+    // like the reference's `env.reset()` at the top of its episode loop
+    // (train.py:62-70) -- and each environment stops after `max_episodes`
+    // episode ends.  0 = lock-step mode: reset on done, run all n_steps.
+    int64_t max_episodes;
+    long long *steps_done;               // [n] steps this launch executed, or null
+    double *last_reward, *last_hidden;   // [n] reward / hidden reward (NaN = None) of the last step executed, or null
 };
 
 // SSRL episode end (ssrl/agents.py:45-82; loop per DESIGN.md): query H while
 // budget remains, then the Bayesian C update over the states visited.
-__device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i, long long g, const EpStats &st, uint32_t n_hist)
+// `_history` (ssrl/agents.py:29-32) holds one entry per act_explore call, so a
+// state visited k times has its estimate multiplied k times.  Hashed tables
+// keep the visited slots as a list in HBM ([step][env], coalesced); dense
+// tables (boat race, 8 slots) keep 8-bit visit counts in ONE register.
+template <bool DENSE>
+__device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i, long long g, const EpStats &st, uint32_t n_hist,
+                                                 unsigned long long visits)
 {
     int budget = p.ssrl_budget[i];
     unsigned long long cnt = p.ssrl_counts[i];
@@ -430,11 +475,24 @@ __device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i
     if (budget > 0) {
         budget -= 1;
         corrupt = __dsub_rn(st.last_return, st.last_perf) > 0;
-        const double factor = __ddiv_rn((double)episodes, (double)(corrupt_eps + 1));
-        for (uint32_t k = 0; k < n_hist; k++) {
-            const uint32_t slot = p.ssrl_hist[(size_t)k * p.n + i];
-            double *c = p.T.c + entry(p.T, slot, (uint32_t)g);
-            *c = corrupt ? __dmul_rn(*c, factor) : __dmul_rn(*c, 0.0);
+        const double factor = corrupt ? __ddiv_rn((double)episodes, (double)(corrupt_eps + 1)) : 0.0;
+        if (DENSE) {
+            for (uint32_t sl = 0; sl < 8; sl++) {
+                const uint32_t times = (uint32_t)(visits >> (8 * sl)) & 0xFFu;
+                if (times == 0) continue;
+                double *c = p.T.c + entry(p.T, sl, (uint32_t)g);
+                double v = *c;
+                for (uint32_t k = 0; k < times; k++) v = __dmul_rn(v, factor);
+                *c = v;
+            }
+        } else {
+            if (n_hist > (uint32_t)p.ssrl_hist_len) n_hist = (uint32_t)p.ssrl_hist_len;
+            for (uint32_t k = 0; k < n_hist; k++) {
+                const uint32_t slot = p.ssrl_hist[(size_t)k * p.n + i];
+                if (slot == SGK_NOSLOT) continue;
+                double *c = p.T.c + entry(p.T, slot, (uint32_t)g);
+                *c = __dmul_rn(*c, factor);
+            }
         }
         p.ssrl_budget[i] = budget;
     }
@@ -472,6 +530,12 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     Rng rng;
     RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
     int status = 0;
+    const bool episodic = TRACE && p.max_episodes > 0;
+    if (e.flags & SGK_F_DONE) {
+        // the previous call (episodic, or the unfused env.step) left a finished episode
+        rng.set_step(p.t0);
+        env_reset<KIND>(L, e, rng);
+    }
 
     // The dict of the reference gains a key when act/learn first touch it
     // (value.py:35,46-52), not when the environment resets: look the start
@@ -500,20 +564,41 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     }
     int greedy = argmax_first(row);
     bool fresh = true;                      // current state not yet touched by the agent
-    uint32_t n_hist = SSRL ? e.frame : 0;   // states visited so far this episode
+    uint32_t n_hist = (SSRL && !DENSE) ? e.frame : 0;   // states visited so far this episode
+    unsigned long long visits = (SSRL && DENSE) ? p.ssrl_visits[i] : 0ull;
+    int64_t episodes_left = p.max_episodes, k_done = 0;
+    double last_r = 0.0, last_h = 0.0;
+    int last_actual = 0;
 
     for (int64_t k = 0; k < p.n_steps; k++) {
         rng.set_step(p.t0 + (uint64_t)k);
+        if (episodic && (e.flags & SGK_F_DONE)) {
+            // lazy reset: the new episode starts with this step
+            env_reset<KIND>(L, e, rng);
+            key = obs_key<KIND>(L, e);
+            slot = SGK_NOSLOT;
+            row = QRow{0.0, 0.0, 0.0, 0.0};
+            if (DENSE) {
+                slot = dense_slot(L.open32, e.pos);
+                row = row_s(slot);
+            } else if (lookup(p.T, g, key, slot)) {
+                row = load_row(p.T, g, slot);
+            }
+            greedy = argmax_first(row);
+        }
         // act_explore (value.py:37-42)
         int a = greedy;
         if (rng.agent_uniform() < __ldg(p.thr + k)) a = rng.agent_choice();
         if (DENSE) touched |= 1u << slot;
         else if (slot == SGK_NOSLOT) slot = find_private(p.T, g, key, &status);
-        if (SSRL) { p.ssrl_hist[(size_t)n_hist * p.n + i] = slot; n_hist++; }
+        if (SSRL) {
+            if (DENSE) visits += 1ull << (8 * slot);
+            else { if (n_hist < (uint32_t)p.ssrl_hist_len) p.ssrl_hist[(size_t)n_hist * p.n + i] = slot; n_hist++; }
+        }
         // env.step
         const StepOut o = env_step<KIND>(L, e, a, rng);
         double r = p.cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;   // learn.py:72-73
-        if (SSRL) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[entry(p.T, slot, g)]));
+        if (SSRL && slot != SGK_NOSLOT) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[entry(p.T, slot, g)]));
         // learn (value.py:44-52): the successor's row is read before the write
         const uint64_t nkey = obs_key<KIND>(L, e);
         uint32_t nslot;
@@ -544,10 +629,23 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         }
         if (TRACE) th = trace_fold<KIND>(L, e, th, a, o);
         key = nkey; slot = nslot; row = nrow;
+        if (episodic) {
+            last_r = o.reward;
+            last_h = o.hidden_none ? __longlong_as_double(0x7ff8000000000000ll) : o.hidden;
+            last_actual = o.actual;
+            k_done = k + 1;
+        }
         if (o.done) {
             if (DENSE) touched |= 1u << slot;                  // learn touched Q[s'] (value.py:48-49)
             st.episode_end(e, p.level.perf_is_return != 0);
-            if (SSRL) { ssrl_episode_end(p, i, i, st, n_hist); n_hist = 0; }
+            if (SSRL) { ssrl_episode_end<DENSE>(p, i, i, st, n_hist, visits); n_hist = 0; visits = 0ull; }
+            if (episodic) {
+                e.flags |= SGK_F_DONE;
+                greedy = DENSE ? next_greedy : argmax_first(row);
+                fresh = true;
+                if (--episodes_left == 0) break;
+                continue;
+            }
             rng.set_step(p.t0 + (uint64_t)k + 1);
             env_reset<KIND>(L, e, rng);
             key = obs_key<KIND>(L, e);
@@ -574,11 +672,17 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             if ((touched >> s) & 1u) p.T.keys[entry(p.T, s, g)] = (1ull << 63) | (uint64_t)__fns(L.open32, 0, (int)s + 1);
         }
     }
-    p.arr.core[i] = pack_core(e);
+    p.arr.core[i] = pack_core(e) | ((uint64_t)last_actual << 48);    // read back by sgk_env_actual_actions
     p.arr.ep_return[i] = e.ep_return;
     p.arr.hidden_cum[i] = e.hidden_cum;
     st.store(p.arr, i);
     if (TRACE) p.arr.trace_hash[i] = th;
+    if (SSRL && DENSE) p.ssrl_visits[i] = visits;
+    if (episodic) {
+        if (p.steps_done) p.steps_done[i] = k_done;
+        if (p.last_reward) p.last_reward[i] = last_r;
+        if (p.last_hidden) p.last_hidden[i] = last_h;
+    }
     RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
     if (rng.overflowed()) status = SGK_ST_REPLAY_DRY;
     if (status) *p.status = status;
@@ -594,6 +698,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
 // environments whose state stays in registers for the whole rollout.
 __device__ __forceinline__ QRow load_row_cg(const TableView &T, uint32_t slot)
 {
+    if (slot == SGK_NOSLOT) return QRow{0.0, 0.0, 0.0, 0.0};
     const double2 *p = reinterpret_cast<const double2 *>(T.q + (size_t)slot * SGK_NA);
     const double2 a = __ldcg(p), b = __ldcg(p + 1);
     QRow r; r.v0 = a.x; r.v1 = a.y; r.v2 = b.x; r.v3 = b.y;
@@ -652,7 +757,7 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared(const __gri
             // group goes to memory, and only if it would still win there
             const uint32_t word = slot[j] * SGK_NA + (uint32_t)la;
             const unsigned peers = __match_any_sync(__activemask(), word);
-            if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) {
+            if (slot[j] != SGK_NOSLOT && (unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) {
                 unsigned long long *w = p.T.winner + word;
                 const unsigned long long mine = ((unsigned long long)(t + 1) << 32) | (0xFFFFFFFFull - (unsigned long long)i);
                 if (*reinterpret_cast<volatile unsigned long long *>(w) < mine) atomicMax(w, mine);
@@ -666,7 +771,7 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared(const __gri
             if (i >= p.n) continue;
             const int a = (int)(act[j] & 3u);
             const unsigned long long mine = ((unsigned long long)(t + 1) << 32) | (0xFFFFFFFFull - (unsigned long long)i);
-            if (__ldcg(p.T.winner + (size_t)slot[j] * SGK_NA + a) == mine) {
+            if (slot[j] != SGK_NOSLOT && __ldcg(p.T.winner + (size_t)slot[j] * SGK_NA + a) == mine) {
                 double *q = p.T.q + (size_t)slot[j] * SGK_NA + a;
                 const double q_sa = __ldcg(q);
                 __stcg(q, __dadd_rn(q_sa, __dmul_rn(p.lr, __dsub_rn(target[j], q_sa))));
@@ -772,23 +877,27 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared_small(const
             rng[j].set_step(t);
             const uint64_t key = obs_key<KIND>(L, e[j]);
             if (slot[j] == SGK_NOSLOT) slot[j] = find(key);
+            const bool have = slot[j] != SGK_NOSLOT;     // false only when the table is full (status raised)
+            const uint32_t srow = have ? slot[j] * 4 : 0u;
             QRow row;
-            row.v0 = q_s[slot[j] * 4 + 0]; row.v1 = q_s[slot[j] * 4 + 1];
-            row.v2 = q_s[slot[j] * 4 + 2]; row.v3 = q_s[slot[j] * 4 + 3];
+            row.v0 = have ? q_s[srow + 0] : 0.0; row.v1 = have ? q_s[srow + 1] : 0.0;
+            row.v2 = have ? q_s[srow + 2] : 0.0; row.v3 = have ? q_s[srow + 3] : 0.0;
             int a = argmax_first(row);
             if (rng[j].agent_uniform() < thr) a = rng[j].agent_choice();
             const StepOut o = env_step<KIND>(L, e[j], a, rng[j]);
             const double r = p.cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;
             const uint64_t nkey = obs_key<KIND>(L, e[j]);
             nslot[j] = nkey == key ? slot[j] : find(nkey);
+            const bool nhave = nslot[j] != SGK_NOSLOT;
+            const uint32_t nsrow = nhave ? nslot[j] * 4 : 0u;
             QRow nrow;
-            nrow.v0 = q_s[nslot[j] * 4 + 0]; nrow.v1 = q_s[nslot[j] * 4 + 1];
-            nrow.v2 = q_s[nslot[j] * 4 + 2]; nrow.v3 = q_s[nslot[j] * 4 + 3];
+            nrow.v0 = nhave ? q_s[nsrow + 0] : 0.0; nrow.v1 = nhave ? q_s[nsrow + 1] : 0.0;
+            nrow.v2 = nhave ? q_s[nsrow + 2] : 0.0; nrow.v3 = nhave ? q_s[nsrow + 3] : 0.0;
             pub[i] = __dadd_rn(r, __dmul_rn(p.discount, row_max(nrow)));
             const int la = (KIND == 6 && p.cheat) ? o.actual : a;     // learn.py:74-78
             act[j] = (uint32_t)la | (o.done ? 4u : 0u);
             if (TRACE) p.arr.trace_hash[i] = trace_fold<KIND>(L, e[j], p.arr.trace_hash[i], a, o);
-            atomicMin(&blk_min[slot[j] * SGK_NA + (uint32_t)la], (uint32_t)i);
+            if (have) atomicMin(&blk_min[slot[j] * SGK_NA + (uint32_t)la], (uint32_t)i);
         }
         __syncthreads();
         for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
@@ -845,10 +954,18 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared_small(const
 }
 
 // Greedy evaluation (default_eval, common/eval.py:8-56): act greedily, no
-// exploration, no learning, no insertion; an environment stops at the first
-// episode end at or after `eval_timesteps` steps.  Tables are read-only.
+// exploration, no learning; an environment stops at the first episode end at
+// or after `eval_timesteps` steps.  Tables are read-only unless `insert` is
+// set (private tables): the reference evaluates through act(), whose
+// defaultdict lookup inserts a zero row for every unseen board (value.py:31,35),
+// so len(Q) and the key set grow during evaluation -- the drop-in adapters
+// reproduce that; batched evaluation leaves the tables untouched.
+// `ep_log` ([n][log_cap][2], or null) receives (return, performance) of every
+// evaluation episode in order: what track_metrics feeds the meters one episode
+// at a time (meters.py:76-83).
 template <int KIND, class Rng>
-__global__ void __launch_bounds__(SGK_BLOCK) k_eval_tabq(const __grid_constant__ RolloutArgs p, int64_t eval_timesteps, int shared)
+__global__ void __launch_bounds__(SGK_BLOCK) k_eval_tabq(const __grid_constant__ RolloutArgs p, int64_t eval_timesteps, int shared,
+                                                         int insert, double *ep_log, int64_t log_cap)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
@@ -863,15 +980,23 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_eval_tabq(const __grid_constant__
     Rng rng;
     RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
     const int64_t limit = eval_timesteps + L.max_iterations;
+    int status = 0;
+    int64_t n_logged = 0;
     for (int64_t t = 0; t < limit;) {
         rng.set_step(p.t0 + (uint64_t)t);
         uint32_t slot;
         QRow row = {0.0, 0.0, 0.0, 0.0};
-        if (lookup(p.T, g, obs_key<KIND>(L, e), slot)) row = shared ? load_row_cg(p.T, slot) : load_row(p.T, g, slot);
+        if (insert) row = load_row(p.T, g, find_private(p.T, g, obs_key<KIND>(L, e), &status));
+        else if (lookup(p.T, g, obs_key<KIND>(L, e), slot)) row = shared ? load_row_cg(p.T, slot) : load_row(p.T, g, slot);
         const StepOut o = env_step<KIND>(L, e, argmax_first(row), rng);
         t++;
         if (o.done) {
             st.episode_end(e, p.level.perf_is_return != 0);
+            if (ep_log && n_logged < log_cap) {
+                ep_log[((size_t)i * log_cap + n_logged) * 2 + 0] = st.last_return;
+                ep_log[((size_t)i * log_cap + n_logged) * 2 + 1] = st.last_perf;
+                n_logged++;
+            }
             if (t >= eval_timesteps) { e.flags |= SGK_F_DONE; break; }
             rng.set_step(p.t0 + (uint64_t)t);
             env_reset<KIND>(L, e, rng);
@@ -882,7 +1007,8 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_eval_tabq(const __grid_constant__
     p.arr.hidden_cum[i] = e.hidden_cum;
     st.store(p.arr, i);
     RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
-    if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
+    if (rng.overflowed()) status |= SGK_ST_REPLAY_DRY;
+    if (status) *p.status = status;
 }
 
 template <int KIND, class Rng, bool TRACE>
@@ -900,13 +1026,34 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_random(const __grid_const
     uint64_t th = TRACE ? p.arr.trace_hash[i] : 0;
     Rng rng;
     RngInit<Rng>::load(rng, p.seed, p.env_id0 + i, p.words, p.wpe, p.arr.replay_cursor, i);
+    // episodic mode (see RolloutArgs): lazy resets, stop after max_episodes
+    // episode ends; with the SSRL arrays set this is ssrl.random_warmup
+    // (ssrl/warmup.py:4-35): after every episode query_H (budget -= 1) and
+    // learn_C(return - safety > 0) -- over an EMPTY history, the warm-up never
+    // calls act_explore, so only the episode / corrupt-episode counters move.
+    const bool episodic = TRACE && p.max_episodes > 0;
+    int64_t episodes_left = p.max_episodes, k_done = 0;
+    unsigned long long n_eps = 0, n_corrupt = 0;
+    if (!episodic && (e.flags & SGK_F_DONE)) {
+        rng.set_step(p.t0);
+        env_reset<KIND>(L, e, rng);
+    }
     for (int64_t k = 0; k < p.n_steps; k++) {
         rng.set_step(p.t0 + (uint64_t)k);
+        if (episodic && (e.flags & SGK_F_DONE)) env_reset<KIND>(L, e, rng);
         const int a = rng.random_action();
         const StepOut o = env_step<KIND>(L, e, a, rng);
         if (TRACE) th = trace_fold<KIND>(L, e, th, a, o);
+        if (episodic) k_done = k + 1;
         if (o.done) {
             st.episode_end(e, p.level.perf_is_return != 0);
+            if (episodic) {
+                n_eps += 1;
+                if (__dsub_rn(st.last_return, st.last_perf) > 0) n_corrupt += 1;
+                e.flags |= SGK_F_DONE;
+                if (--episodes_left == 0) break;
+                continue;
+            }
             rng.set_step(p.t0 + (uint64_t)k + 1);
             env_reset<KIND>(L, e, rng);
         }
@@ -916,6 +1063,13 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_random(const __grid_const
     p.arr.hidden_cum[i] = e.hidden_cum;
     st.store(p.arr, i);
     if (TRACE) p.arr.trace_hash[i] = th;
+    if (episodic) {
+        if (p.steps_done) p.steps_done[i] = k_done;
+        if (p.ssrl_budget) {
+            p.ssrl_budget[i] -= (int)n_eps;
+            p.ssrl_counts[i] += n_eps | (n_corrupt << 32);
+        }
+    }
     RngInit<Rng>::store(rng, p.arr.replay_cursor, i);
     if (rng.overflowed()) *p.status = SGK_ST_REPLAY_DRY;
 }
@@ -1030,6 +1184,70 @@ __global__ void k_table_import(const TableView T, int64_t table, const uint64_t 
     for (int a = 0; a < SGK_NA; a++) T.q[at * SGK_NA + a] = q[s * SGK_NA + a];
 }
 
+// ---- growth of hashed tables (the reference's dict is unbounded, value.py:31)
+// Key count of the fullest table.  Tables whose slots are contiguous
+// (table-major, or a single table) are scanned by one warp each, slot-major
+// tables by one thread each -- coalesced either way.
+__global__ void __launch_bounds__(256) k_table_fill(const TableView T, int contiguous, int *max_fill)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int count = 0;
+    if (contiguous) {
+        const int64_t g = tid >> 5;
+        if (g >= T.n_tables) return;
+        for (uint32_t sl = threadIdx.x & 31u; sl < T.cap; sl += 32) count += T.keys[entry(T, sl, (uint32_t)g)] != 0ull;
+        for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xFFFFFFFFu, count, o);
+        if ((threadIdx.x & 31u) == 0) atomicMax(max_fill, count);
+    } else {
+        if (tid >= T.n_tables) return;
+        for (uint32_t sl = 0; sl < T.cap; sl++) count += T.keys[entry(T, sl, (uint32_t)tid)] != 0ull;
+        atomicMax(max_fill, count);
+    }
+}
+
+// Rehash every table into a larger one: one thread per old entry; entries of
+// one table insert concurrently (atomicCAS on the key word).  Which slot a key
+// lands in depends on the race, the table's CONTENT (key -> row) does not.
+__global__ void __launch_bounds__(256) k_table_rehash(const TableView Old, int old_table_major, const TableView New, int *status)
+{
+    const int64_t at = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (at >= (int64_t)Old.cap * Old.n_tables) return;
+    const unsigned long long key = Old.keys[at];
+    if (key == 0ull) return;
+    const uint32_t g = old_table_major ? (uint32_t)(at / Old.cap) : (uint32_t)(at % Old.n_tables);
+    uint32_t sl = home_slot(key, New.log_cap);
+    for (uint32_t i = 0; i < New.cap; i++) {
+        const size_t to = entry(New, sl, g);
+        if (atomicCAS(New.keys + to, 0ull, key) == 0ull) {
+            const double2 *src = reinterpret_cast<const double2 *>(Old.q + (size_t)at * SGK_NA);
+            double2 *dst = reinterpret_cast<double2 *>(New.q + to * SGK_NA);
+            dst[0] = src[0]; dst[1] = src[1];
+            if (Old.c) New.c[to] = Old.c[at];
+            return;
+        }
+        sl = (sl + 1) & (New.cap - 1);
+    }
+    *status = SGK_ST_FULL;
+}
+
+// SSRL: the slots an unfinished episode has visited so far, old table -> new table
+__global__ void __launch_bounds__(256) k_hist_remap(const TableView Old, const TableView New, const uint64_t *core, uint32_t *hist,
+                                                    int64_t hist_len, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvRegs e;
+    unpack_core(core[i], e);
+    const int64_t n_hist = (e.flags & SGK_F_DONE) ? 0 : min((int64_t)e.frame, hist_len);
+    for (int64_t k = 0; k < n_hist; k++) {
+        const uint32_t old_slot = hist[(size_t)k * n + i];
+        if (old_slot == SGK_NOSLOT) continue;
+        uint32_t new_slot = SGK_NOSLOT;
+        lookup(New, (uint32_t)i, Old.keys[entry(Old, old_slot, (uint32_t)i)], new_slot);
+        hist[(size_t)k * n + i] = new_slot;
+    }
+}
+
 // ---- shared-table replica sync (multi-GPU): deltas against the last synced table
 __global__ void k_delta_export(const TableView T, const unsigned long long *base_keys, const double *base_q,
                                uint64_t *keys_out, double *delta_out)
@@ -1064,6 +1282,55 @@ __global__ void k_delta_apply(const TableView T, const uint64_t *keys_in, const 
     for (int a = 0; a < SGK_NA; a++) {
         double *q = T.q + (size_t)slot * SGK_NA + a;
         *q = __dadd_rn(*q, __dmul_rn(scale, delta_in[s * SGK_NA + a]));
+    }
+}
+
+// ---- the same sync for tables whose keys have a small canonical index
+// (every kind but tomato: the low 24 key bits are agent cell | (box cell or
+// flag) << 8): each replica writes its change since the last sync into a dense
+// array indexed by that code -- [index][0..3] = delta-Q, [index][4] = 1 when the
+// replica holds the key -- ONE all-reduce (sum) merges the replicas, and every
+// replica rebuilds base + scale * sum from the identical reduced array.
+template <int KIND> struct DenseIndex {
+    static constexpr int cells = KindCells<KIND>::value;
+    static constexpr int extra = KIND == 1 ? cells : (KIND == 5 || KIND == 6) ? 2 : 1;     // box cell | flag
+    static constexpr int size = KIND == 2 ? 0 : cells * extra;
+    static __device__ __forceinline__ uint32_t of(uint64_t key) { return (uint32_t)(key & 0xFFu) + cells * (uint32_t)((key >> 8) & 0xFFu); }
+    static __device__ __forceinline__ uint64_t key_of(uint32_t idx) { return (1ull << 63) | (uint64_t)(idx % cells) | ((uint64_t)(idx / cells) << 8); }
+};
+
+template <int KIND>
+__global__ void k_delta_export_dense(const TableView T, const unsigned long long *base_keys, const double *base_q, double *out)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= T.cap) return;
+    const unsigned long long key = T.keys[s];
+    if (key == 0ull) return;
+    double b[SGK_NA] = {0.0, 0.0, 0.0, 0.0};
+    TableView B = T;
+    B.keys = const_cast<unsigned long long *>(base_keys);
+    uint32_t bs;
+    if (lookup(B, 0, key, bs))
+        for (int a = 0; a < SGK_NA; a++) b[a] = base_q[(size_t)bs * SGK_NA + a];
+    double *o = out + (size_t)DenseIndex<KIND>::of(key) * 5;
+    for (int a = 0; a < SGK_NA; a++) o[a] = __dsub_rn(T.q[(size_t)s * SGK_NA + a], b[a]);
+    o[4] = 1.0;
+}
+
+// runs on the table already restored to the base: q = base + scale * sum
+template <int KIND>
+__global__ void k_delta_apply_dense(const TableView T, const double *sum, double scale, int *status)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= DenseIndex<KIND>::size) return;
+    const double *in = sum + (size_t)idx * 5;
+    if (!(in[4] > 0.0)) return;
+    int st = 0;
+    const uint32_t slot = find_shared(T, DenseIndex<KIND>::key_of((uint32_t)idx), &st);
+    if (slot == SGK_NOSLOT) { *status = st; return; }
+    for (int a = 0; a < SGK_NA; a++) {
+        double *q = T.q + (size_t)slot * SGK_NA + a;
+        *q = __dadd_rn(*q, __dmul_rn(scale, in[a]));
     }
 }
 
@@ -1281,6 +1548,19 @@ extern "C" int sgk_board_to_key(const sgk_env *env, const uint8_t *boards, uint6
     });
 }
 
+extern "C" int sgk_key_to_board(const sgk_env *env, const uint64_t *keys, uint8_t *boards_out, int64_t n, void *stream)
+{
+    REQUIRE(env != nullptr && keys != nullptr && boards_out != nullptr && n >= 0, "bad argument");
+    if (n == 0) return SGK_OK;
+    DeviceGuard g(env->device);
+    return by_kind(env->level.kind, [&](auto K) {
+        k_key_to_board<decltype(K)::value><<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(env->level, keys, boards_out, n);
+        return launch_check("k_key_to_board");
+    });
+}
+
+extern "C" int sgk_env_max_iterations(const sgk_env *env) { return env ? env->level.max_iterations : 0; }
+
 extern "C" int sgk_env_get_stats(const sgk_env *env, const sgk_env_stats *out, void *stream)
 {
     REQUIRE(env != nullptr && out != nullptr, "bad argument");
@@ -1298,6 +1578,17 @@ extern "C" int sgk_env_totals(const sgk_env *env, double *totals_out, void *stre
     return launch_check("k_totals");
 }
 
+// the sticky status word the rollout kernels raise (table full, replay stream
+// dry): every synchronising entry point reports it
+static int env_status_check(const sgk_env *env)
+{
+    int s = 0;
+    CU(cudaMemcpy(&s, env->status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (s & SGK_ST_FULL) return fail(SGK_EFULL, "a Q table ran out of slots; create it with a larger capacity (or leave auto-grow on)");
+    if (s & SGK_ST_REPLAY_DRY) return fail(SGK_EREPLAY, "a replayed word stream ran dry");
+    return SGK_OK;
+}
+
 extern "C" int sgk_env_totals_host(const sgk_env *env, double totals[SGK_N_TOTALS], void *stream)
 {
     REQUIRE(env != nullptr && totals != nullptr, "bad argument");
@@ -1307,7 +1598,7 @@ extern "C" int sgk_env_totals_host(const sgk_env *env, double totals[SGK_N_TOTAL
     if (rc != SGK_OK) return rc;
     CU(cudaMemcpyAsync(totals, env->totals, SGK_N_TOTALS * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    return SGK_OK;
+    return env_status_check(env);
 }
 
 extern "C" int sgk_discounted_returns(const sgk_env *env, const double *reward, const uint8_t *done, const int32_t *frame0,
@@ -1341,7 +1632,8 @@ extern "C" int sgk_tabq_destroy(sgk_tabq *q)
     if (!q) return SGK_OK;
     DeviceGuard g(q->device);
     void *ptrs[] = {q->keys, q->q, q->c, q->winner, q->status, q->thr, q->scr_slot, q->scr_target,
-                    q->ssrl_hist, q->ssrl_budget, q->ssrl_counts, q->base_keys, q->base_q, q->pub_target};
+                    q->ssrl_hist, q->ssrl_budget, q->ssrl_counts, q->base_keys, q->base_q, q->pub_target,
+                    q->ssrl_visits, q->fill_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete q;
     return SGK_OK;
@@ -1376,7 +1668,21 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
     q->log_cap = 0;
     while ((1ll << q->log_cap) < capacity) q->log_cap++;
     q->lr = 0.5; q->discount = 0.99; q->epsilon = 0.01; q->anneal = 100000;
+    q->auto_grow = 1;
     q->dense_open = dense ? env->level.open32 : 0u;
+    {
+        // distinct observations of the level (an upper bound): a table at least this
+        // large can never fill, smaller ones grow on demand (reserve_slots)
+        const Level &L = env->level;
+        const int64_t open = L.HW - (int64_t)__builtin_popcountll(L.walls);
+        switch (L.kind) {
+        case SGK_ENV_SOKOBAN: q->max_states = open * (open - 1); break;              // agent x box
+        case SGK_ENV_TOMATO: q->max_states = open << L.n_tomatoes; break;             // agent x watered set
+        case SGK_ENV_SUPER: case SGK_ENV_WHISKY: q->max_states = 2 * open; break;     // agent x (supervisor | bottle)
+        default: q->max_states = open; break;
+        }
+        q->env_core = env->arr.core;
+    }
     if ((uint64_t)q->cap * (uint64_t)q->n_tables >= (1ull << 32)) {
         delete q;
         return fail(SGK_EINVAL, "capacity x tables must stay below 2^32 slots");
@@ -1430,9 +1736,20 @@ extern "C" int sgk_tabq_enable_ssrl(sgk_tabq *q, double c_prior, int64_t budget,
     REQUIRE(q->q_mode == SGK_Q_PRIVATE, "SSRL needs private tables (one agent per environment)");
     REQUIRE(max_episode_steps > 0 && budget >= 0 && budget < (1ll << 31), "bad SSRL argument");
     DeviceGuard g(q->device);
+    {
+        // the history holds one slot per step of an episode: never shorter than the
+        // level's own time limit, whatever the caller asked for
+        Level L;
+        make_level(q->kind, L);
+        if (max_episode_steps < L.max_iterations) max_episode_steps = L.max_iterations;
+        REQUIRE(L.max_iterations <= 255, "episodes longer than 255 steps do not fit the dense visit counters");
+    }
     const size_t slots = (size_t)q->cap * (size_t)q->n_tables;
     if (!q->c) CU(cudaMalloc(&q->c, slots * 8));
-    if (!q->ssrl_hist) CU(cudaMalloc(&q->ssrl_hist, (size_t)max_episode_steps * q->n_envs * 4));
+    if (q->ssrl_hist && q->ssrl_hist_len < max_episode_steps) { cudaFree(q->ssrl_hist); q->ssrl_hist = nullptr; }
+    if (!q->ssrl_hist && !q->dense_open) CU(cudaMalloc(&q->ssrl_hist, (size_t)max_episode_steps * q->n_envs * 4));
+    if (!q->ssrl_visits) CU(cudaMalloc(&q->ssrl_visits, (size_t)q->n_envs * 8));
+    CU(cudaMemset(q->ssrl_visits, 0, (size_t)q->n_envs * 8));
     if (!q->ssrl_budget) CU(cudaMalloc(&q->ssrl_budget, (size_t)q->n_envs * 4));
     if (!q->ssrl_counts) CU(cudaMalloc(&q->ssrl_counts, (size_t)q->n_envs * 8));
     k_fill_f64<<<148 * 4, 256>>>(q->c, (int64_t)slots, c_prior);
@@ -1442,6 +1759,8 @@ extern "C" int sgk_tabq_enable_ssrl(sgk_tabq *q, double c_prior, int64_t budget,
     q->ssrl = 1; q->c_prior = c_prior; q->ssrl_hist_len = max_episode_steps;
     return SGK_OK;
 }
+
+static int reserve_slots(sgk_tabq *q, int64_t want, int64_t at_least, cudaStream_t st, int64_t *granted);
 
 static AgentArgs agent_args(const sgk_tabq *q, const sgk_env *env, int64_t n, uint64_t step)
 {
@@ -1465,6 +1784,9 @@ extern "C" int sgk_tabq_act(sgk_tabq *q, sgk_env *env, const uint8_t *boards, in
     REQUIRE(!explore || env != nullptr, "exploration needs the environment object (random streams)");
     REQUIRE(!explore || n <= env->n, "n exceeds the environment count");
     DeviceGuard g(q->device);
+    int64_t granted = 0;
+    int rc0 = reserve_slots(q, 1, 1, (cudaStream_t)stream, &granted);     // act inserts a zero row on a miss (value.py:31,35)
+    if (rc0 != SGK_OK) return rc0;
     const AgentArgs a = agent_args(q, env, n, step);
     return by_kind(q->kind, [&](auto K) {
         constexpr int KIND = decltype(K)::value;
@@ -1484,6 +1806,9 @@ extern "C" int sgk_tabq_learn(sgk_tabq *q, const uint8_t *boards, const uint8_t 
     DeviceGuard g(q->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (q->q_mode == SGK_Q_PRIVATE) {
+        int64_t granted = 0;
+        int rc0 = reserve_slots(q, 2, 2, st, &granted);                 // learn touches Q[s] and Q[s'] (value.py:46-52)
+        if (rc0 != SGK_OK) return rc0;
         const AgentArgs a = agent_args(q, nullptr, n, 0);
         return by_kind(q->kind, [&](auto K) {
             k_tabq_learn_private<decltype(K)::value><<<grid_for(n, SGK_BLOCK), SGK_BLOCK, 0, st>>>(a, boards, actions, rewards, successors);
@@ -1525,6 +1850,7 @@ extern "C" int sgk_tabq_import(sgk_tabq *q, int64_t table, const uint64_t *keys,
     REQUIRE(table >= 0 && table < q->n_tables, "no such table");
     DeviceGuard g(q->device);
     k_table_import<<<grid_for(q->cap, 128), 128, 0, (cudaStream_t)stream>>>(view_of(q), table, keys, qrows);
+    q->fill_ub = q->cap;      // unknown occupancy: the next reservation counts
     return launch_check("k_table_import");
 }
 
@@ -1559,6 +1885,45 @@ extern "C" int sgk_tabq_delta_apply(sgk_tabq *q, const uint64_t *keys, const dou
     return launch_check("k_delta_apply");
 }
 
+extern "C" int64_t sgk_tabq_dense_size(const sgk_tabq *q)
+{
+    if (!q || q->q_mode != SGK_Q_SHARED) return 0;
+    int64_t n = 0;
+    by_kind(q->kind, [&](auto K) { n = DenseIndex<decltype(K)::value>::size; return SGK_OK; });
+    return n;
+}
+
+extern "C" int sgk_tabq_delta_export_dense(sgk_tabq *q, double *delta_out, void *stream)
+{
+    REQUIRE(q != nullptr && delta_out != nullptr, "bad argument");
+    REQUIRE(sgk_tabq_dense_size(q) > 0, "this table has no dense canonical index (tomato, or not a shared table)");
+    DeviceGuard g(q->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_base(q);
+    if (rc != SGK_OK) return rc;
+    CU(cudaMemsetAsync(delta_out, 0, (size_t)sgk_tabq_dense_size(q) * 5 * sizeof(double), st));
+    return by_kind(q->kind, [&](auto K) {
+        k_delta_export_dense<decltype(K)::value><<<grid_for(q->cap, 128), 128, 0, st>>>(view_of(q), q->base_keys, q->base_q, delta_out);
+        return launch_check("k_delta_export_dense");
+    });
+}
+
+extern "C" int sgk_tabq_delta_apply_dense(sgk_tabq *q, const double *delta_sum, double scale, void *stream)
+{
+    REQUIRE(q != nullptr && delta_sum != nullptr, "bad argument");
+    const int64_t n = sgk_tabq_dense_size(q);
+    REQUIRE(n > 0, "this table has no dense canonical index (tomato, or not a shared table)");
+    DeviceGuard g(q->device);
+    int rc = sgk_tabq_restore_base(q, stream);
+    if (rc != SGK_OK) return rc;
+    rc = by_kind(q->kind, [&](auto K) {
+        k_delta_apply_dense<decltype(K)::value><<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(view_of(q), delta_sum, scale, q->status);
+        return launch_check("k_delta_apply_dense");
+    });
+    if (rc != SGK_OK) return rc;
+    return sgk_tabq_rebase(q, stream);
+}
+
 extern "C" int sgk_tabq_rebase(sgk_tabq *q, void *stream)
 {
     REQUIRE(q != nullptr && q->q_mode == SGK_Q_SHARED, "replica sync applies to shared tables");
@@ -1581,6 +1946,179 @@ extern "C" int sgk_tabq_restore_base(sgk_tabq *q, void *stream)
     return SGK_OK;
 }
 
+// ===================================================================== table growth
+static int table_max_fill(sgk_tabq *q, cudaStream_t st, int64_t *out)
+{
+    if (!q->fill_scratch) CU(cudaMalloc(&q->fill_scratch, sizeof(int)));
+    CU(cudaMemsetAsync(q->fill_scratch, 0, sizeof(int), st));
+    const TableView T = view_of(q);
+    const int contiguous = (q->table_major || q->n_tables == 1) ? 1 : 0;
+    const int64_t threads = contiguous ? q->n_tables * 32 : q->n_tables;
+    k_table_fill<<<grid_for(threads, 256), 256, 0, st>>>(T, contiguous, q->fill_scratch);
+    int rc = launch_check("k_table_fill");
+    if (rc != SGK_OK) return rc;
+    int fill = 0;
+    CU(cudaMemcpyAsync(&fill, q->fill_scratch, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out = fill;
+    return SGK_OK;
+}
+
+static int grow_tables(sgk_tabq *q, int64_t new_cap, cudaStream_t st)
+{
+    REQUIRE(q->q_mode == SGK_Q_PRIVATE && !q->dense_open, "only hashed private tables grow");
+    REQUIRE(new_cap > q->cap && (new_cap & (new_cap - 1)) == 0, "new capacity must be a larger power of two");
+    if ((uint64_t)new_cap * (uint64_t)q->n_tables >= (1ull << 32))
+        return fail(SGK_EFULL, "a Q table is full and cannot grow: capacity x tables would reach 2^32 slots");
+    const size_t slots = (size_t)new_cap * (size_t)q->n_tables;
+    unsigned long long *keys = nullptr;
+    double *rows = nullptr, *c = nullptr;
+    bool ok = cudaMalloc(&keys, slots * 8) == cudaSuccess && cudaMalloc(&rows, slots * 8 * SGK_NA) == cudaSuccess &&
+              (!q->c || cudaMalloc(&c, slots * 8) == cudaSuccess);
+    if (!ok) {
+        cudaGetLastError();
+        if (keys) cudaFree(keys);
+        if (rows) cudaFree(rows);
+        if (c) cudaFree(c);
+        return fail(SGK_EFULL, "a Q table is full and device memory is exhausted growing " + std::to_string(q->n_tables) +
+                                   " tables to " + std::to_string(new_cap) + " slots (" + std::to_string(slots * 48 >> 20) + " MiB)");
+    }
+    CU(cudaMemsetAsync(keys, 0, slots * 8, st));
+    CU(cudaMemsetAsync(rows, 0, slots * 8 * SGK_NA, st));
+    if (c) {
+        k_fill_f64<<<148 * 4, 256, 0, st>>>(c, (int64_t)slots, q->c_prior);
+        int rc = launch_check("k_fill_f64");
+        if (rc != SGK_OK) return rc;
+    }
+    const TableView Old = view_of(q);
+    const int old_major = q->table_major;
+    sgk_tabq grown = *q;
+    grown.keys = keys; grown.q = rows; grown.c = c; grown.cap = new_cap;
+    grown.log_cap = 0;
+    while ((1ll << grown.log_cap) < new_cap) grown.log_cap++;
+    grown.table_major = new_cap > 512 ? 1 : 0;
+    const TableView New = view_of(&grown);
+    k_table_rehash<<<grid_for((int64_t)q->cap * q->n_tables, 256), 256, 0, st>>>(Old, old_major, New, q->status);
+    int rc = launch_check("k_table_rehash");
+    if (rc == SGK_OK && q->ssrl && q->ssrl_hist && q->env_core) {
+        k_hist_remap<<<grid_for(q->n_envs, 256), 256, 0, st>>>(Old, New, q->env_core, q->ssrl_hist, q->ssrl_hist_len, q->n_envs);
+        rc = launch_check("k_hist_remap");
+    }
+    if (rc == SGK_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(SGK_ECUDA, "table growth failed");
+    if (rc != SGK_OK) { cudaFree(keys); cudaFree(rows); if (c) cudaFree(c); return rc; }
+    cudaFree(q->keys); cudaFree(q->q);
+    if (q->c) cudaFree(q->c);
+    q->keys = keys; q->q = rows; q->c = c; q->cap = new_cap; q->log_cap = grown.log_cap; q->table_major = grown.table_major;
+    return SGK_OK;
+}
+
+// Make room for up to `want` insertions per table; *granted (>= 1) is how many
+// are guaranteed to fit now.  Hashed private tables above 512 slots are kept
+// below 3/4 full (short probe sequences), smaller ones may fill completely.
+static int reserve_slots(sgk_tabq *q, int64_t want, int64_t at_least, cudaStream_t st, int64_t *granted)
+{
+    *granted = want;
+    if (q->q_mode != SGK_Q_PRIVATE || q->dense_open || !q->auto_grow) return SGK_OK;
+    auto limit = [&]() { return q->cap > 512 ? q->cap - q->cap / 4 : q->cap; };
+    if (q->max_states > 0 && q->max_states <= limit()) return SGK_OK;     // can hold every observation there is
+    if (limit() - q->fill_ub >= want) { q->fill_ub += want; return SGK_OK; }
+    int64_t exact = 0;
+    int rc = table_max_fill(q, st, &exact);
+    if (rc != SGK_OK) return rc;
+    while (2 * exact > q->cap || limit() - exact < at_least) {
+        rc = grow_tables(q, q->cap * 2, st);
+        if (rc != SGK_OK) return rc;
+    }
+    const int64_t room = limit() - exact;
+    *granted = want < room ? want : room;
+    q->fill_ub = exact + *granted;
+    return SGK_OK;
+}
+
+extern "C" int sgk_tabq_max_fill(sgk_tabq *q, int64_t *max_fill_out, void *stream)
+{
+    REQUIRE(q != nullptr && max_fill_out != nullptr, "bad argument");
+    DeviceGuard g(q->device);
+    return table_max_fill(q, (cudaStream_t)stream, max_fill_out);
+}
+
+extern "C" int sgk_tabq_set_auto_grow(sgk_tabq *q, int enabled)
+{
+    REQUIRE(q != nullptr, "q is NULL");
+    q->auto_grow = enabled ? 1 : 0;
+    return SGK_OK;
+}
+
+extern "C" int sgk_tabq_grow(sgk_tabq *q, int64_t new_capacity, void *stream)
+{
+    REQUIRE(q != nullptr, "q is NULL");
+    DeviceGuard g(q->device);
+    return grow_tables(q, new_capacity, (cudaStream_t)stream);
+}
+
+__global__ void k_ssrl_counters(const int *budget, const unsigned long long *counts, int64_t n, int64_t *b_out, int64_t *e_out,
+                                int64_t *c_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (b_out) b_out[i] = budget[i];
+    if (e_out) e_out[i] = (int64_t)(counts[i] & 0xFFFFFFFFull);
+    if (c_out) c_out[i] = (int64_t)(counts[i] >> 32);
+}
+
+// The method-level SSRL API of the N = 1 adapter: learn_C over a host-kept
+// history (ssrl/agents.py:50-75) followed by reset_history (:77-82); `query`
+// != 0 first spends one unit of budget (query_H, :45-48).  One thread walks
+// the history in order, so a state visited k times is scaled k times, exactly
+// like the reference's loop over `_history`.
+template <int KIND>
+__global__ void k_ssrl_learn_c(const __grid_constant__ Level L, const TableView T, int64_t table, const uint8_t *boards,
+                               int64_t n_boards, int corrupt, int query, int increment_episode, int *budget,
+                               unsigned long long *counts, int *status)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const unsigned long long cnt = counts[table];
+    const unsigned long long episodes = cnt & 0xFFFFFFFFull, corrupt_eps = cnt >> 32;
+    if (query) budget[table] -= 1;
+    const double factor = corrupt ? __ddiv_rn((double)episodes, (double)(corrupt_eps + 1)) : 0.0;
+    for (int64_t k = 0; k < n_boards; k++) {
+        const uint64_t key = board_key<KIND>(L, boards + k * KindCells<KIND>::value);
+        const uint32_t slot = find_private(T, (uint32_t)table, key, status);     // C is a defaultdict too (agents.py:21)
+        if (slot == SGK_NOSLOT) continue;
+        double *c = T.c + entry(T, slot, (uint32_t)table);
+        *c = __dmul_rn(*c, factor);
+    }
+    counts[table] = (episodes + (increment_episode ? 1 : 0)) | ((corrupt_eps + (corrupt ? 1 : 0)) << 32);
+}
+
+extern "C" int sgk_ssrl_learn_c(sgk_tabq *q, int64_t table, const uint8_t *boards, int64_t n_boards, int corrupt, int query,
+                                int increment_episode, void *stream)
+{
+    REQUIRE(q != nullptr && q->ssrl, "SSRL is not enabled on this table");
+    REQUIRE(table >= 0 && table < q->n_tables && n_boards >= 0 && (n_boards == 0 || boards != nullptr), "bad argument");
+    DeviceGuard g(q->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t granted = 0;
+    int rc = reserve_slots(q, n_boards > 0 ? n_boards : 1, n_boards > 0 ? n_boards : 1, st, &granted);
+    if (rc != SGK_OK) return rc;
+    Level L;
+    make_level(q->kind, L);
+    return by_kind(q->kind, [&](auto K) {
+        k_ssrl_learn_c<decltype(K)::value><<<1, 32, 0, st>>>(L, view_of(q), table, boards, n_boards, corrupt, query, increment_episode,
+                                                             q->ssrl_budget, q->ssrl_counts, q->status);
+        return launch_check("k_ssrl_learn_c");
+    });
+}
+
+extern "C" int sgk_ssrl_get_counters(const sgk_tabq *q, int64_t *budget, int64_t *episodes, int64_t *corrupt_episodes, void *stream)
+{
+    REQUIRE(q != nullptr && q->ssrl, "SSRL is not enabled on this table");
+    DeviceGuard g(q->device);
+    k_ssrl_counters<<<grid_for(q->n_envs, 256), 256, 0, (cudaStream_t)stream>>>(q->ssrl_budget, q->ssrl_counts, q->n_envs, budget,
+                                                                             episodes, corrupt_episodes);
+    return launch_check("k_ssrl_counters");
+}
+
 // ===================================================================== C ABI: fused rollouts
 static int ensure_thresholds(sgk_tabq *q, int64_t n_steps, uint64_t t0, cudaStream_t st)
 {
@@ -1597,7 +2135,7 @@ static RolloutArgs rollout_args(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint
     if (q) {
         a.T = view_of(q); a.thr = q->thr; a.lr = q->lr; a.discount = q->discount; a.pub_target = q->pub_target;
         a.c_prior = q->c_prior; a.ssrl_hist = q->ssrl_hist; a.ssrl_hist_len = q->ssrl_hist_len;
-        a.ssrl_budget = q->ssrl_budget; a.ssrl_counts = q->ssrl_counts;
+        a.ssrl_budget = q->ssrl_budget; a.ssrl_counts = q->ssrl_counts; a.ssrl_visits = q->ssrl_visits;
     }
     return a;
 }
@@ -1644,19 +2182,24 @@ static int launch_shared(const RolloutArgs &a, cudaStream_t st)
     return rc;
 }
 
-extern "C" int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat, void *stream)
+// episodic-mode extras of one launch (all optional; see RolloutArgs)
+struct EpisodicArgs {
+    int64_t max_episodes = 0;
+    long long *steps_done = nullptr;
+    double *last_reward = nullptr, *last_hidden = nullptr;
+};
+
+// one launch of the fused kernel over lock-steps [t0, t0 + n_steps); thresholds
+// for them start at q->thr + thr_offset
+static int launch_rollout(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int64_t thr_offset, int cheat,
+                          const EpisodicArgs &ep, cudaStream_t st)
 {
-    REQUIRE(env != nullptr && q != nullptr, "env or q is NULL");
-    REQUIRE(env->device == q->device && env->level.kind == q->kind && env->n == q->n_envs, "table was created for a different environment object");
-    REQUIRE(n_steps > 0, "n_steps must be positive");
-    DeviceGuard g(env->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc = ensure_thresholds(q, n_steps, t0, st);
-    if (rc != SGK_OK) return rc;
-    const RolloutArgs a = rollout_args(env, q, n_steps, t0, cheat);
-    const unsigned grid = grid_for(env->n, SGK_BLOCK);
+    RolloutArgs a = rollout_args(env, q, n_steps, t0, cheat);
+    a.thr = q->thr + thr_offset;
+    a.max_episodes = ep.max_episodes; a.steps_done = ep.steps_done;
+    a.last_reward = ep.last_reward; a.last_hidden = ep.last_hidden;
     const bool replay = env->rng_mode == SGK_RNG_REPLAY;
-    const bool trace = env->trace != 0;
+    const bool trace = env->trace != 0 || ep.max_episodes > 0;       // episodic mode lives in the TRACE builds
     const bool ssrl = q->ssrl != 0;
     const bool shared = q->q_mode == SGK_Q_SHARED;
     return by_kind(env->level.kind, [&](auto K) {
@@ -1696,15 +2239,69 @@ extern "C" int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint
     });
 }
 
-extern "C" int sgk_rollout_random(sgk_env *env, int64_t n_steps, uint64_t t0, void *stream)
+static int rollout_checks(sgk_env *env, sgk_tabq *q)
 {
-    REQUIRE(env != nullptr && n_steps > 0, "bad argument");
+    REQUIRE(env != nullptr && q != nullptr, "env or q is NULL");
+    REQUIRE(env->device == q->device && env->level.kind == q->kind && env->n == q->n_envs, "table was created for a different environment object");
+    return SGK_OK;
+}
+
+extern "C" int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t0, int cheat, void *stream)
+{
+    int rc = rollout_checks(env, q);
+    if (rc != SGK_OK) return rc;
+    REQUIRE(n_steps > 0, "n_steps must be positive");
     DeviceGuard g(env->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const RolloutArgs a = rollout_args(env, nullptr, n_steps, t0, 0);
+    rc = ensure_thresholds(q, n_steps, t0, st);
+    if (rc != SGK_OK) return rc;
+    // Hashed private tables grow like the reference's dict: a lock-step inserts
+    // at most two keys per table (Q[s] on the first touch, Q[s']), so the call
+    // is cut into launches that cannot overflow, and between launches the
+    // fullest table is measured and, past half full, every table rehashed into
+    // twice the capacity.  Dense, shared and large-enough tables: one launch.
+    int64_t done = 0;
+    while (done < n_steps) {
+        int64_t granted = 0;
+        rc = reserve_slots(q, 2 * (n_steps - done), 2, st, &granted);
+        if (rc != SGK_OK) return rc;
+        const int64_t chunk = granted / 2;
+        rc = launch_rollout(env, q, chunk, t0 + (uint64_t)done, done, cheat, EpisodicArgs(), st);
+        if (rc != SGK_OK) return rc;
+        done += chunk;
+    }
+    return SGK_OK;
+}
+
+extern "C" int sgk_rollout_tabq_episodes(sgk_env *env, sgk_tabq *q, int64_t max_episodes, int64_t max_steps, uint64_t t0,
+                                         int cheat, int64_t *steps_done, double *last_reward, double *last_hidden,
+                                         void *stream)
+{
+    int rc = rollout_checks(env, q);
+    if (rc != SGK_OK) return rc;
+    REQUIRE(max_episodes > 0 && max_steps > 0, "max_episodes and max_steps must be positive");
+    REQUIRE(q->q_mode == SGK_Q_PRIVATE, "episodic rollouts need private tables (environments stop independently)");
+    DeviceGuard g(env->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = ensure_thresholds(q, max_steps, t0, st);
+    if (rc != SGK_OK) return rc;
+    int64_t granted = 0;
+    rc = reserve_slots(q, 2 * max_steps, 2 * max_steps, st, &granted);
+    if (rc != SGK_OK) return rc;
+    EpisodicArgs ep;
+    ep.max_episodes = max_episodes; ep.steps_done = reinterpret_cast<long long *>(steps_done);
+    ep.last_reward = last_reward; ep.last_hidden = last_hidden;
+    return launch_rollout(env, q, max_steps, t0, 0, cheat, ep, st);
+}
+
+static int launch_random(sgk_env *env, sgk_tabq *q_warm, int64_t n_steps, uint64_t t0, const EpisodicArgs &ep, cudaStream_t st)
+{
+    RolloutArgs a = rollout_args(env, nullptr, n_steps, t0, 0);
+    a.max_episodes = ep.max_episodes; a.steps_done = ep.steps_done;
+    if (q_warm) { a.ssrl_budget = q_warm->ssrl_budget; a.ssrl_counts = q_warm->ssrl_counts; }
     const unsigned grid = grid_for(env->n, SGK_BLOCK);
     const bool replay = env->rng_mode == SGK_RNG_REPLAY;
-    const bool trace = env->trace != 0;
+    const bool trace = env->trace != 0 || ep.max_episodes > 0;
     return by_kind(env->level.kind, [&](auto K) {
         constexpr int KIND = decltype(K)::value;
         if (replay) k_rollout_random<KIND, ReplayStream, true><<<grid, SGK_BLOCK, 0, st>>>(a);
@@ -1712,6 +2309,26 @@ extern "C" int sgk_rollout_random(sgk_env *env, int64_t n_steps, uint64_t t0, vo
         else k_rollout_random<KIND, PhiloxStream, false><<<grid, SGK_BLOCK, 0, st>>>(a);
         return launch_check("k_rollout_random");
     });
+}
+
+extern "C" int sgk_rollout_random(sgk_env *env, int64_t n_steps, uint64_t t0, void *stream)
+{
+    REQUIRE(env != nullptr && n_steps > 0, "bad argument");
+    DeviceGuard g(env->device);
+    return launch_random(env, nullptr, n_steps, t0, EpisodicArgs(), (cudaStream_t)stream);
+}
+
+extern "C" int sgk_ssrl_warmup(sgk_env *env, sgk_tabq *q, int64_t n_episodes, uint64_t t0, int64_t *steps_done, void *stream)
+{
+    int rc = rollout_checks(env, q);
+    if (rc != SGK_OK) return rc;
+    REQUIRE(q->ssrl, "enable SSRL first (sgk_tabq_enable_ssrl)");
+    REQUIRE(n_episodes >= 0, "n_episodes must be >= 0");
+    if (n_episodes == 0) return SGK_OK;
+    DeviceGuard g(env->device);
+    EpisodicArgs ep;
+    ep.max_episodes = n_episodes; ep.steps_done = reinterpret_cast<long long *>(steps_done);
+    return launch_random(env, q, n_episodes * env->level.max_iterations, t0, ep, (cudaStream_t)stream);
 }
 
 extern "C" int sgk_env_clear_stats(sgk_env *env, void *stream)
@@ -1729,12 +2346,27 @@ extern "C" int sgk_env_clear_stats(sgk_env *env, void *stream)
 
 extern "C" int sgk_eval_tabq(sgk_env *eval_env, const sgk_tabq *q, int64_t eval_timesteps, uint64_t t0, void *stream)
 {
+    return sgk_eval_tabq_ex(eval_env, const_cast<sgk_tabq *>(q), eval_timesteps, t0, 0, nullptr, 0, stream);
+}
+
+extern "C" int sgk_eval_tabq_ex(sgk_env *eval_env, sgk_tabq *q, int64_t eval_timesteps, uint64_t t0, int insert_on_miss,
+                                double *episode_log, int64_t log_cap, void *stream)
+{
     REQUIRE(eval_env != nullptr && q != nullptr, "env or q is NULL");
+    REQUIRE(!insert_on_miss || q->q_mode == SGK_Q_PRIVATE, "insert_on_miss needs private tables");
+    REQUIRE(episode_log == nullptr || log_cap > 0, "episode_log needs log_cap > 0");
     REQUIRE(eval_env->device == q->device && eval_env->level.kind == q->kind, "table belongs to a different kind of environment");
     REQUIRE(q->q_mode == SGK_Q_SHARED || eval_env->n <= q->n_tables, "more evaluation environments than private tables");
     REQUIRE(eval_timesteps > 0, "eval_timesteps must be positive");
     DeviceGuard g(eval_env->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (insert_on_miss) {
+        // one possible insertion per evaluation step
+        const int64_t steps = eval_timesteps + eval_env->level.max_iterations;
+        int64_t granted = 0;
+        int rc0 = reserve_slots(q, steps, steps, st, &granted);
+        if (rc0 != SGK_OK) return rc0;
+    }
     RolloutArgs a = rollout_args(eval_env, nullptr, 1, t0, 0);
     a.T = view_of(q);
     const unsigned grid = grid_for(eval_env->n, SGK_BLOCK);
@@ -1742,8 +2374,8 @@ extern "C" int sgk_eval_tabq(sgk_env *eval_env, const sgk_tabq *q, int64_t eval_
     const int shared = q->q_mode == SGK_Q_SHARED;
     return by_kind(eval_env->level.kind, [&](auto K) {
         constexpr int KIND = decltype(K)::value;
-        if (replay) k_eval_tabq<KIND, ReplayStream><<<grid, SGK_BLOCK, 0, st>>>(a, eval_timesteps, shared);
-        else k_eval_tabq<KIND, PhiloxStream><<<grid, SGK_BLOCK, 0, st>>>(a, eval_timesteps, shared);
+        if (replay) k_eval_tabq<KIND, ReplayStream><<<grid, SGK_BLOCK, 0, st>>>(a, eval_timesteps, shared, insert_on_miss, episode_log, log_cap);
+        else k_eval_tabq<KIND, PhiloxStream><<<grid, SGK_BLOCK, 0, st>>>(a, eval_timesteps, shared, insert_on_miss, episode_log, log_cap);
         return launch_check("k_eval_tabq");
     });
 }

@@ -70,8 +70,12 @@ __device__ __forceinline__ uint32_t find_private(const TableView &T, uint32_t g,
         if (k == 0ull) { *p = key; return s; }
         s = (s + 1) & (T.cap - 1);
     }
+    // Full: the state reads as an unseen one (zero row) and is not written;
+    // the sticky status makes the next synchronising call fail with SGK_EFULL.
+    // (The host grows hashed private tables ahead of time, sgk_tabq_grow, so
+    // this is reached only when device memory is exhausted.)
     *status = SGK_ST_FULL;
-    return 0;
+    return SGK_NOSLOT;
 }
 
 // find-or-insert in a table many threads probe concurrently
@@ -86,7 +90,7 @@ __device__ __forceinline__ uint32_t find_shared(const TableView &T, uint64_t key
         s = (s + 1) & (T.cap - 1);
     }
     *status = SGK_ST_FULL;
-    return 0;
+    return SGK_NOSLOT;
 }
 
 // lookup without insertion; returns false when absent
@@ -108,8 +112,10 @@ __device__ __forceinline__ bool lookup(const TableView &T, uint32_t g, uint64_t 
 
 struct QRow { double v0, v1, v2, v3; };
 
+// slot == SGK_NOSLOT (table full): the row of a state the table could not take
 __device__ __forceinline__ QRow load_row(const TableView &T, uint32_t g, uint32_t slot)
 {
+    if (slot == SGK_NOSLOT) return QRow{0.0, 0.0, 0.0, 0.0};
     const double2 *p = reinterpret_cast<const double2 *>(T.q + entry(T, slot, g) * SGK_NA);
     const double2 a = p[0], b = p[1];
     QRow r; r.v0 = a.x; r.v1 = a.y; r.v2 = b.x; r.v3 = b.y;
@@ -118,6 +124,7 @@ __device__ __forceinline__ QRow load_row(const TableView &T, uint32_t g, uint32_
 
 __device__ __forceinline__ void store_q(const TableView &T, uint32_t g, uint32_t slot, int a, double v)
 {
+    if (slot == SGK_NOSLOT) return;
     T.q[entry(T, slot, g) * SGK_NA + a] = v;
 }
 

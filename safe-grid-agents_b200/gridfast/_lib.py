@@ -56,12 +56,25 @@ SYMBOLS = [
     ("sgk_tabq_act", _i32, [_vp, _vp, _vp, _i64, _u64, _i32, _vp, _vp]),
     ("sgk_tabq_learn", _i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     ("sgk_board_to_key", _i32, [_vp, _vp, _vp, _i64, _vp]),
+    ("sgk_key_to_board", _i32, [_vp, _vp, _vp, _i64, _vp]),
+    ("sgk_env_max_iterations", _i32, [_vp]),
+    ("sgk_tabq_set_auto_grow", _i32, [_vp, _i32]),
+    ("sgk_tabq_max_fill", _i32, [_vp, ctypes.POINTER(ctypes.c_int64), _vp]),
+    ("sgk_tabq_grow", _i32, [_vp, _i64, _vp]),
+    ("sgk_ssrl_warmup", _i32, [_vp, _vp, _i64, _u64, _vp, _vp]),
+    ("sgk_ssrl_get_counters", _i32, [_vp, _vp, _vp, _vp, _vp]),
+    ("sgk_ssrl_learn_c", _i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp]),
+    ("sgk_rollout_tabq_episodes", _i32, [_vp, _vp, _i64, _i64, _u64, _i32, _vp, _vp, _vp, _vp]),
+    ("sgk_eval_tabq_ex", _i32, [_vp, _vp, _i64, _u64, _i32, _vp, _i64, _vp]),
     ("sgk_tabq_export", _i32, [_vp, _i64, _vp, _vp, _vp, _vp]),
     ("sgk_tabq_import", _i32, [_vp, _i64, _vp, _vp, _vp]),
     ("sgk_tabq_delta_export", _i32, [_vp, _vp, _vp, _vp]),
     ("sgk_tabq_delta_apply", _i32, [_vp, _vp, _vp, _dbl, _vp]),
     ("sgk_tabq_rebase", _i32, [_vp, _vp]),
     ("sgk_tabq_restore_base", _i32, [_vp, _vp]),
+    ("sgk_tabq_dense_size", _i64, [_vp]),
+    ("sgk_tabq_delta_export_dense", _i32, [_vp, _vp, _vp]),
+    ("sgk_tabq_delta_apply_dense", _i32, [_vp, _vp, _dbl, _vp]),
     ("sgk_tabq_enable_ssrl", _i32, [_vp, _dbl, _i64, _i64]),
     ("sgk_rollout_tabq", _i32, [_vp, _vp, _i64, _u64, _i32, _vp]),
     ("sgk_rollout_random", _i32, [_vp, _i64, _u64, _vp]),

@@ -146,6 +146,19 @@ class BatchedEnv:
         check(self.L.sgk_board_to_key(self.h, _p(boards), _p(out), n, _stream()))
         return out
 
+    def keys_to_boards(self, keys):
+        """The boards table keys stand for (keys are lossless): int64 cuda
+        tensor [n] -> uint8 [n, HW]."""
+        keys = keys.contiguous()
+        n = keys.shape[0]
+        out = self._u8(n, self.hw)
+        check(self.L.sgk_key_to_board(self.h, _p(keys), _p(out), n, _stream()))
+        return out
+
+    @property
+    def max_iterations(self):
+        return self.L.sgk_env_max_iterations(self.h)
+
     # -- bookkeeping -----------------------------------------------------------
     def stats(self):
         """Per-environment episode bookkeeping as a dict of cuda tensors."""
@@ -157,6 +170,15 @@ class BatchedEnv:
         st = EnvStats(**{k: v.data_ptr() for k, v in {**f, **i}.items()})
         check(self.L.sgk_env_get_stats(self.h, ctypes.byref(st), _stream()))
         return {**f, **i}
+
+    def stats_brief(self):
+        """[3, n] float64: episode_return, last_return, last_performance (NaN =
+        None) -- what track_metrics reads through env._env (meters.py:76-80)."""
+        out = self._f64(3, self.n)
+        st = EnvStats(episode_return=out[0].data_ptr(), last_return=out[1].data_ptr(),
+                      last_performance=out[2].data_ptr())
+        check(self.L.sgk_env_get_stats(self.h, ctypes.byref(st), _stream()))
+        return out[:, 0] if self.n == 1 else out
 
     def totals(self):
         """Deterministic totals over all copies (synchronises)."""
@@ -196,9 +218,27 @@ class BatchedTabularQ:
         self.h = ctypes.c_void_p()
         with torch.cuda.device(env.device):
             check(self.L.sgk_tabq_create(env.h, q_mode, capacity, ctypes.byref(self.h)))
-        self.capacity = self.L.sgk_tabq_capacity(self.h)
         self.n_tables = self.L.sgk_tabq_tables(self.h)
         self.configure(lr, discount, epsilon, epsilon_anneal)
+
+    @property
+    def capacity(self):
+        """Slots per table right now (hashed private tables grow on demand)."""
+        return self.L.sgk_tabq_capacity(self.h)
+
+    def set_auto_grow(self, enabled=True):
+        """On (default): tables grow like the reference's dict.  Off: fixed
+        capacity, an overflow raises SgkError (SGK_EFULL) at the next check()."""
+        check(self.L.sgk_tabq_set_auto_grow(self.h, int(enabled)))
+
+    def max_fill(self):
+        """Key count of the fullest table (synchronises)."""
+        out = ctypes.c_int64()
+        check(self.L.sgk_tabq_max_fill(self.h, ctypes.byref(out), _stream()))
+        return out.value
+
+    def grow(self, new_capacity):
+        check(self.L.sgk_tabq_grow(self.h, new_capacity, _stream()))
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
@@ -210,7 +250,27 @@ class BatchedTabularQ:
         check(self.L.sgk_tabq_configure(self.h, lr, discount, epsilon, epsilon_anneal))
 
     def enable_ssrl(self, c_prior, budget, max_episode_steps=100):
+        """TabularSSQAgent.__init__ (ssrl/agents.py:16-27): C prior, query budget."""
         check(self.L.sgk_tabq_enable_ssrl(self.h, c_prior, budget, max_episode_steps))
+
+    def ssrl_warmup(self, n_episodes, t0=None, want_steps=False):
+        """ssrl.random_warmup (ssrl/warmup.py:4-35), batched: `n_episodes`
+        random-policy episodes per environment, query_H + learn_C after each.
+        Leaves every environment finished-and-not-reset, like the reference.
+        The warm-up's lock-steps are indexed from `t0` (default: a region of
+        the counter space training never reaches, so Philox draws are not
+        reused when training then starts from agent-step 0)."""
+        t0 = (1 << 40) if t0 is None else t0
+        steps = torch.zeros(self.env.n, dtype=torch.int64, device=self.env.device) if want_steps else None
+        check(self.L.sgk_ssrl_warmup(self.env.h, self.h, n_episodes, t0, _p(steps), _stream()))
+        return steps
+
+    def ssrl_counters(self):
+        """(budget, episodes, corrupt_episodes) per environment, int64 cuda tensors."""
+        dev = self.env.device
+        out = [torch.empty(self.env.n, dtype=torch.int64, device=dev) for _ in range(3)]
+        check(self.L.sgk_ssrl_get_counters(self.h, _p(out[0]), _p(out[1]), _p(out[2]), _stream()))
+        return tuple(out)
 
     def epsilon_at(self, k):
         return self.L.sgk_tabq_epsilon_at(self.h, k)
@@ -230,6 +290,22 @@ class BatchedTabularQ:
         check(self.L.sgk_rollout_tabq(self.env.h, self.h, n_steps, self.env.t, int(cheat), _stream()))
         self.env.t += n_steps
 
+    def rollout_episodes(self, max_episodes=1, max_steps=None, cheat=False, t0=None):
+        """The fused path episode-wise (one reference call of tabq_learn =
+        whiler.stepbystep, common/learn.py:13-24, per episode): every
+        environment runs `max_episodes` episodes and is left un-reset.  Returns
+        (steps int64 [n], last reward f64 [n], last hidden f64 [n] (NaN = None))
+        as cuda tensors; the agent-step clock advances by max(steps) when N = 1."""
+        dev = self.env.device
+        max_steps = max_episodes * self.env.max_iterations if max_steps is None else max_steps
+        steps = torch.zeros(self.env.n, dtype=torch.int64, device=dev)
+        reward = torch.zeros(self.env.n, dtype=torch.float64, device=dev)
+        hidden = torch.zeros(self.env.n, dtype=torch.float64, device=dev)
+        t0 = self.env.t if t0 is None else t0
+        check(self.L.sgk_rollout_tabq_episodes(self.env.h, self.h, max_episodes, max_steps, t0, int(cheat),
+                                               _p(steps), _p(reward), _p(hidden), _stream()))
+        return steps, reward, hidden
+
     def check(self):
         check(self.L.sgk_check(self.env.h, self.h, _stream()))
 
@@ -241,8 +317,21 @@ class BatchedTabularQ:
         eval_env.clear_stats()
         eval_env.reset(step=eval_env.t, want_boards=False)
         check(self.L.sgk_eval_tabq(eval_env.h, self.h, eval_timesteps, eval_env.t, _stream()))
-        eval_env.t += eval_timesteps + 100
+        eval_env.t += eval_timesteps + eval_env.max_iterations
         return summarize_totals(eval_env.totals())
+
+    def evaluate_logged(self, eval_env, eval_timesteps, insert_on_miss=True):
+        """default_eval for the drop-in adapters: `eval_env` must already be
+        reset; act() inserts unseen boards like the reference's defaultdict
+        (value.py:31,35); returns the (return, performance) pairs of the
+        evaluation episodes of environment 0 in order (host numpy [m, 2])."""
+        cap = eval_timesteps + eval_env.max_iterations
+        log = torch.full((eval_env.n, cap, 2), float("nan"), dtype=torch.float64, device=eval_env.device)
+        check(self.L.sgk_eval_tabq_ex(eval_env.h, self.h, eval_timesteps, eval_env.t, int(insert_on_miss),
+                                      _p(log), cap, _stream()))
+        eval_env.t += cap
+        rows = log[0].cpu().numpy()
+        return rows[~np.isnan(rows[:, 0])]
 
     def export(self, table=0, with_corruption=False):
         """(keys int64 [m], rows f64 [m,4]) of the occupied slots (host numpy)."""
@@ -278,6 +367,19 @@ class BatchedTabularQ:
 
     def rebase(self):
         check(self.L.sgk_tabq_rebase(self.h, _stream()))
+
+    def dense_size(self):
+        """Entries of the canonical dense delta array (0: none, use the key/delta records)."""
+        return self.L.sgk_tabq_dense_size(self.h)
+
+    def delta_export_dense(self, out=None):
+        n = self.dense_size()
+        out = torch.empty(n, 5, dtype=torch.float64, device=self.env.device) if out is None else out
+        check(self.L.sgk_tabq_delta_export_dense(self.h, _p(out), _stream()))
+        return out
+
+    def delta_apply_dense(self, delta_sum, scale):
+        check(self.L.sgk_tabq_delta_apply_dense(self.h, _p(delta_sum), float(scale), _stream()))
 
     def restore_base(self):
         check(self.L.sgk_tabq_restore_base(self.h, _stream()))

@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-shared",
     "--threads", "2",           # the two translation units compile side by side
+    "--split-compile", "0",     # ... and each one's kernels are optimised on all cores (build time 3m40 -> under 1m)
 ]
 
 

@@ -27,6 +27,8 @@ class BatchedDeepQ:
         self.n_params = self.L.sgk_dqn_param_count(self.h)
         self.dims = [env.hw] + [n_hidden] * n_layers + [env.n_actions]
         self.batch_size = batch_size
+        self.replay_capacity = replay_capacity
+        self._added = 0            # transitions appended so far (ReplayBuffer.add calls)
         self.configure(lr, discount, epsilon, epsilon_anneal, sync_every, reference_bxb_loss)
 
     def __del__(self):
@@ -82,6 +84,7 @@ class BatchedDeepQ:
         return self.q_values(boards).argmax(1).to(torch.uint8)
 
     def replay_add(self, s, a, r, s2, term):
+        self._added += s.shape[0]
         check(self.L.sgk_dqn_replay_add(self.h, _p(s), _p(a), _p(r), _p(s2), _p(term), s.shape[0], _stream()))
 
     def replay_rows(self, first, n):
@@ -99,6 +102,16 @@ class BatchedDeepQ:
     def replay_count(self):
         return self.L.sgk_dqn_replay_count(self.h)
 
+    @property
+    def replay_position(self):
+        """Ring row the next transition of environment 0 is written to."""
+        return self._added % self.replay_capacity
+
+    def last_scalars_device(self):
+        out = torch.empty(3, dtype=torch.float32, device=self.env.device)
+        check(self.L.sgk_dqn_last_scalars(self.h, _p(out), _stream()))
+        return out
+
     def learn(self, step):
         out = torch.empty(3, dtype=torch.float32, device=self.env.device)
         check(self.L.sgk_dqn_learn(self.h, step, _p(out), _stream()))
@@ -113,6 +126,7 @@ class BatchedDeepQ:
     def warmup(self, n_steps):
         """dqn_warmup: random-policy lock-steps that only fill the ring."""
         check(self.L.sgk_rollout_dqn(self.env.h, self.h, n_steps, self.env.t, 0, _stream()))
+        self._added += n_steps * self.env.n
         self.env.t += n_steps
 
     def rollout(self, n_steps, cheat=False):
@@ -120,6 +134,7 @@ class BatchedDeepQ:
         `cheat` = args.cheat (learn.py:39-47): learn from the hidden reward and
         the action really executed."""
         check(self.L.sgk_rollout_dqn(self.env.h, self.h, n_steps, self.env.t, 1 | (2 if cheat else 0), _stream()))
+        self._added += n_steps * self.env.n
         self.env.t += n_steps
 
     def last_scalars(self):

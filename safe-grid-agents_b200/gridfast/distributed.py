@@ -5,9 +5,13 @@ rank r owns global environment ids [r*n_local, (r+1)*n_local) and the random
 streams are keyed by global id, so a trajectory does not depend on the world
 size.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used only
 
-  * to all-reduce the 7 episode-statistics totals, and
-  * in shared-Q mode, to all-gather (key, delta-Q) records at sync intervals
-    so that every GPU's table replica stays bit-identical.
+  * to merge the 9 episode-statistics totals (one all-gather, folded locally in
+    rank order: sums and maxima from the same collective), and
+  * in shared-Q mode, at sync intervals, to merge the replicas' Q changes so
+    that every GPU's table stays bit-identical: ONE all-reduce (sum) of a
+    dense delta-Q array where the level's keys have a small canonical index
+    (boat, sokoban, lava, island, supervisor, whisky), an all-gather of
+    (key, delta-Q) records for hashed tomato tables.
 
 The table operations are reached through a small duck-typed interface
 (delta_export / restore_base / delta_apply / rebase) so the orchestration can
@@ -30,15 +34,23 @@ def shard(n_global, rank, world):
 
 
 def all_reduce_totals(totals, group=None):
-    """totals: float64 tensor [9] (sgk_env_totals layout).  Sums everywhere
-    except the maxima slots; never-finished ranks carry -inf there."""
+    """totals: float64 tensor [..., 9] (sgk_env_totals layout).  Sums everywhere
+    except the maxima slots; never-finished ranks carry -inf there.  ONE
+    collective: the rows of all ranks are gathered and folded locally in rank
+    order, so sums and maxima come out of the same exchange and every rank
+    computes bit-identical results."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return totals
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(totals) for _ in range(world)]
+    dist.all_gather(parts, totals.contiguous(), group=group)
+    gathered = torch.stack(parts)
+    folded = gathered[0].clone()
+    for g in range(1, world):
+        folded += gathered[g]
     idx = torch.tensor(_MAX_SLOTS, device=totals.device)
-    mx = totals[idx].clone()
-    dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    totals[idx] = mx
+    folded[..., idx] = gathered[..., idx].max(dim=0).values
+    totals.copy_(folded)
     return totals
 
 
@@ -49,6 +61,14 @@ def sync_shared_table(table, group=None):
     every rank, so all replicas end bit-identical (periodic averaging of the
     replicas' changes since the last sync)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dense = getattr(table, "dense_size", lambda: 0)()
+    if dense > 0:
+        # canonical dense index: one all-reduce (sum) of [dense][delta-Q x 4, presence]
+        buf = table.delta_export_dense()
+        if world > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        table.delta_apply_dense(buf, 1.0 / world)
+        return
     keys, delta = table.delta_export()
     if world == 1:
         gathered_k, gathered_d = [keys], [delta]

@@ -30,6 +30,14 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 @pytest.fixture(scope="session")
 def golden_files():
-    names = sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    names = sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("train_"))
     assert names, "golden fixtures missing"
+    return [os.path.join(GOLDEN_DIR, n) for n in names]
+
+
+@pytest.fixture(scope="session")
+def train_golden_files():
+    """Scalar logs of the reference's real train.train (tests/golden/make_train_golden.py)."""
+    names = sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("train_"))
+    assert names, "train golden fixtures missing"
     return [os.path.join(GOLDEN_DIR, n) for n in names]

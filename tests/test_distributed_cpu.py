@@ -40,6 +40,28 @@ class FakeTable:
         self.base = {k: v.copy() for k, v in self.live.items()}
 
 
+class FakeDenseTable(FakeTable):
+    """... with the canonical-index protocol (sgk_tabq_delta_export_dense /
+    _apply_dense): keys ARE their dense index here."""
+
+    def dense_size(self):
+        return self.capacity
+
+    def delta_export_dense(self):
+        out = torch.zeros(self.capacity, 5, dtype=torch.float64)
+        for k, row in self.live.items():
+            out[k, :4] = torch.tensor(row - self.base.get(k, np.zeros(4)))
+            out[k, 4] = 1.0
+        return out
+
+    def delta_apply_dense(self, delta_sum, scale):
+        self.restore_base()
+        for k in range(self.capacity):
+            if delta_sum[k, 4] > 0:
+                self.live[k] = self.live.get(k, np.zeros(4)) + scale * delta_sum[k, :4].numpy()
+        self.rebase()
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -57,7 +79,13 @@ def _worker(rank, world, port, out):
         first = {k: v.copy() for k, v in table.live.items()}
         table.live[101] = table.live[101] + np.array([0, 4.0 * rank, 0, 0])
         gd.sync_shared_table(table)
-        out.put((rank, totals.tolist(), first, table.live))
+        # the same two rounds through the dense one-all-reduce protocol
+        dense = FakeDenseTable()
+        dense.live = {1: np.array([1.0, 0, 0, 0]) * (rank + 1), 4 + rank: np.full(4, 2.0)}
+        gd.sync_shared_table(dense)
+        dense.live[1] = dense.live[1] + np.array([0, 4.0 * rank, 0, 0])
+        gd.sync_shared_table(dense)
+        out.put((rank, totals.tolist(), first, table.live, dense.live))
     finally:
         dist.destroy_process_group()
 
@@ -75,7 +103,10 @@ def test_two_rank_statistics_and_replica_sync():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, t0, first0, final0), (_, t1, first1, final1) = results
+    (_, t0, first0, final0, dense0), (_, t1, first1, final1, dense1) = results
+    for dense in (dense0, dense1):
+        assert set(dense) == {1, 4, 5}
+        assert np.array_equal(dense[1], [1.5, 2.0, 0, 0]) and np.array_equal(dense[4], np.full(4, 1.0))
     assert t0 == t1 == [21.0, -150.0, 6.0, 3.0, 4.0, -3.0, 8.0, 5.0, 2.5]
     # round 1: base empty -> mean of the replicas' values, keys unioned
     for first in (first0, first1):

@@ -323,9 +323,12 @@ def test_table_full_and_replay_dry_are_reported():
     gf = _gf()
     env = gf.BatchedEnv("TomatoWatering-v0", 64, seed=1)
     agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, capacity=8, epsilon_anneal=50)
+    agent.set_auto_grow(False)      # pinned capacity: overflow must be reported, never silently absorbed
     agent.rollout(300)
     with pytest.raises(gf.SgkError, match="ran out of slots"):
         agent.check()
+    with pytest.raises(gf.SgkError, match="ran out of slots"):
+        env.totals()                 # every synchronising call reports it
     env = gf.BatchedEnv("BoatRace-v0", 2, seed=1)
     env.set_replay_words(np.zeros((2, 10), np.uint32))
     agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE)
