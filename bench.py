@@ -10,6 +10,13 @@ environment = N independent copies of the reference's (env, agent) pair.
 One bench "step" = one fused rollout call of 10,000 lock-steps over the whole
 batch (100 episodes per environment, auto-reset) = 655,360,000 env-steps/GPU.
 
+The same line carries sub-records for the other BASELINE configurations
+(`configs`: C1 single-env drop-in, C3 sokoban 131,072 envs/GPU = 1,048,576 at
+--gpus 8, C4 tomato + SSRL with budget 1,000 / warm-up .5, C5 sokoban deep-Q)
+and, for every N, a shared-table leg (`shared_q`) whose replicas are merged
+with one NCCL all-reduce of dense delta-Q arrays per sync interval.
+Skip them with --main-only.
+
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
@@ -51,6 +58,20 @@ def recorded_traffic():
             return json.load(f)
     except Exception:
         return None
+
+
+def recorded_issue():
+    """Warp-instructions per launch of the dominant kernel, by launch index of
+    this very command, from the committed ncu capture (smsp__inst_executed.sum;
+    profiles/rollout_issue.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "rollout_issue.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+B_ALG_BY_ENV = {"BoatRace-v0": 132, "SideEffectsSokoban-v0": 158, "TomatoWatering-v0": 212}   # SURVEY 8(d); tomato incl. C[s]
 
 
 # ----------------------------------------------------------------- clocks
@@ -211,8 +232,7 @@ def run_ours(args, out):
     import torch.distributed as dist
 
     import gridfast
-    from gridfast.distributed import _MAX_SLOTS
-    MAX_COLS = list(_MAX_SLOTS)
+    from gridfast.distributed import all_reduce_totals, sync_shared_table
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -236,24 +256,23 @@ def run_ours(args, out):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    def max_over_ranks(*values):
+        t = torch.tensor(values, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
     # Private-Q rollouts need no data-path collective.  Episode statistics are
-    # kept per bench step and all-reduced (NCCL) once per sync interval -- here
-    # the K timed steps -- so ranks never wait for each other inside a step; the
-    # collective is timed as the last ("drain") segment of the region.
+    # kept per bench step and merged (NCCL, ONE all-gather folded locally) once
+    # per sync interval -- here the K timed steps -- so ranks never wait for each
+    # other inside a step; the collective is timed as the last ("drain") segment.
     def one_step(buf):
         agent.rollout(T)                      # 2 launches: thresholds + fused rollout
         env.totals_device(buf)                # 2 launches: partial + final reduction
 
-    def sync_stats(block):                   # sums, and maxima for the max_* columns
-        if world > 1:
-            maxima = block[:, MAX_COLS].clone()
-            dist.all_reduce(block)
-            dist.all_reduce(maxima, op=dist.ReduceOp.MAX)
-            block[:, MAX_COLS] = maxima
-
     for _ in range(W):
         one_step(totals)
-    sync_stats(torch.zeros(K, 9, dtype=torch.float64, device=dev))   # same collectives as the timed ones
+    all_reduce_totals(torch.zeros(K, 9, dtype=torch.float64, device=dev))   # same collective as the timed one
     agent.check()
     barrier()
 
@@ -272,8 +291,8 @@ def run_ours(args, out):
             kend[k].record()
             env.totals_device(stats[k])
             ends[k].record()
-        starts[K].record()                    # sync interval ends: one all-reduce of all K rows
-        sync_stats(stats)
+        starts[K].record()                    # sync interval ends: one collective over all K rows
+        all_reduce_totals(stats)
         ends[K].record()
         barrier()
     agent.check()
@@ -281,13 +300,14 @@ def run_ours(args, out):
     drain_ms = starts[K].elapsed_time(ends[K])
     kernel_ms_by_step = [round(s.elapsed_time(e), 4) for s, e in zip(kstart, kend)]    # this rank's
     kernel_ms = sum(s.elapsed_time(e) for s, e in zip(kstart, kend))
-    t = torch.tensor([step_ms, kernel_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, kernel_ms = float(t[0]), float(t[1])
+    step_ms, kernel_ms = max_over_ranks(step_ms, kernel_ms)
     value = world * n * T * K / (step_ms / 1e3)
+    episodes_finished = float(stats[-1, 0])
 
-    # ---- end to end through the host-buffer C-ABI call (pinned host memory)
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory):
+    # every step uploads the environment state words, runs the rollout, and
+    # reads back boards, state and totals; L2 is flushed before each step like
+    # in the device-timed region, and only the steps themselves are timed
     core_in = torch.empty(n, dtype=torch.int64).pin_memory()
     core_out = torch.empty(n, dtype=torch.int64).pin_memory()
     boards_out = torch.empty(n, env.hw, dtype=torch.uint8).pin_memory()
@@ -295,25 +315,65 @@ def run_ours(args, out):
     for _ in range(2):
         agent.rollout_host(T, core_in, core_out, boards_out)
         core_in.copy_(core_out)
-    barrier()
-    t0 = time.perf_counter()
+    e2e_s = 0.0
     for _ in range(K):
-        host_totals = agent.rollout_host(T, core_in, core_out, boards_out)
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        host_totals = agent.rollout_host(T, core_in, core_out, boards_out)      # synchronises
+        e2e_s += time.perf_counter() - t0
         core_in.copy_(core_out)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * T * K / float(t[0])
+    (e2e_s,) = max_over_ranks(e2e_s)
+    e2e_value = world * n * T * K / e2e_s
     h2d = n * 8
     d2h = n * env.hw + n * 8 + 9 * 8
+    del host_totals
+
+    # ---- the other BASELINE configurations and the shared-table leg
+    extra = {}
+    if not args.main_only:
+        del agent, env
+        torch.cuda.empty_cache()
+        ctx = dict(torch=torch, dist=dist, gridfast=gridfast, world=world, rank=rank, local=local, dev=dev, flush=flush,
+                   barrier=barrier, max_over_ranks=max_over_ranks, sync_shared_table=sync_shared_table)
+        extra["configs"] = {"C3": bench_c3(ctx), "C4": bench_c4(ctx), "C5": bench_c5(ctx)}
+        extra["shared_q"] = bench_shared(ctx)
+        if world == 1:
+            extra["configs"]["C1"] = bench_c1(ctx)
 
     if rank == 0:
         peak, peak_src = measured_peak()
         per_launch_s = kernel_ms / 1e3 / K
-        achieved = B_ALG * n * T / per_launch_s / 1e9
+        clk = clocks.summary()
+        f_sm = (clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965) * 1e6
+        issue = recorded_issue()
+        roof = {"kernel": "k_rollout_private<boat,philox>", "kernel_ms_per_launch": kernel_ms / K,
+                # epsilon anneals over the first 100,000 agent steps: early launches explore
+                # (environments of a warp spread over the states), later ones run greedy
+                "kernel_ms_by_launch": kernel_ms_by_step}
         traffic = recorded_traffic()
+        roof["traffic"] = None if traffic is None else traffic.get("dram_bytes_per_launch")
+        # what the unfused one-step contract of SURVEY 8(d) would move; the fused kernel keeps
+        # state in registers and tables in shared memory, so this is traffic REMOVED, not moved
+        contract = B_ALG * n * T / per_launch_s / 1e9
+        roof["hbm_contract"] = {"algorithmic_bytes_per_env_step": B_ALG, "algorithmic_GBps": contract, "peak": peak,
+                                "ratio_to_peak": contract / peak, "peak_source": peak_src,
+                                "note": "not a utilisation: bytes the fusion removed from HBM"}
+        if issue is not None:
+            # the bound that binds: warp-instruction issue, 4 schedulers x 148 SMs x f_SM
+            per_launch = issue["warp_instructions_by_launch"]
+            timed = per_launch[W:W + K] if len(per_launch) >= W + K else per_launch
+            inst = sum(timed) / len(timed)
+            achieved = inst / per_launch_s / 1e9
+            issue_peak = 4 * 148 * f_sm / 1e9
+            roof.update({"bound": "issue", "achieved": achieved, "peak": issue_peak, "unit": "Gwarp-inst/s",
+                         "frac": achieved / issue_peak, "warp_instructions_per_launch": inst,
+                         "warp_instructions_per_env_step": inst * 32 / (n * T),
+                         "peak_source": "4 issue slots x 148 SMs x SM clock sampled under load (%.0f MHz)" % (f_sm / 1e6),
+                         "instruction_count_source": issue.get("source")})
+        else:
+            roof.update({"bound": "hbm", "achieved": contract, "peak": peak, "unit": "GB/s", "frac": contract / peak,
+                         "peak_source": peak_src})
         line = {
             "metric": "env-steps/sec (step + tabular-Q update)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms / K,
@@ -321,19 +381,14 @@ def run_ours(args, out):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": n, "locksteps_per_call": T,
                        "q_mode": "private", "rng": "philox4x32-10", "l2": "flushed between timed iterations (256 MiB memset)",
-                       "episodes_finished": float(host_totals[0])},
-            "roofline": {"bound": "hbm", "kernel": "k_rollout_private<boat,philox>",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
-                         "algorithmic_bytes_per_env_step": B_ALG, "peak_source": peak_src,
-                         "kernel_ms_per_launch": kernel_ms / K,
-                         # epsilon anneals over the first 100,000 agent steps: early launches explore
-                         # (environments of a warp spread over the states), later ones run greedy
-                         "kernel_ms_by_launch": kernel_ms_by_step},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                       "episodes_finished": episodes_finished},
+            "roofline": roof,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "l2": "flushed before every step", "timed": "host wall clock around each sgk_rollout_tabq_host call"},
             "gpu_launches": 4 * K, "stats_allreduce_ms": drain_ms,
-            "clocks": clocks.summary(),
+            "clocks": clk,
         }
+        line.update(extra)
         if world == 1:
             line["hbm_point"] = hbm_point(torch, gridfast, peak)
             t = time.perf_counter()
@@ -341,10 +396,236 @@ def run_ours(args, out):
             line["cpu_baseline"] = {
                 "value": rate, "unit": "env-steps/s", "cores": 1, "kind": "port",
                 "sample": "150000 env-steps of boat-race tabular-Q, python oracle port, 1 process (%.1f s)" % (time.perf_counter() - t),
+                "note": "the port's closed-form epsilon schedule skips the reference's O(anneal) list.pop(0) per step "
+                        "(value.py:57): it is FASTER than the real reference agent, i.e. a conservative baseline",
                 "c_port": c_port_rate()}
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------- sub-records
+def _timed_calls(ctx, fn, reps, warm):
+    """`reps` calls of fn, each preceded by an (untimed) L2 flush, CUDA events on
+    the launching stream; returns seconds per call, max over ranks."""
+    torch = ctx["torch"]
+    for _ in range(warm):
+        fn()
+    ctx["barrier"]()
+    total = 0.0
+    per_call = []
+    for _ in range(reps):
+        ctx["flush"].zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        per_call.append(a.elapsed_time(b) / 1e3)
+        total += per_call[-1]
+    (total,) = ctx["max_over_ranks"](total)
+    return total / reps, per_call
+
+
+def bench_c3(ctx):
+    """BASELINE config 3: side-effects sokoban, tabular Q with hidden-reward
+    (safety performance) tracking, 131,072 environments per GPU -- 1,048,576 at
+    --gpus 8 -- private tables, 10,000 lock-steps per call."""
+    gf, world, rank = ctx["gridfast"], ctx["world"], ctx["rank"]
+    n, T = 131072, 10000
+    env = gf.BatchedEnv("SideEffectsSokoban-v0", n, seed=0, env_id0=rank * n, device=ctx["local"])
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **HP)
+    sec, per_call = _timed_calls(ctx, lambda: agent.rollout(T), reps=5, warm=3)
+    agent.check()
+    tot = env.totals()
+    peak, _ = measured_peak()
+    rate = world * n * T / sec
+    b_alg = B_ALG_BY_ENV["SideEffectsSokoban-v0"]
+    rec = {"workload": "side-effects sokoban tabular-Q, 131072 envs/GPU (%d global), private hashed tables (128 slots), "
+                       "10000 lock-steps per call" % (world * n),
+           "value": rate, "unit": "env-steps/s", "ms_per_call": 1e3 * sec, "kernel": "k_rollout_private<sokoban,philox>",
+           "kernel_ms_by_call": [round(1e3 * s, 3) for s in per_call],
+           "roofline": {"bound": "hbm", "achieved": rate / world * b_alg / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": rate / world * b_alg / 1e9 / peak, "algorithmic_bytes_per_env_step": b_alg,
+                        "note": "671 MB of private tables per GPU do not fit L2: bound by dependent table loads "
+                                "(ncu long_scoreboard), see profiles/"},
+           "mean_return": tot["sum_return"] / max(tot["episodes"], 1),
+           "mean_safety_performance": tot["sum_performance"] / max(tot["episodes"], 1), "episodes_rank0": tot["episodes"]}
+    del agent, env
+    ctx["torch"].cuda.empty_cache()
+    return rec
+
+
+def bench_c4(ctx):
+    """BASELINE config 4 as SURVEY 8(d) specifies it: tomato watering, 65,536
+    environments per GPU, SSRL agent with C_prior .01, budget 1,000 queries per
+    environment, warm-up fraction .5 -> 500 random-policy warm-up episodes per
+    environment (ssrl/warmup.py), then 10,000 learning lock-steps per call."""
+    gf, world, rank, torch = ctx["gridfast"], ctx["world"], ctx["rank"], ctx["torch"]
+    n, T, budget, warm = 65536, 10000, 1000, 0.5
+    env = gf.BatchedEnv("TomatoWatering-v0", n, seed=0, env_id0=rank * n, device=ctx["local"])
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **HP)
+    agent.enable_ssrl(c_prior=0.01, budget=budget)
+    n_warm = int(budget * warm)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx["barrier"]()
+    a.record()
+    agent.ssrl_warmup(n_warm)
+    b.record()
+    torch.cuda.synchronize()
+    (warm_s,) = ctx["max_over_ranks"](a.elapsed_time(b) / 1e3)
+    env.clear_stats()
+    sec, per_call = _timed_calls(ctx, lambda: agent.rollout(T), reps=2, warm=1)
+    agent.check()
+    tot = env.totals()
+    bud, eps, corrupt = [t.double().mean().item() for t in agent.ssrl_counters()]
+    peak, _ = measured_peak()
+    rate = world * n * T / sec
+    b_alg = B_ALG_BY_ENV["TomatoWatering-v0"]
+    rec = {"workload": "tomato watering + SSRL (C_prior .01, budget 1000, warm-up .5), 65536 envs/GPU, private hashed "
+                       "tables grown on demand, 10000 lock-steps per call",
+           "value": rate, "unit": "env-steps/s", "ms_per_call": 1e3 * sec, "kernel": "k_rollout_private<tomato,philox,ssrl>",
+           "kernel_ms_by_call": [round(1e3 * s, 3) for s in per_call],
+           "warmup": {"episodes_per_env": n_warm, "seconds": warm_s, "env_steps_per_s": world * n * n_warm * 100 / warm_s,
+                      "kernel": "k_rollout_random<tomato,philox> (episodic)"},
+           "roofline": {"bound": "hbm", "achieved": rate / world * b_alg / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": rate / world * b_alg / 1e9 / peak, "algorithmic_bytes_per_env_step": b_alg,
+                        "note": "tables of %d slots x 65536 envs = %.1f GB per GPU: bound by dependent probes into HBM"
+                                % (agent.capacity, agent.capacity * n * 48 / 1e9)},
+           "table_capacity": agent.capacity, "table_max_fill": agent.max_fill(),
+           "mean_budget_left": bud, "mean_episodes": eps, "mean_corrupt_episodes": corrupt,
+           "mean_return": tot["sum_return"] / max(tot["episodes"], 1),
+           "mean_safety_performance": tot["sum_performance"] / max(tot["episodes"], 1)}
+    del agent, env
+    torch.cuda.empty_cache()
+    return rec
+
+
+def bench_c5(ctx):
+    """BASELINE config 5: side-effects sokoban DeepQAgent, 4,096 lock-step
+    environments sharing one 36-100-100-4 Q network, replay ring in HBM, the
+    reference's ratio of one 64-sample optimiser step per env-step (batch
+    262,144 per lock-step), network math on tcgen05."""
+    gf, world, rank, torch = ctx["gridfast"], ctx["world"], ctx["rank"], ctx["torch"]
+    n, batch, T = 4096, 64 * 4096, 500
+    env = gf.BatchedEnv("SideEffectsSokoban-v0", n, seed=0, env_id0=rank * n, device=ctx["local"])
+    agent = gf.BatchedDeepQ(env, replay_capacity=100 * n, batch_size=batch, lr=1e-3, epsilon=0.01,
+                            epsilon_anneal=100000, sync_every=10000, reference_bxb_loss=True)
+    agent.set_tensor_cores(True)
+    agent.warmup(100)
+    sec, per_call = _timed_calls(ctx, lambda: agent.rollout(T), reps=2, warm=1)
+    flop = T * (n * 28000.0 + batch * 4 * 28000.0)          # SURVEY 8(d): act forward + 4x forward per learned sample
+    tf = flop / sec / 1e12
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tpeak = float(json.load(f)["bf16_tflops_sustained"])
+            tsrc = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        tpeak, tsrc = 1400.0, "fallback (B200_PROFILING.md sustained)"
+    rec = {"workload": "side-effects sokoban deep-Q, 4096 envs/GPU, one shared MLP 36-100-100-4, replay ring 409600 "
+                       "transitions in HBM, batch 262144 per lock-step (= 64 learned samples per env-step), "
+                       "%d lock-steps per call" % T,
+           "value": world * n * T / sec, "unit": "env-steps/s", "ms_per_call": 1e3 * sec, "us_per_lockstep": 1e6 * sec / T,
+           "learned_samples_per_s": world * batch * T / sec, "precision": agent.precision,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                        "peak_source": tsrc, "flops": "model flops: 28.0 kFLOP per forward, x4 per learned sample"},
+           "loss_gradnorm_clip": agent.last_scalars()}
+    del agent, env
+    torch.cuda.empty_cache()
+    return rec
+
+
+def bench_c1(ctx):
+    """BASELINE config 1, `python main.py boat tabular-q --lr .5`: ONE
+    environment behind the reference's own loop shape, through the fused
+    LEARN_MAP function (one launch per episode, Train/epsilon logged per step)."""
+    import argparse
+
+    import numpy as np
+    gf = ctx["gridfast"]
+
+    class NullWriter:
+        def add_scalar(self, *a, **k):
+            pass
+        add_scalars = add_scalar
+
+    class Meter:
+        val = avg = max = 0.0
+
+        def update(self, v, n=1):
+            self.val = v
+
+    args = argparse.Namespace(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=100000, cheat=False, eval_every=10 ** 9)
+    np.random.seed(0)
+    env = gf.make("BoatRace-v0", rng="numpy")
+    agent = gf.GpuTabularQAgent(env, args)
+    history = {"writer": NullWriter(), "t": 0, "episode": 0, "returns": Meter(), "safeties": Meter(), "margins": Meter(),
+               "margins_support": Meter()}
+
+    def episodes(m):
+        for _ in range(m):
+            state = (env.reset(), 0.0, False, {})
+            history["episode"] += 1
+            gf.tabq_learn_fused(agent, env, state, history, args)
+    episodes(20)
+    t0, s0 = time.perf_counter(), history["t"]
+    episodes(300)
+    dt = time.perf_counter() - t0
+    steps = history["t"] - s0
+    return {"workload": "boat-race tabular-Q, ONE environment, reference loop shape (train.py:62-70) through "
+                        "gridfast.tabq_learn_fused on numpy's global stream, 300 episodes",
+            "value": steps / dt, "unit": "env-steps/s", "us_per_env_step": 1e6 * dt / steps,
+            "launches_per_episode": 5, "note": "latency-bound by construction (one environment); the reference agent "
+            "half alone costs 26-48 us per step on one core (SURVEY 3.5)"}
+
+
+def bench_shared(ctx):
+    """Shared-table mode: every GPU keeps a replica of ONE Q table for all its
+    environments; every `sync_interval` lock-steps the replicas are merged with
+    one NCCL all-reduce of the dense delta-Q array.  Reports the
+    rollout rate and the cost of a sync; checks that all replicas end identical."""
+    gf, world, rank, torch, dist = ctx["gridfast"], ctx["world"], ctx["rank"], ctx["torch"], ctx["dist"]
+    out = {}
+    for name, env_id, n, T in (("boat", "BoatRace-v0", 65536, 2000), ("sokoban", "SideEffectsSokoban-v0", 131072, 1000)):
+        for interval in (100, 1000):
+            env = gf.BatchedEnv(env_id, n, seed=0, env_id0=rank * n, device=ctx["local"])
+            agent = gf.BatchedTabularQ(env, gf.Q_SHARED, **HP)
+            agent.rebase()
+            sync_ms = []
+
+            def run():
+                done = 0
+                while done < T:
+                    agent.rollout(interval)
+                    done += interval
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    ctx["sync_shared_table"](agent)
+                    b.record()
+                    sync_ms.append((a, b))
+            sec, _ = _timed_calls(ctx, run, reps=2, warm=1)
+            agent.check()
+            ms = sorted(a.elapsed_time(b) for a, b in sync_ms[-2 * (T // interval):])
+            keys, rows = agent.export(0)
+            order = keys.argsort()
+            blob = torch.as_tensor(rows[order].reshape(-1).copy()).to(ctx["dev"])
+            same = True
+            if world > 1:
+                sizes = [torch.zeros(1, dtype=torch.int64, device=ctx["dev"]) for _ in range(world)]
+                dist.all_gather(sizes, torch.tensor([blob.numel()], device=ctx["dev"]))
+                same = all(int(s) == blob.numel() for s in sizes)
+                if same:
+                    blobs = [torch.empty_like(blob) for _ in range(world)]
+                    dist.all_gather(blobs, blob)
+                    same = all(torch.equal(x, blobs[0]) for x in blobs)
+            out["%s_sync%d" % (name, interval)] = {
+                "envs_per_gpu": n, "sync_interval": interval, "value": world * n * T / sec, "unit": "env-steps/s",
+                "sync_ms_median": ms[len(ms) // 2], "sync_ms_max": ms[-1], "syncs_timed": len(ms),
+                "collective": "1 x all_reduce(sum) of %d x 5 float64 (dense delta-Q + presence)" % agent.dense_size(),
+                "states": int(len(keys)), "replicas_identical": bool(same)}
+            del agent, env
+            torch.cuda.empty_cache()
+    return out
 
 
 def _claim_stdout():
@@ -388,6 +669,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--main-only", action="store_true", help="only the headline C2 measurement (skip C1/C3/C4/C5 and the shared-table leg)")
     args = ap.parse_args()
     out = _claim_stdout()
     if args.impl == "reference":

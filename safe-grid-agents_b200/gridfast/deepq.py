@@ -68,6 +68,11 @@ class BatchedDeepQ:
     def set_tensor_cores(self, enabled=True):
         """Forward passes on tcgen05 (TF32 in, fp32 accumulate) instead of fp32 FFMA."""
         check(self.L.sgk_dqn_set_tensor_cores(self.h, int(enabled)))
+        self._tc = bool(enabled)
+
+    @property
+    def precision(self):
+        return "tcgen05 TF32 operands, fp32 accumulate" if getattr(self, "_tc", False) else "fp32 FFMA"
 
     def sync_target(self):
         check(self.L.sgk_dqn_sync_target(self.h, _stream()))
