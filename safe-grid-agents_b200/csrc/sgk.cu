@@ -2025,7 +2025,9 @@ static int reserve_slots(sgk_tabq *q, int64_t want, int64_t at_least, cudaStream
     int64_t exact = 0;
     int rc = table_max_fill(q, st, &exact);
     if (rc != SGK_OK) return rc;
-    while (2 * exact > q->cap || limit() - exact < at_least) {
+    // grow once the fullest table passes 11/16: tables then sit between 11/32 and 3/4 full (at 1/2 the
+    // C4 run of bench.py carried 103 GB of tables where 51 GB do)
+    while (16 * exact > 11 * q->cap || limit() - exact < at_least) {
         rc = grow_tables(q, q->cap * 2, st);
         if (rc != SGK_OK) return rc;
     }
@@ -2258,7 +2260,7 @@ extern "C" int sgk_rollout_tabq(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint
     // Hashed private tables grow like the reference's dict: a lock-step inserts
     // at most two keys per table (Q[s] on the first touch, Q[s']), so the call
     // is cut into launches that cannot overflow, and between launches the
-    // fullest table is measured and, past half full, every table rehashed into
+    // fullest table is measured and, past 11/16 full, every table rehashed into
     // twice the capacity.  Dense, shared and large-enough tables: one launch.
     int64_t done = 0;
     while (done < n_steps) {

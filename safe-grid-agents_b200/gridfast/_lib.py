@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsgk.so")
+# SGK_LIB_PATH: load another build of the same library (A/B measurements of compiler flags)
+LIB_PATH = os.environ.get("SGK_LIB_PATH") or os.path.join(HERE, "libsgk.so")
 
 ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, ENV_LAVA, ENV_ISLAND, ENV_SUPER, ENV_WHISKY = 0, 1, 2, 3, 4, 5, 6
 RNG_PHILOX, RNG_REPLAY = 0, 1
