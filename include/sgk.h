@@ -374,13 +374,20 @@ int sgk_dqn_learn(sgk_dqn *d, uint64_t step, float *loss_out, void *stream);
 int sgk_dqn_learn_batch(sgk_dqn *d, const uint8_t *s, const uint8_t *a, const double *r, const uint8_t *s2,
                         const uint8_t *term, int64_t n, float *loss_out, void *stream);
 int sgk_dqn_last_scalars(const sgk_dqn *d, float *out3, void *stream);
-/* Run the network on the 5th-generation tensor cores: every forward pass
- * (acting, online and target networks in learn) as one fused tcgen05 kernel,
- * and the backward pass as an error-chain kernel plus sample-reduction
- * weight-gradient kernels -- TF32 operands, fp32 accumulation in TMEM.  Covers
- * the reference's default architecture (n_layers 2, n_hidden <= 100).  Off by
- * default: the fp32 path is the parity reference. */
-int sgk_dqn_set_tensor_cores(sgk_dqn *d, int enabled);
+/* How the network math runs.  The reference's default architecture (n_layers 2,
+ * n_hidden <= 100, value.py:148-158) runs on the 5th-generation tensor cores:
+ * every forward pass (acting, online and target networks in learn) as one fused
+ * tcgen05 kernel with activations resident in tensor memory, the backward pass
+ * as an error-chain kernel plus sample-reduction weight-gradient kernels.
+ *   mode 3 (default where supported)  3xTF32 forward: every fp32 operand split
+ *           into two TF32 numbers, three MMA passes, fp32 accumulation -- Q
+ *           values within 1e-5 of torch fp32 (the tolerance north_star states);
+ *           backward in single-pass TF32
+ *   mode 1  single-pass TF32 everywhere (about 1e-3)
+ *   mode 0  fp32 FFMA kernels (the parity reference for gradients / optimiser;
+ *           the only mode for other architectures) */
+int sgk_dqn_set_tensor_cores(sgk_dqn *d, int mode);
+int sgk_dqn_get_tensor_cores(const sgk_dqn *d);
 /* n_steps lock-steps of the dqn_learn body (common/learn.py:29-58) for every
  * environment: act_explore, env.step, replay.add, learn, update_epsilon,
  * target sync every sync_every steps, reset when done.  `mode` is a bit set:

@@ -878,6 +878,8 @@ void cg_eval(const cg_sim *s, uint64_t seed, int64_t env_id0, int64_t n_eval, in
 }
 
 /* ------------------------------------------------------------------ accessors */
+/* Continue from agent-step t (the epsilon schedule and the Philox counters are indexed by it). */
+void cg_set_t(cg_sim *s, int64_t t) { s->t = t; }
 int cg_hw(const cg_sim *s) { return s->L.HW; }
 int64_t cg_t(const cg_sim *s) { return s->t; }
 

@@ -63,6 +63,7 @@ def lib():
         L.cg_ssrl_warmup.argtypes = [vp, i64, u64, vp]
         L.cg_get_ssrl_counters.argtypes = [vp, vp, vp, vp]
         L.cg_clear_stats.argtypes = [vp]
+        L.cg_set_t.argtypes = [vp, i64]
         _lib = L
     return _lib
 
@@ -99,6 +100,10 @@ class Sim:
     @property
     def t(self):
         return self.L.cg_t(self.h)
+
+    @t.setter
+    def t(self, value):
+        self.L.cg_set_t(self.h, value)
 
     def rollout(self, n_steps, trace=False, boards=False):
         out = {}

@@ -608,8 +608,8 @@ static bool tc_supported(const sgk_dqn *d)
 static int ensure_packed(sgk_dqn *d, int which, cudaStream_t st)
 {
     if (!d->w_image[which]) {
-        CU(cudaMalloc(&d->w_image[which], tc::FWD_IMAGE_BYTES));
-        CU(cudaMemsetAsync(d->w_image[which], 0, tc::FWD_IMAGE_BYTES, st));
+        CU(cudaMalloc(&d->w_image[which], 2 * tc::FWD_IMAGE_BYTES));        // [hi | lo] images
+        CU(cudaMemsetAsync(d->w_image[which], 0, 2 * tc::FWD_IMAGE_BYTES, st));
         d->w_image_dirty[which] = 1;
     }
     if (which == 0 && !d->w_image_bwd) {
@@ -618,7 +618,7 @@ static int ensure_packed(sgk_dqn *d, int which, cudaStream_t st)
     }
     if (!d->w_image_dirty[which]) return SGK_OK;
     const float *P = d->params[which];
-    tc::k_pack_weights<<<dim3(which == 0 ? 5 : 3, 6), 256, 0, st>>>(P + d->w_off[0], P + d->w_off[1], P + d->w_off[2], d->dims[0], d->dims[1],
+    tc::k_pack_weights<<<dim3(which == 0 ? 8 : 6, 6), 256, 0, st>>>(P + d->w_off[0], P + d->w_off[1], P + d->w_off[2], d->dims[0], d->dims[1],
                                                          d->n_actions, d->w_image[which], which == 0 ? d->w_image_bwd : nullptr);
     d->w_image_dirty[which] = 0;
     return launch_check("k_pack_weights");
@@ -630,7 +630,8 @@ static int forward_tc(sgk_dqn *d, int which, const uint8_t *boards, int64_t rows
 {
     static bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(tc::k_mlp_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem::TOTAL));
+        CU(cudaFuncSetAttribute(tc::k_mlp_forward_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemTs::TOTAL));
+        CU(cudaFuncSetAttribute(tc::k_mlp_forward_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemTs::TOTAL));
         attr_set = true;
     }
     int prc = ensure_packed(d, which, st);
@@ -645,8 +646,9 @@ static int forward_tc(sgk_dqn *d, int which, const uint8_t *boards, int64_t rows
     p.boards = boards; p.rows = rows; p.q_out = q_out; p.h1_out = h1; p.h2_out = h2;
     const int64_t tiles = (rows + tc::TILE_M - 1) / tc::TILE_M;
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, d->sm_count);
-    tc::k_mlp_forward_tc<<<grid, tc::TILE_M, tc::Smem::TOTAL, st>>>(p);
-    return launch_check("k_mlp_forward_tc");
+    if (d->use_tc >= 3) tc::k_mlp_forward_ts<true><<<grid, tc::TS_THREADS, tc::SmemTs::TOTAL, st>>>(p);
+    else tc::k_mlp_forward_ts<false><<<grid, tc::TS_THREADS, tc::SmemTs::TOTAL, st>>>(p);
+    return launch_check("k_mlp_forward_ts");
 }
 
 // backward pass on the tensor cores: error chain, then the three weight /
@@ -764,6 +766,8 @@ extern "C" int sgk_dqn_create(const sgk_env *env, int n_layers, int n_hidden, in
     }
     d->n_params = off;
     d->cap = replay_capacity; d->batch = batch_size; d->seed = seed;
+    // the reference's default architecture runs on the tensor cores at fp32 accuracy (3xTF32)
+    d->use_tc = tc_supported(d) ? 3 : 0;
     cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, env->device);
     d->lr = 1e-3; d->discount = 0.99; d->epsilon = 0.01; d->anneal = 100000; d->sync_every = 10000; d->bxb_loss = 1;
     const size_t pb = (size_t)d->n_params * sizeof(float);
@@ -1138,9 +1142,12 @@ extern "C" int sgk_dqn_set_tensor_cores(sgk_dqn *d, int enabled)
 {
     REQUIRE(d != nullptr, "d is NULL");
     REQUIRE(!enabled || tc_supported(d), "the tensor-core forward covers n_layers == 2, n_hidden <= 100, boards <= 64 cells");
-    d->use_tc = enabled ? 1 : 0;
+    REQUIRE(enabled == 0 || enabled == 1 || enabled == 3, "enabled must be 0 (fp32 FFMA), 1 (single-pass TF32) or 3 (3xTF32)");
+    d->use_tc = enabled;
     return SGK_OK;
 }
+
+extern "C" int sgk_dqn_get_tensor_cores(const sgk_dqn *d) { return d ? d->use_tc : 0; }
 
 extern "C" int sgk_dqn_last_scalars(const sgk_dqn *d, float *out3, void *stream)
 {

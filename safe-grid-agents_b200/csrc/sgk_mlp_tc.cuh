@@ -152,8 +152,15 @@ constexpr uint32_t FWD_IMAGE_BYTES = Smem::X;    // W1 | W2 | W3 regions, contig
 // rows and `k_pad` columns, zero padded.  Consecutive threads take consecutive
 // 16-byte pieces of a weight row (coalesced global reads, float4 when the row
 // length allows), four pieces in flight per thread.
+// hi / lo split of an fp32 value into two TF32 numbers: x = hi + lo up to 2^-22 relative
+__device__ __forceinline__ float tf32_part(float x, int lo_part)
+{
+    const float hi = to_tf32(x);
+    return lo_part ? to_tf32(x - hi) : hi;
+}
+
 __device__ __forceinline__ void stage_weights(uint8_t *dst, const float *w, int n_out, int n_in, int rows_pad, int k_pad,
-                                              int tid = threadIdx.x, int nth = blockDim.x)
+                                              int tid = threadIdx.x, int nth = blockDim.x, int lo_part = 0)
 {
     const int chunks = k_pad / 4;
     const bool vec = (n_in & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
@@ -172,7 +179,7 @@ __device__ __forceinline__ void stage_weights(uint8_t *dst, const float *w, int 
                 v.z = k + 2 < n_in ? __ldg(src + 2) : 0.f;
                 v.w = k + 3 < n_in ? __ldg(src + 3) : 0.f;
             }
-            v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            v = make_float4(tf32_part(v.x, lo_part), tf32_part(v.y, lo_part), tf32_part(v.z, lo_part), tf32_part(v.w, lo_part));
         }
         *reinterpret_cast<float4 *>(dst + (size_t)c * rows_pad * 16 + r * 16) = v;
     }
@@ -711,18 +718,271 @@ k_wgrad_finish(const WgradFinishBatch batch, int n_partials)
 // Weights -> operand images in global memory, once per parameter update; the
 // MLP kernels then fetch an image with one bulk copy instead of re-staging the
 // matrices in every CTA.  Block b packs one matrix.
+// The forward image is [hi | lo]: two copies of the W1|W2|W3 operand layout, the
+// TF32-rounded weights and the TF32-rounded remainders (3xTF32, k_mlp_forward_ts).
 __global__ void __launch_bounds__(256) k_pack_weights(const float *w1, const float *w2, const float *w3, int n_in, int n_hidden,
                                                       int n_out, uint8_t *fwd_image, uint8_t *bwd_image)
 {
     const int k_in = (n_in + 7) & ~7;
     const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;    // gridDim.y blocks share a matrix
+    uint8_t *lo = fwd_image + FWD_IMAGE_BYTES;
     switch (blockIdx.x) {
     case 0: stage_weights(fwd_image + Smem::W1, w1, n_hidden, n_in, N_HID, k_in, tid, nth); break;
     case 1: stage_weights(fwd_image + Smem::W2, w2, n_hidden, n_hidden, N_HID, K_HID, tid, nth); break;
     case 2: stage_weights(fwd_image + Smem::W3, w3, n_out, n_hidden, N_OUT, K_HID, tid, nth); break;
-    case 3: if (bwd_image) stage_weights_T(bwd_image + SmemBwd::W3T, w3, n_out, n_hidden, N_HID, 8, tid, nth); break;
+    case 3: stage_weights(lo + Smem::W1, w1, n_hidden, n_in, N_HID, k_in, tid, nth, 1); break;
+    case 4: stage_weights(lo + Smem::W2, w2, n_hidden, n_hidden, N_HID, K_HID, tid, nth, 1); break;
+    case 5: stage_weights(lo + Smem::W3, w3, n_out, n_hidden, N_OUT, K_HID, tid, nth, 1); break;
+    case 6: if (bwd_image) stage_weights_T(bwd_image + SmemBwd::W3T, w3, n_out, n_hidden, N_HID, 8, tid, nth); break;
     default: if (bwd_image) stage_weights_T(bwd_image + SmemBwd::W2T, w2, n_hidden, n_hidden, N_HID, K_HID, tid, nth); break;
     }
+}
+
+// ===================================================================== forward, fp32-accurate (3xTF32)
+// k_mlp_forward_ts: the same fused three-layer forward with
+//   * 3xTF32: every fp32 operand is split into two TF32 numbers, x = hi + lo,
+//     and a product a*b is accumulated as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi in
+//     the fp32 TMEM accumulator (the dropped lo*lo term is 2^-22 relative):
+//     Q values agree with torch fp32 to ~1e-6, inside the 1e-5 of north_star.
+//     Boards are small integers, exact in TF32, so layer 1 needs two passes;
+//   * activations that never leave tensor memory: the epilogue reads its
+//     accumulator row (tcgen05.ld), applies bias + ReLU, splits hi / lo and
+//     writes both back to TMEM (tcgen05.st), where the next layer's MMAs take
+//     them as the A operand (tcgen05.mma with A in TMEM) -- shared memory
+//     holds only the two weight images (160 KB) and the board tile;
+//   * 8 warps: both warpgroups drain the accumulator (warp w owns TMEM lanes
+//     32*(w%4).., the warpgroup picks the column half), and the next tile's
+//     boards are fetched while the current tile computes.
+struct SmemTs {
+    static constexpr int HI = 0;                                   // W1|W2|W3 (layout of Smem), TF32-rounded
+    static constexpr int LO = FWD_IMAGE_BYTES;                     // ... remainders
+    static constexpr int X = 2 * FWD_IMAGE_BYTES;                  // [MAX_K_IN/4][128][16 B]
+    static constexpr int BIAS = X + (MAX_K_IN / 4) * Smem::CHUNK_A;
+    static constexpr int BAR = BIAS + (2 * N_HID + N_OUT) * 4;
+    static constexpr int TOTAL = BAR + 32;
+};
+constexpr int TS_THREADS = 256;
+constexpr uint32_t TS_D_A = 0, TS_D_B = 128, TS_H_HI = 256, TS_H_LO = 384;     // TMEM columns (512 allocated)
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// 16 accumulator columns of this thread's lane; the wait carries the registers
+// so that nothing consuming them can be scheduled ahead of it
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                    "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                    "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+
+// hidden-layer epilogue of one thread: columns [c0, c1) of its accumulator row ->
+// bias, ReLU -> hi / lo TF32 parts into the A-operand region of TMEM (+ fp32 copy in HBM)
+template <bool X3>
+__device__ __forceinline__ void ts_hidden_epilogue(uint32_t lane_base, uint32_t d_col, const float *bias, int c0, int c1,
+                                                   float *h_out_row, int n_hidden)
+{
+    const bool vec = (n_hidden & 3) == 0;
+#pragma unroll 1
+    for (int c = c0; c < c1; c += 16) {
+        float v[16];
+        tmem_ld16(lane_base + d_col + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + bias[c + i], 0.f);
+        if (h_out_row) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) store4(h_out_row, c + i, n_hidden, vec, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            if (c + 8 * g >= K_HID) break;            // the 112-column accumulator has 104 operand columns
+            float hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                hi[i] = to_tf32(v[8 * g + i]);
+                lo[i] = X3 ? to_tf32(v[8 * g + i] - hi[i]) : 0.f;
+            }
+            tmem_st8(lane_base + TS_H_HI + c + 8 * g, hi);
+            if (X3) tmem_st8(lane_base + TS_H_LO + c + 8 * g, lo);
+        }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(TS_THREADS, 1) k_mlp_forward_ts(const Params p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_base_slot;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + SmemTs::BAR);
+    uint64_t *mbar_w = mbar + 1;
+    float *bias = reinterpret_cast<float *>(smem + SmemTs::BIAS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant; column half
+    const int row_in_tile = quad * 32 + lane;
+    const int k_in = (p.n_in + 7) & ~7;                   // 36 -> 40, 25 -> 32, 63 -> 64
+    const int n_chunks = k_in / 4;
+
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        mbar_init(mbar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        bulk_load(smem + SmemTs::HI, p.w_image, X3 ? 2 * FWD_IMAGE_BYTES : FWD_IMAGE_BYTES, mbar_w);
+    }
+    for (int i = threadIdx.x; i < 2 * N_HID + N_OUT; i += blockDim.x) {
+        float b = 0.f;
+        if (i < N_HID) b = i < p.n_hidden ? p.b1[i] : 0.f;
+        else if (i < 2 * N_HID) b = i - N_HID < p.n_hidden ? p.b2[i - N_HID] : 0.f;
+        else b = i - 2 * N_HID < p.n_out ? p.b3[i - 2 * N_HID] : 0.f;
+        bias[i] = b;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t a_x = smem_u32(smem + SmemTs::X);
+    const uint32_t w_hi = smem_u32(smem + SmemTs::HI), w_lo = smem_u32(smem + SmemTs::LO);
+    constexpr uint32_t IDESC_HID = make_idesc(TILE_M, N_HID), IDESC_OUT = make_idesc(TILE_M, N_OUT);
+    uint32_t phase = 0;
+
+    // this thread's share of a board row: chunks half, half + 2, ... (4 cells each), kept in registers
+    uint32_t cells[MAX_K_IN / 8];
+    auto fetch = [&](int64_t tile) {
+        const int64_t row = tile * TILE_M + row_in_tile;
+#pragma unroll
+        for (int j = 0; j < MAX_K_IN / 8; j++) {
+            const int c = half + 2 * j;
+            uint32_t w = 0;
+            if (c < n_chunks && row < p.rows) {
+                const uint8_t *b = p.boards + row * p.n_in + 4 * c;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (4 * c + i < p.n_in) w |= (uint32_t)__ldg(b + i) << (8 * i);
+            }
+            cells[j] = w;
+        }
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int j = 0; j < MAX_K_IN / 8; j++) {
+            const int c = half + 2 * j;
+            if (c < n_chunks) {
+                const uint32_t w = cells[j];
+                *reinterpret_cast<float4 *>(smem + SmemTs::X + (size_t)c * Smem::CHUNK_A + row_in_tile * 16) =
+                    make_float4((float)(w & 0xFFu), (float)((w >> 8) & 0xFFu), (float)((w >> 16) & 0xFFu), (float)(w >> 24));
+            }
+        }
+    };
+    const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
+    if ((int64_t)blockIdx.x < n_tiles) { fetch(blockIdx.x); stage(); }
+    mbar_wait(mbar_w, 0);                                  // weight images have landed
+    // column split of the 104 operand columns between the warpgroups (multiples of 16 for tcgen05.ld.x16)
+    const int c0 = half ? 64 : 0, c1 = half ? N_HID : 64;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * TILE_M + row_in_tile;
+        const bool valid = row < p.rows;
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        // ---- layer 1: D_a = X * W1^T  (X exact in TF32: hi and lo weight passes)
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < k_in / 8; k++)
+                mma_tf32(tmem + TS_D_A, make_desc(a_x + k * 2 * Smem::CHUNK_A, Smem::CHUNK_A, 128),
+                         make_desc(w_hi + Smem::W1 + k * 2 * Smem::CHUNK_H, Smem::CHUNK_H, 128), IDESC_HID, k > 0);
+            if (X3)
+                for (int k = 0; k < k_in / 8; k++)
+                    mma_tf32(tmem + TS_D_A, make_desc(a_x + k * 2 * Smem::CHUNK_A, Smem::CHUNK_A, 128),
+                             make_desc(w_lo + Smem::W1 + k * 2 * Smem::CHUNK_H, Smem::CHUNK_H, 128), IDESC_HID, 1);
+            mma_commit(mbar);
+        }
+        const bool more = tile + gridDim.x < n_tiles;
+        if (more) fetch(tile + gridDim.x);                 // global loads in flight under the MMAs and epilogues
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+        if (more) stage();                                 // layer 1 is done with the board tile
+        ts_hidden_epilogue<X3>(lane_base, TS_D_A, bias, c0, c1, (valid && p.h1_out) ? p.h1_out + row * p.n_hidden : nullptr, p.n_hidden);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        // ---- layer 2: D_b = H1 * W2^T, A from tensor memory
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < K_HID / 8; k++)
+                mma_tf32_ts(tmem + TS_D_B, tmem + TS_H_HI + 8 * k, make_desc(w_hi + Smem::W2 + k * 2 * Smem::CHUNK_H, Smem::CHUNK_H, 128), IDESC_HID, k > 0);
+            if (X3) {
+                for (int k = 0; k < K_HID / 8; k++)
+                    mma_tf32_ts(tmem + TS_D_B, tmem + TS_H_HI + 8 * k, make_desc(w_lo + Smem::W2 + k * 2 * Smem::CHUNK_H, Smem::CHUNK_H, 128), IDESC_HID, 1);
+                for (int k = 0; k < K_HID / 8; k++)
+                    mma_tf32_ts(tmem + TS_D_B, tmem + TS_H_LO + 8 * k, make_desc(w_hi + Smem::W2 + k * 2 * Smem::CHUNK_H, Smem::CHUNK_H, 128), IDESC_HID, 1);
+            }
+            mma_commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+        ts_hidden_epilogue<X3>(lane_base, TS_D_B, bias + N_HID, c0, c1, (valid && p.h2_out) ? p.h2_out + row * p.n_hidden : nullptr, p.n_hidden);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        // ---- layer 3: D_a[:, 0:16] = H2 * W3^T
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < K_HID / 8; k++)
+                mma_tf32_ts(tmem + TS_D_A, tmem + TS_H_HI + 8 * k, make_desc(w_hi + Smem::W3 + k * 2 * Smem::CHUNK_O, Smem::CHUNK_O, 128), IDESC_OUT, k > 0);
+            if (X3) {
+                for (int k = 0; k < K_HID / 8; k++)
+                    mma_tf32_ts(tmem + TS_D_A, tmem + TS_H_HI + 8 * k, make_desc(w_lo + Smem::W3 + k * 2 * Smem::CHUNK_O, Smem::CHUNK_O, 128), IDESC_OUT, 1);
+                for (int k = 0; k < K_HID / 8; k++)
+                    mma_tf32_ts(tmem + TS_D_A, tmem + TS_H_LO + 8 * k, make_desc(w_hi + Smem::W3 + k * 2 * Smem::CHUNK_O, Smem::CHUNK_O, 128), IDESC_OUT, 1);
+            }
+            mma_commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+        if (half == 0) {
+            float v[8];
+            tmem_ld8(lane_base + TS_D_A, v);
+            if (valid) {
+                const float *b3 = bias + 2 * N_HID;
+                if (p.n_out == 4) {
+                    *reinterpret_cast<float4 *>(p.q_out + row * 4) = make_float4(v[0] + b3[0], v[1] + b3[1], v[2] + b3[2], v[3] + b3[3]);
+                } else {
+                    for (int i = 0; i < p.n_out && i < 8; i++) p.q_out[row * p.n_out + i] = v[i] + b3[i];
+                }
+            }
+        }
+        // the loop's first barrier orders this read of D_a before the next tile's layer 1
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
 }  // namespace tc

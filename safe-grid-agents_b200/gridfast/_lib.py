@@ -97,6 +97,7 @@ SYMBOLS = [
     ("sgk_dqn_learn_batch", _i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     ("sgk_dqn_last_scalars", _i32, [_vp, _vp, _vp]),
     ("sgk_dqn_set_tensor_cores", _i32, [_vp, _i32]),
+    ("sgk_dqn_get_tensor_cores", _i32, [_vp]),
     ("sgk_rollout_dqn", _i32, [_vp, _vp, _i64, _u64, _i32, _vp]),
     ("sgk_discounted_returns", _i32, [_vp, _vp, _vp, _vp, _i64, _dbl, _vp, _vp]),
     ("sgk_env_get_core", _i32, [_vp, _vp, _vp]),
@@ -121,6 +122,8 @@ def load():
                 "(there is no CPU fallback)" % LIB_PATH)
         lib = ctypes.CDLL(LIB_PATH)
         for name, restype, argtypes in SYMBOLS:
+            if os.environ.get("SGK_LIB_PATH") and not hasattr(lib, name):
+                continue             # an older A/B build may predate an entry point
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = restype
             fn.argtypes = argtypes

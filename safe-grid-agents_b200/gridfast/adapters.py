@@ -551,8 +551,8 @@ class GpuDeepQAgent:
             discount=args.discount, epsilon=args.epsilon, epsilon_anneal=args.epsilon_anneal,
             sync_every=getattr(args, "sync_every", 10000),
             reference_bxb_loss=getattr(args, "reference_bxb_loss", True), seed=getattr(args, "seed", 0) or 0)
-        if getattr(args, "tensor_cores", False):
-            self.net.set_tensor_cores(True)
+        if getattr(args, "tensor_cores", None) is not None:      # default: tensor cores on (3xTF32) where supported
+            self.net.set_tensor_cores(args.tensor_cores)
         self.replay = _ReplayView(self)
         self._k = 0
         self.epsilon = self._epsilon_at(0)      # value.py:76: the first pop, no 0.0 override

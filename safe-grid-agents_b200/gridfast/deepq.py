@@ -65,14 +65,21 @@ class BatchedDeepQ:
                           if isinstance(m, torch.nn.Linear) for p in (m.weight, m.bias)])
         self.set_params(flat, which)
 
-    def set_tensor_cores(self, enabled=True):
-        """Forward passes on tcgen05 (TF32 in, fp32 accumulate) instead of fp32 FFMA."""
-        check(self.L.sgk_dqn_set_tensor_cores(self.h, int(enabled)))
-        self._tc = bool(enabled)
+    def set_tensor_cores(self, mode=3):
+        """3 (or True): tcgen05 with 3xTF32 forwards -- fp32 accuracy, the default
+        for the reference's architecture; 1: single-pass TF32; 0 (or False):
+        fp32 FFMA kernels."""
+        mode = 3 if mode is True else int(mode)
+        check(self.L.sgk_dqn_set_tensor_cores(self.h, mode))
+
+    @property
+    def tensor_core_mode(self):
+        return self.L.sgk_dqn_get_tensor_cores(self.h)
 
     @property
     def precision(self):
-        return "tcgen05 TF32 operands, fp32 accumulate" if getattr(self, "_tc", False) else "fp32 FFMA"
+        return {0: "fp32 FFMA", 1: "tcgen05, single-pass TF32 operands, fp32 accumulate",
+                3: "tcgen05, 3xTF32 forward (fp32-accurate) + single-pass TF32 backward, fp32 accumulate"}[self.tensor_core_mode]
 
     def sync_target(self):
         check(self.L.sgk_dqn_sync_target(self.h, _stream()))

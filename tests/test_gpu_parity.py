@@ -369,6 +369,36 @@ def test_full_size_boat_65536_envs_bit_exact():
     assert torch.equal(env2.stats()["sum_return"], env.stats()["sum_return"])
 
 
+def test_full_size_boat_annealed_phase_with_the_trace_free_kernel():
+    """The kernel bench.py times (TRACE = 0 build, dense tables in shared memory)
+    in the phase most of its launches run in: 65,536 environments started at
+    agent-step 100,000 -- epsilon annealed to its floor, greedy lock-step --
+    for 3,000 lock-steps, against the C oracle: every environment's episode
+    statistics and board, and the key set and every Q row of 67 tables spread
+    over the batch."""
+    gf = _gf()
+    from oracle import cgrid
+    n, T, seed, t0 = 65536, 3000, 21, 100000
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=100000)
+    env = gf.BatchedEnv("BoatRace-v0", n, seed=seed)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **hp)
+    env.t = t0
+    agent.rollout(T)                      # trace off: the production instantiation
+    agent.check()
+    assert agent.epsilon_at(t0 + 5) == agent.epsilon_at(t0 + T)      # on the floor of the schedule
+    sim = cgrid.Sim(cgrid.BOAT, n, seed=seed, **hp)
+    sim.t = t0
+    sim.rollout(T)
+    _cmp_stats(env, sim, with_hash=False)
+    for i in list(range(0, n, 997)) + [n - 1]:
+        _cmp_table(env, agent, sim, i)
+    tot = env.totals()
+    ref = sim.env_stats()
+    assert tot["episodes"] == ref["episodes"].sum() == n * (T // 100)
+    assert tot["sum_return"] == ref["sum_return"].sum()              # integer-valued: exact in any order
+    assert tot["sum_performance"] == ref["sum_perf"].sum()
+
+
 def test_boat_hashed_and_dense_tables_agree_with_oracle():
     """Boat race private tables default to the minimal-perfect-hash layout
     (capacity 8); the generic hashed layout (capacity 16) must give the same
