@@ -77,6 +77,9 @@ struct sgk_dqn {
     uint8_t *w_image[2];              // forward image of Q / target_Q
     uint8_t *w_image_bwd;             // W3^T | W2^T of Q
     int w_image_dirty[2];             // parameters changed since the image was packed
+    uint8_t *h_img[2];                // FP16 operand images of H1 / H2 (forward -> fused backward)
+    int64_t h_img_tiles;
+    float *fb_partial; int64_t fb_partial_cap;     // per-CTA gradient partials of the fused backward
 };
 
 static const int SPLITS = 256;   // upper bound of the batch splits of the weight-gradient GEMMs
@@ -626,7 +629,7 @@ static int ensure_packed(sgk_dqn *d, int which, cudaStream_t st)
 
 // the fused tensor-core forward: boards (uint8) -> Q, optionally H1 / H2 in fp32
 static int forward_tc(sgk_dqn *d, int which, const uint8_t *boards, int64_t rows, float *q_out, float *h1, float *h2,
-                      cudaStream_t st)
+                      cudaStream_t st, bool want_images = false)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -645,20 +648,69 @@ static int forward_tc(sgk_dqn *d, int which, const uint8_t *boards, int64_t rows
     p.n_in = d->dims[0]; p.n_hidden = d->dims[1]; p.n_out = d->n_actions;
     p.boards = boards; p.rows = rows; p.q_out = q_out; p.h1_out = h1; p.h2_out = h2;
     const int64_t tiles = (rows + tc::TILE_M - 1) / tc::TILE_M;
+    p.h1_img = p.h2_img = nullptr;
+    if (want_images) {
+        if (d->h_img_tiles < tiles) {
+            for (int k = 0; k < 2; k++) { if (d->h_img[k]) cudaFree(d->h_img[k]); d->h_img[k] = nullptr; }
+            d->h_img_tiles = 0;
+            for (int k = 0; k < 2; k++) CU(cudaMalloc(&d->h_img[k], (size_t)tiles * tc::H_IMG_TILE_BYTES));
+            d->h_img_tiles = tiles;
+        }
+        p.h1_img = d->h_img[0]; p.h2_img = d->h_img[1];
+    }
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, d->sm_count);
     if (d->use_tc >= 3) tc::k_mlp_forward_ts<true><<<grid, tc::TS_THREADS, tc::SmemTs::TOTAL, st>>>(p);
     else tc::k_mlp_forward_ts<false><<<grid, tc::TS_THREADS, tc::SmemTs::TOTAL, st>>>(p);
     return launch_check("k_mlp_forward_ts");
 }
 
-// backward pass on the tensor cores: error chain, then the three weight /
-// bias gradients as sample-reductions (sgk_mlp_tc.cuh)
+// backward pass fused into one kernel (+ one folding the per-CTA partials): sgk_mlp_tc.cuh k_mlp_backward_fused
+static int backward_fused(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(tc::k_mlp_backward_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemFb::TOTAL));
+        attr_set = true;
+    }
+    int prc = ensure_packed(d, 0, st);
+    if (prc != SGK_OK) return prc;
+    const int H = d->dims[1], A = d->n_actions, n_in = d->dims[0];
+    const int64_t tiles = (B + tc::TILE_M - 1) / tc::TILE_M;
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, d->sm_count);
+    tc::FusedBwdParams p;
+    p.w_image = d->w_image_bwd; p.dq = dq; p.h1_img = d->h_img[0]; p.h2_img = d->h_img[1]; p.boards = d->xb;
+    p.n_in = n_in; p.n_hidden = H; p.n_out = A; p.n1pad = (n_in + 1 + 15) / 16 * 16; p.rows = B;
+    p.scale_up = 0.5f * (float)B;          // the loss put 2/B into dQ: brings the FP16 copies into range
+    const int stride = tc::N_OUT + tc::N_HID + p.n1pad;
+    const int64_t need = (int64_t)grid * tc::TILE_M * stride;
+    if (d->fb_partial_cap < need) {
+        if (d->fb_partial) cudaFree(d->fb_partial);
+        d->fb_partial = nullptr; d->fb_partial_cap = 0;
+        CU(cudaMalloc(&d->fb_partial, (size_t)need * 4));
+        d->fb_partial_cap = need;
+    }
+    p.partial = d->fb_partial;
+    tc::k_mlp_backward_fused<<<grid, tc::FB_THREADS, tc::SmemFb::TOTAL, st>>>(p);
+    int rc = launch_check("k_mlp_backward_fused");
+    if (rc != SGK_OK) return rc;
+    tc::FusedFinish f;
+    f.partial = d->fb_partial; f.n_partials = (int)grid; f.n_in = n_in; f.n_hidden = H; f.n_out = A; f.n1pad = p.n1pad;
+    f.dW1 = d->grads + d->w_off[0]; f.db1 = d->grads + d->b_off[0];
+    f.dW2 = d->grads + d->w_off[1]; f.db2 = d->grads + d->b_off[1];
+    f.dW3 = d->grads + d->w_off[2]; f.db3 = d->grads + d->b_off[2];
+    tc::k_bwd_fused_finish<<<grid_for(d->n_params, 256), 256, 0, st>>>(f);
+    return launch_check("k_bwd_fused_finish");
+}
+
+// the unfused tensor-core backward (SGK_BWD_UNFUSED=1, kept for A/B measurements): error chain, then the
+// three weight / bias gradients as sample-reductions (sgk_mlp_tc.cuh)
 static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
         CU(cudaFuncSetAttribute(tc::k_mlp_backward_data_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemBwd::TOTAL));
         CU(cudaFuncSetAttribute(tc::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemWg::TOTAL));
+        CU(cudaFuncSetAttribute(tc::k_wgrad_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemWm::TOTAL));
         attr_set = true;
     }
     const int H = d->dims[1], A = d->n_actions, n_in = d->dims[0];
@@ -678,7 +730,10 @@ static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
     tc::k_mlp_backward_data_tc<<<grid_bwd, tc::TILE_M, tc::SmemBwd::TOTAL, st>>>(bp);
     int rc = launch_check("k_mlp_backward_data_tc");
     if (rc != SGK_OK) return rc;
-    const int64_t wg_tiles = (B + tc::WG_TILE - 1) / tc::WG_TILE;
+    // weight gradients: k_wgrad_mn (128-sample tiles, MN-major operands, no transposition) unless
+    // SGK_WGRAD_SCATTER selects the older scatter-transposing kernel (64-sample tiles) for A/B runs
+    static const bool scatter = getenv("SGK_WGRAD_SCATTER") != nullptr;
+    const int64_t wg_tiles = scatter ? (B + tc::WG_TILE - 1) / tc::WG_TILE : tiles;
     const unsigned wg_grid = (unsigned)std::min<int64_t>(wg_tiles, 3 * (int64_t)d->sm_count);
     const int64_t per_layer = (int64_t)wg_grid * tc::TILE_M * tc::N_HID;
     const int64_t need = 3 * per_layer;
@@ -697,6 +752,7 @@ static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
         tc::WgradParams &wp = wb.layer[y];
         wp.P = P; wp.ldp = ldp; wp.mdim = mdim; wp.Q = Q; wp.ldq = ldq; wp.ndim = ndim;
         wp.npad = (ndim + 1 + 15) / 16 * 16; wp.add_ones = 1; wp.rows = B; wp.partial = d->partials + (size_t)y * per_layer;
+        wp.scale_up = 0.5f * (float)B;      // the loss put 2/B into dQ: brings the error signals into FP16's range
         tc::WgradFinish &f = fb.layer[y];
         f.partial = wp.partial; f.npad = wp.npad; f.mdim = mdim; f.ndim = ndim;
         f.dW = d->grads + d->w_off[layer]; f.db = d->grads + d->b_off[layer];
@@ -707,7 +763,8 @@ static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
     set(2, dh1, H, H, d->x, n_in, n_in, 0);         // dW1, db1
     if (wg_tiles <= 3 * (int64_t)d->sm_count) {
         // small batches: one layer alone cannot fill the GPU (batch 4,096 = 64 tiles)
-        tc::k_wgrad_tc<<<dim3(wg_grid, 3), tc::TILE_M, tc::SmemWg::TOTAL, st>>>(wb);
+        if (scatter) tc::k_wgrad_tc<<<dim3(wg_grid, 3), tc::TILE_M, tc::SmemWg::TOTAL, st>>>(wb);
+        else tc::k_wgrad_mn<<<dim3(wg_grid, 3), tc::WM_THREADS, tc::SmemWm::TOTAL, st>>>(wb);
         tc::k_wgrad_finish<<<dim3((max_total + tc::WGF_ELEMS - 1) / tc::WGF_ELEMS, 3), tc::WGF_ELEMS * tc::WGF_LANES, 0, st>>>(fb, (int)wg_grid);
     } else {
         // large batches: every layer fills the GPU by itself; side by side they only
@@ -716,7 +773,8 @@ static int backward_tc(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t st)
             tc::WgradBatch one_w; one_w.layer[0] = wb.layer[y]; one_w.layer[1] = one_w.layer[2] = wb.layer[y];
             tc::WgradFinishBatch one_f; one_f.layer[0] = fb.layer[y]; one_f.layer[1] = one_f.layer[2] = fb.layer[y];
             const int total = fb.layer[y].mdim * (fb.layer[y].ndim + 1);
-            tc::k_wgrad_tc<<<dim3(wg_grid, 1), tc::TILE_M, tc::SmemWg::TOTAL, st>>>(one_w);
+            if (scatter) tc::k_wgrad_tc<<<dim3(wg_grid, 1), tc::TILE_M, tc::SmemWg::TOTAL, st>>>(one_w);
+            else tc::k_wgrad_mn<<<dim3(wg_grid, 1), tc::WM_THREADS, tc::SmemWm::TOTAL, st>>>(one_w);
             tc::k_wgrad_finish<<<dim3((total + tc::WGF_ELEMS - 1) / tc::WGF_ELEMS, 1), tc::WGF_ELEMS * tc::WGF_LANES, 0, st>>>(one_f, (int)wg_grid);
         }
     }
@@ -733,7 +791,8 @@ extern "C" int sgk_dqn_destroy(sgk_dqn *d)
                     d->b_idx, d->partials, d->q_env, d->boards_env, d->thr, d->status, d->xb, d->xb2, d->loss_partial};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < DQN_MAX_LAYERS; l++) { if (d->act[l]) cudaFree(d->act[l]); if (d->act_t[l]) cudaFree(d->act_t[l]); }
-    for (uint8_t *img : {d->w_image[0], d->w_image[1], d->w_image_bwd}) if (img) cudaFree(img);
+    for (uint8_t *img : {d->w_image[0], d->w_image[1], d->w_image_bwd, d->h_img[0], d->h_img[1]}) if (img) cudaFree(img);
+    if (d->fb_partial) cudaFree(d->fb_partial);
     if (d->sv_table) cudaFree(d->sv_table);
     if (d->sv_cursor) cudaFree(d->sv_cursor);
     if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
@@ -892,9 +951,13 @@ static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
 {
     const int L = d->n_linear, A = d->n_actions;
     int rc;
+    static const bool unfused = getenv("SGK_BWD_UNFUSED") != nullptr;
     if (d->use_tc) {
-        // tensor-core forwards; H1 / H2 come back in fp32 for the backward pass
-        if ((rc = forward_tc(d, 0, d->xb, B, d->act[2], d->act[0], d->act[1], st))) return rc;
+        // tensor-core forwards; H1 / H2 come back as FP16 operand images for the fused backward
+        // (in fp32 for the unfused A/B path)
+        if (unfused) rc = forward_tc(d, 0, d->xb, B, d->act[2], d->act[0], d->act[1], st);
+        else rc = forward_tc(d, 0, d->xb, B, d->act[2], nullptr, nullptr, st, true);
+        if (rc) return rc;
         if ((rc = forward_tc(d, 1, d->xb2, B, d->act_t[2], nullptr, nullptr, st))) return rc;
     } else {
         if ((rc = forward(d, 0, d->x, B, d->act, st))) return rc;        // Qs = Q(states)
@@ -907,7 +970,7 @@ static int learn_staged(sgk_dqn *d, int64_t B, float *loss_out, cudaStream_t st)
     k_loss_dq<<<grid_for(B, 256), 256, 0, st>>>(d->act[L - 1], d->b_a, d->y, A, B, d->bxb_loss, d->scalars, dcur);
     if ((rc = launch_check("k_loss"))) return rc;
     if (d->use_tc) {
-        if ((rc = backward_tc(d, B, dcur, st))) return rc;
+        if ((rc = unfused ? backward_tc(d, B, dcur, st) : backward_fused(d, B, dcur, st))) return rc;
     } else {
         // partial buffer for the split-K weight / bias gradients
         int64_t need = 0;

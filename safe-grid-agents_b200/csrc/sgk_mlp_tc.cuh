@@ -44,7 +44,12 @@ struct Params {
     float *q_out;                               // [rows][n_out]
     float *h1_out, *h2_out;                     // [rows][n_hidden] or null
     const uint8_t *w_image;                     // W1|W2|W3 already in the shared-memory operand layout (k_pack_weights), or null
+    // k_mlp_forward_ts: post-ReLU activations as FP16 operand images for the fused backward,
+    // [tile][14 chunks][128 rows][16 B] with a 1.0 at feature n_hidden (bias-gradient column), or null
+    uint8_t *h1_img, *h2_img;
 };
+constexpr int H_IMG_CHUNKS = N_HID / 8;                         // 14 chunks of 8 halfs
+constexpr int H_IMG_TILE_BYTES = H_IMG_CHUNKS * TILE_M * 16;    // 28,672 bytes per 128-row tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -557,6 +562,7 @@ struct WgradParams {
     int npad, add_ones;
     int64_t rows;
     float *partial;                    // [gridDim.x][128][npad]
+    float scale_up;                    // k_wgrad_mn: P is multiplied by this before FP16 conversion (and divided out at read-out)
 };
 
 constexpr int WG_TILE = 64;    // samples per tile: 60 KB of operands => three CTAs per SM hide the row-load latency
@@ -672,6 +678,435 @@ __global__ void __launch_bounds__(TILE_M, 1) k_wgrad_tc(const __grid_constant__ 
     else wgrad_layer(batch.layer[2]);
 }
 
+// k_wgrad_mn: the same reduction WITHOUT the transposition.  A tile of 128
+// samples is staged the way the forward stages its operands -- thread r copies
+// row r in 16-byte pieces, piece c to chunk c (coalesced loads, conflict-free
+// stores) -- and that very layout, read with MN-major descriptors, is the
+// transposed operand the reduction needs: for element (feature f, sample r) at
+// (f/8) * CHUNK + r * 16 + (f%8) * 2 the 8-feature groups are SBO = CHUNK bytes
+// apart, consecutive samples (the MMA's K) 16 bytes apart and groups of 8
+// samples LBO = 128 bytes apart: the canonical no-swizzle MN-major form.
+// Operands are FP16 (kind::f16, fp32 accumulate): MN-major TF32 operands exist
+// only in the 128B_BASE32B swizzled layout (which the K-major chain operands
+// cannot share), FP16 has TF32's 10 mantissa bits, and its narrow range is
+// handled by scaling the error signals up by `scale_up` (B/2, undoing the
+// loss's 2/B) before conversion and back down at read-out.  8 tcgen05.mma
+// (K = 16 samples each) fold a tile into the TMEM accumulator
+// D[m][n] += sum_r P[r][m] * Q[r][n].  61 KB of shared memory and 128 TMEM
+// columns per CTA: three CTAs per SM, loads of one overlapping MMAs of another.
+constexpr int CHUNK_F16 = TILE_M * 16;      // one 16-byte piece (8 halfs) of all 128 rows
+struct SmemWm {
+    static constexpr int PA = 0;                              // [16][128][16 B]  P rows, 128 features (M side)
+    static constexpr int QB = PA + 16 * CHUNK_F16;            // [14][128][16 B]  Q rows, 112 features (N side)
+    static constexpr int BAR = QB + 14 * CHUNK_F16;
+    static constexpr int TOTAL = BAR + 16;
+};
+constexpr int WM_THREADS = 256;
+
+// kind::f16 instruction descriptor: F16 operands (format 0), F32 accumulate, both operands MN-major
+__device__ __forceinline__ constexpr uint32_t make_idesc_f16_mn(int m, int n)
+{
+    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// two floats -> packed half2 bits, round to nearest, saturating (no infinities)
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// row (fp32, n values) -> FP16 chunks 0 .. of the chunk-major operand, scaled; invalid rows are zeros;
+// ones_at >= 0 plants a 1.0 at that feature (bias-gradient column)
+__device__ __forceinline__ void stage_rows_f16(uint8_t *buf, const float *row, int n, bool vec, bool valid, int r, int ones_at,
+                                               float scale)
+{
+    const int chunks = (n + (ones_at >= 0 ? 1 : 0) + 7) / 8;
+    for (int c0 = 0; c0 < chunks; c0 += 4) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            v[u] = (valid && 2 * c0 + u < 2 * chunks) ? load4(row, 8 * c0 + 4 * u, n, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int c = c0 + u;
+            if (c >= chunks) break;
+            float f[8] = {v[2 * u].x * scale, v[2 * u].y * scale, v[2 * u].z * scale, v[2 * u].w * scale,
+                          v[2 * u + 1].x * scale, v[2 * u + 1].y * scale, v[2 * u + 1].z * scale, v[2 * u + 1].w * scale};
+            if (valid && ones_at >= 0 && ones_at / 8 == c) f[ones_at & 7] = 1.f;
+            uint4 w;
+            w.x = pack_half2(f[0], f[1]); w.y = pack_half2(f[2], f[3]); w.z = pack_half2(f[4], f[5]); w.w = pack_half2(f[6], f[7]);
+            *reinterpret_cast<uint4 *>(buf + (size_t)c * CHUNK_F16 + r * 16) = w;
+        }
+    }
+}
+
+__device__ __forceinline__ void wgrad_mn_layer(const WgradParams &p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_base_slot;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + SmemWm::BAR);
+    const int warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < SmemWm::BAR / 16; e += blockDim.x)
+        reinterpret_cast<float4 *>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t tmem = tmem_alloc_and_sync(&tmem_base_slot, warp, 128);
+    const uint32_t a_p = smem_u32(smem + SmemWm::PA), b_q = smem_u32(smem + SmemWm::QB);
+    const uint32_t idesc = make_idesc_f16_mn(TILE_M, p.npad);
+    uint32_t phase = 0;
+    bool first = true;
+    const int r = threadIdx.x & (TILE_M - 1), side = threadIdx.x >> 7;          // threads 0..127: P rows, 128..255: Q rows
+    const bool pvec = (p.ldp & 3) == 0, qvec = (p.ldq & 3) == 0;
+    const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * TILE_M + r;
+        const bool valid = row < p.rows;
+        if (side == 0) stage_rows_f16(smem + SmemWm::PA, p.P + row * p.ldp, p.mdim, pvec, valid, r, -1, p.scale_up);
+        else stage_rows_f16(smem + SmemWm::QB, p.Q + row * p.ldq, p.ndim, qvec, valid, r, p.add_ones ? p.ndim : -1, 1.f);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < TILE_M / 16; s++)         // K = 16 samples per instruction: 256 bytes further along the rows
+                mma_f16(tmem, make_desc(a_p + s * 256, 128, CHUNK_F16), make_desc(b_q + s * 256, 128, CHUNK_F16), idesc,
+                        (!first || s > 0) ? 1u : 0u);
+            mma_commit(mbar);
+        }
+        first = false;
+        mbar_wait(mbar, phase); phase ^= 1;               // the operands may be overwritten by the next tile
+        tc_fence_after();
+    }
+    // accumulator row m (= feature m of P) -> partial; warps 0..3 own TMEM lanes 32 * warp ..
+    if (warp < 4) {
+        const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+        float *out = p.partial + ((size_t)blockIdx.x * TILE_M + threadIdx.x) * p.npad;
+        const int n_c8 = warp * 32 < p.mdim ? p.npad / 8 : 0;
+        const bool keep = (int)threadIdx.x < p.mdim;
+        const float down = 1.f / p.scale_up;
+        for (int c8 = 0; c8 < n_c8; c8++) {
+            float v[8];
+            tmem_ld8(tmem_row + c8 * 8, v);
+            if (keep) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) out[c8 * 8 + i] = v[i] * down;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
+}
+
+__global__ void __launch_bounds__(WM_THREADS, 3) k_wgrad_mn(const __grid_constant__ WgradBatch batch)
+{
+    if (blockIdx.y == 0) wgrad_mn_layer(batch.layer[0]);
+    else if (blockIdx.y == 1) wgrad_mn_layer(batch.layer[1]);
+    else wgrad_mn_layer(batch.layer[2]);
+}
+
+// ===================================================================== fused backward
+// k_mlp_backward_fused: the whole backward pass of a 128-sample tile without
+// leaving the SM -- error chain AND the three weight / bias gradients:
+//     dH2 = (dQ  * W3) .* (H2 > 0)      TF32 K-major chain (as k_mlp_backward_data_tc)
+//     dH1 = (dH2 * W2) .* (H1 > 0)
+//     dW3^T += [H2|1]^T dQ              FP16 MN-major reductions over the tile's samples,
+//     dW2   += dH2^T [H1|1]             accumulators resident in TMEM across all tiles
+//     dW1   += dH1^T [X|1]              of the CTA (the |1 column yields the bias gradient)
+// H1 / H2 arrive as the FP16 operand images the forward wrote (one TMA bulk copy
+// per tile and layer, 28 KB, landing directly in MMA operand layout; the next
+// tile's copy is issued the moment the buffer is free), the ReLU masks are read
+// from those images, dH2 / dH1 never exist outside shared memory, and each CTA
+// writes one partial per gradient that k_bwd_fused_finish folds in CTA order
+// (deterministic).  HBM traffic per tile: 2 x 28 KB of images + dQ + boards,
+// against 3 x (105 + 105) MB read and 210 MB written per 262,144-sample batch by
+// the unfused pair of kernels.
+struct FusedBwdParams {
+    const uint8_t *w_image;            // W3^T | W2^T, TF32 K-major B operands (BWD_IMAGE_BYTES)
+    const float *dq;                   // [rows][n_out], already scaled by the loss (2/B)
+    const uint8_t *h1_img, *h2_img;    // [tiles][14][128][16 B] FP16 images from k_mlp_forward_ts
+    const uint8_t *boards;             // [rows][n_in] uint8
+    int n_in, n_hidden, n_out, n1pad;  // n1pad: (n_in + 1) rounded up to 16 (N of the layer-1 reduction)
+    int64_t rows;
+    float scale_up;                    // FP16 copies of the error signals carry this factor (B/2)
+    float *partial;                    // [gridDim.x][128][16 + 112 + n1pad]
+};
+
+struct SmemFb {
+    static constexpr int W3T = 0;                                   // [2][112][16 B]
+    static constexpr int W2T = W3T + 2 * Smem::CHUNK_H;             // [26][112][16 B]
+    static constexpr int DQ = W2T + (K_HID / 4) * Smem::CHUNK_H;    // [2][128][16 B]   TF32 chain operand (K = 8)
+    static constexpr int DH = DQ + 2 * Smem::CHUNK_A;               // [26][128][16 B]  TF32 chain operand (dH2)
+    static constexpr int H2H = DH + (K_HID / 4) * Smem::CHUNK_A;    // [14][128][16 B]  FP16 image of H2 (M = 128 reads 2 chunks on, into H1H)
+    static constexpr int H1H = H2H + H_IMG_TILE_BYTES;              // [14][128][16 B]  FP16 image of H1
+    static constexpr int DHH = H1H + H_IMG_TILE_BYTES;              // [16][128][16 B]  FP16 dH2, then dH1 (M = 128)
+    static constexpr int DQH = DHH + 16 * CHUNK_F16;                // [2][128][16 B]   FP16 dQ (N = 16)
+    static constexpr int XH = DQH + 2 * CHUNK_F16;                  // [8][128][16 B]   FP16 boards | 1 (N <= 64)
+    static constexpr int BAR = XH + 8 * CHUNK_F16;
+    static constexpr int TOTAL = BAR + 64;
+};
+static_assert(SmemFb::DQ == (int)BWD_IMAGE_BYTES, "the backward weight image is W3^T | W2^T");
+static_assert(SmemFb::TOTAL <= 227 * 1024, "fused backward: shared memory plan exceeds one SM");
+constexpr int FB_THREADS = 256;
+constexpr uint32_t FB_D0 = 0, FB_D1 = 128, FB_ACC2 = 256, FB_ACC1 = 384, FB_ACC3 = 448;     // TMEM columns (512 allocated)
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ float half_bits_to_float(uint32_t h16)
+{
+    float f;
+    asm("{\n\t.reg .b16 h;\n\tcvt.u16.u32 h, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(h16 & 0xFFFFu));
+    return f;
+}
+
+// error-signal epilogue of one thread: 8-column groups [g0, g1) of its accumulator row, masked by the
+// FP16 activation image -> FP16 operand (x scale_up) and, for dH2, the TF32 chain operand
+__device__ __forceinline__ void fb_mask_epilogue(uint32_t lane_base, uint32_t d_col, const uint8_t *act_img, uint8_t *dst_f16,
+                                                 uint8_t *dst_tf32, int r, int g0, int g1, float scale_up)
+{
+#pragma unroll 1
+    for (int g = g0; g < g1; g++) {
+        float v[8];
+        tmem_ld8(lane_base + d_col + 8 * g, v);
+        const uint4 m = *reinterpret_cast<const uint4 *>(act_img + (size_t)g * CHUNK_F16 + r * 16);
+        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t hbits = (mw[i >> 1] >> (16 * (i & 1))) & 0x7FFFu;      // post-ReLU activation: > 0 iff any magnitude bit
+            v[i] = hbits ? v[i] : 0.f;
+        }
+        uint4 w;
+        w.x = pack_half2(v[0] * scale_up, v[1] * scale_up); w.y = pack_half2(v[2] * scale_up, v[3] * scale_up);
+        w.z = pack_half2(v[4] * scale_up, v[5] * scale_up); w.w = pack_half2(v[6] * scale_up, v[7] * scale_up);
+        *reinterpret_cast<uint4 *>(dst_f16 + (size_t)g * CHUNK_F16 + r * 16) = w;
+        if (dst_tf32) {
+            *reinterpret_cast<float4 *>(dst_tf32 + (size_t)(2 * g) * Smem::CHUNK_A + r * 16) =
+                make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+            *reinterpret_cast<float4 *>(dst_tf32 + (size_t)(2 * g + 1) * Smem::CHUNK_A + r * 16) =
+                make_float4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __grid_constant__ FusedBwdParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_base_slot;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + SmemFb::BAR);        // MMA groups
+    uint64_t *mbar_w = mbar + 1, *mbar_h2 = mbar + 2, *mbar_h1 = mbar + 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;                                           // this thread's row of the tile
+    const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
+    // activation buffers start out zero: padding chunks / rows are never written again
+    for (int e = threadIdx.x; e < (SmemFb::BAR - SmemFb::DQ) / 16; e += blockDim.x)
+        reinterpret_cast<float4 *>(smem + SmemFb::DQ)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1); mbar_init(mbar_w, 1); mbar_init(mbar_h2, 1); mbar_init(mbar_h1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(&tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        bulk_load(smem + SmemFb::W3T, p.w_image, BWD_IMAGE_BYTES, mbar_w);
+        if ((int64_t)blockIdx.x < n_tiles) {
+            bulk_load(smem + SmemFb::H2H, p.h2_img + (size_t)blockIdx.x * H_IMG_TILE_BYTES, H_IMG_TILE_BYTES, mbar_h2);
+            bulk_load(smem + SmemFb::H1H, p.h1_img + (size_t)blockIdx.x * H_IMG_TILE_BYTES, H_IMG_TILE_BYTES, mbar_h1);
+        }
+    }
+    const uint32_t tmem = tmem_base_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t s_w3t = smem_u32(smem + SmemFb::W3T), s_w2t = smem_u32(smem + SmemFb::W2T);
+    const uint32_t s_dq = smem_u32(smem + SmemFb::DQ), s_dh = smem_u32(smem + SmemFb::DH);
+    const uint32_t s_h2h = smem_u32(smem + SmemFb::H2H), s_h1h = smem_u32(smem + SmemFb::H1H);
+    const uint32_t s_dhh = smem_u32(smem + SmemFb::DHH), s_dqh = smem_u32(smem + SmemFb::DQH), s_xh = smem_u32(smem + SmemFb::XH);
+    constexpr uint32_t IDESC_CHAIN = make_idesc(TILE_M, N_HID);
+    const uint32_t idesc3 = make_idesc_f16_mn(TILE_M, N_OUT), idesc2 = make_idesc_f16_mn(TILE_M, N_HID);
+    const uint32_t idesc1 = make_idesc_f16_mn(TILE_M, p.n1pad);
+    uint32_t ph_mma = 0, ph_h2 = 0, ph_h1 = 0;
+    bool first = true, g3_pending = false;
+    const int x_chunks = p.n1pad / 8;
+    mbar_wait(mbar_w, 0);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * TILE_M + r;
+        const bool valid = row < p.rows;
+        // ---- this tile's dQ row (half 0) / board row (half 1) into registers, then wait for the previous
+        //      tile's last reduction (it reads XH and DHH) before overwriting its operands
+        float4 dqv = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t cells[16];
+        if (half == 0) {
+            if (valid) {
+                const float *q = p.dq + row * p.n_out;
+                dqv.x = q[0];
+                dqv.y = p.n_out > 1 ? q[1] : 0.f;
+                dqv.z = p.n_out > 2 ? q[2] : 0.f;
+                dqv.w = p.n_out > 3 ? q[3] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                uint32_t w = 0;
+                if (valid && 4 * j < p.n_in) {
+                    const uint8_t *b = p.boards + row * p.n_in + 4 * j;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (4 * j + i < p.n_in) w |= (uint32_t)__ldg(b + i) << (8 * i);
+                }
+                cells[j] = w;
+            }
+        }
+        if (g3_pending) { mbar_wait(mbar, ph_mma); ph_mma ^= 1; tc_fence_after(); g3_pending = false; }
+        if (half == 0) {
+            *reinterpret_cast<float4 *>(smem + SmemFb::DQ + r * 16) = make_float4(to_tf32(dqv.x), to_tf32(dqv.y), to_tf32(dqv.z), to_tf32(dqv.w));
+            uint4 w = make_uint4(pack_half2(dqv.x * p.scale_up, dqv.y * p.scale_up), pack_half2(dqv.z * p.scale_up, dqv.w * p.scale_up), 0u, 0u);
+            *reinterpret_cast<uint4 *>(smem + SmemFb::DQH + r * 16) = w;
+        } else {
+            for (int c = 0; c < x_chunks; c++) {          // 8 cells per FP16 chunk = two packed words
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) f[i] = (float)((cells[2 * c + (i >> 2)] >> (8 * (i & 3))) & 0xFFu);
+                if (valid && p.n_in / 8 == c) f[p.n_in & 7] = 1.f;
+                uint4 w;
+                w.x = pack_half2(f[0], f[1]); w.y = pack_half2(f[2], f[3]); w.z = pack_half2(f[4], f[5]); w.w = pack_half2(f[6], f[7]);
+                *reinterpret_cast<uint4 *>(smem + SmemFb::XH + (size_t)c * CHUNK_F16 + r * 16) = w;
+            }
+        }
+        mbar_wait(mbar_h2, ph_h2); ph_h2 ^= 1;            // H2 image of this tile has landed
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        // ---- group 1: dH2 pre-activation, and dW3^T += [H2|1]^T dQ
+        if (threadIdx.x == 0) {
+            mma_tf32(tmem + FB_D0, make_desc(s_dq, Smem::CHUNK_A, 128), make_desc(s_w3t, Smem::CHUNK_H, 128), IDESC_CHAIN, 0);
+            for (int s = 0; s < TILE_M / 16; s++)
+                mma_f16(tmem + FB_ACC3, make_desc(s_h2h + s * 256, 128, CHUNK_F16), make_desc(s_dqh + s * 256, 128, CHUNK_F16), idesc3,
+                        (!first || s > 0) ? 1u : 0u);
+            mma_commit(mbar);
+        }
+        mbar_wait(mbar, ph_mma); ph_mma ^= 1;
+        tc_fence_after();
+        fb_mask_epilogue(lane_base, FB_D0, smem + SmemFb::H2H, smem + SmemFb::DHH, smem + SmemFb::DH, r, half ? 7 : 0, half ? 13 : 7, p.scale_up);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        const int64_t next = tile + gridDim.x;
+        // ---- group 2: dH1 pre-activation, and dW2 += dH2^T [H1|1]; the H2 buffer is free for the next tile
+        if (threadIdx.x == 0) {
+            if (next < n_tiles) bulk_load(smem + SmemFb::H2H, p.h2_img + (size_t)next * H_IMG_TILE_BYTES, H_IMG_TILE_BYTES, mbar_h2);
+            mbar_wait(mbar_h1, ph_h1);
+            for (int k = 0; k < K_HID / 8; k++)
+                mma_tf32(tmem + FB_D1, make_desc(s_dh + k * 2 * Smem::CHUNK_A, Smem::CHUNK_A, 128),
+                         make_desc(s_w2t + k * 2 * Smem::CHUNK_H, Smem::CHUNK_H, 128), IDESC_CHAIN, k > 0);
+            for (int s = 0; s < TILE_M / 16; s++)
+                mma_f16(tmem + FB_ACC2, make_desc(s_dhh + s * 256, 128, CHUNK_F16), make_desc(s_h1h + s * 256, 128, CHUNK_F16), idesc2,
+                        (!first || s > 0) ? 1u : 0u);
+            mma_commit(mbar);
+        }
+        mbar_wait(mbar_h1, ph_h1); ph_h1 ^= 1;            // everyone reads the H1 image below
+        mbar_wait(mbar, ph_mma); ph_mma ^= 1;
+        tc_fence_after();
+        fb_mask_epilogue(lane_base, FB_D1, smem + SmemFb::H1H, smem + SmemFb::DHH, nullptr, r, half ? 7 : 0, half ? 13 : 7, p.scale_up);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        // ---- group 3: dW1 += dH1^T [X|1]; the H1 buffer is free for the next tile
+        if (threadIdx.x == 0) {
+            if (next < n_tiles) bulk_load(smem + SmemFb::H1H, p.h1_img + (size_t)next * H_IMG_TILE_BYTES, H_IMG_TILE_BYTES, mbar_h1);
+            for (int s = 0; s < TILE_M / 16; s++)
+                mma_f16(tmem + FB_ACC1, make_desc(s_dhh + s * 256, 128, CHUNK_F16), make_desc(s_xh + s * 256, 128, CHUNK_F16), idesc1,
+                        (!first || s > 0) ? 1u : 0u);
+            mma_commit(mbar);
+        }
+        g3_pending = true;
+        first = false;
+    }
+    if (g3_pending) { mbar_wait(mbar, ph_mma); ph_mma ^= 1; tc_fence_after(); }
+    // ---- accumulators -> this CTA's partial: row m, columns [acc3 (16) | acc2 (112) | acc1 (n1pad)], scaled back
+    if (!first) {
+        const int stride = N_OUT + N_HID + p.n1pad;
+        float *out = p.partial + ((size_t)blockIdx.x * TILE_M + r) * stride;
+        const float down = 1.f / p.scale_up;
+        const int c_lo = half ? (N_OUT + N_HID) / 2 : 0, c_hi = half ? stride : (N_OUT + N_HID) / 2;     // multiples of 8
+        for (int c = c_lo; c < c_hi; c += 8) {
+            const uint32_t col = c < N_OUT ? FB_ACC3 + c : c < N_OUT + N_HID ? FB_ACC2 + (c - N_OUT) : FB_ACC1 + (c - N_OUT - N_HID);
+            float v[8];
+            tmem_ld8(lane_base + col, v);
+            *reinterpret_cast<float4 *>(out + c) = make_float4(v[0] * down, v[1] * down, v[2] * down, v[3] * down);
+            *reinterpret_cast<float4 *>(out + c + 4) = make_float4(v[4] * down, v[5] * down, v[6] * down, v[7] * down);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+
+// partials -> gradients, torch layout: one thread per parameter, CTA partials summed in index order
+struct FusedFinish {
+    const float *partial; int n_partials, n_in, n_hidden, n_out, n1pad;
+    float *dW1, *db1, *dW2, *db2, *dW3, *db3;
+};
+__global__ void __launch_bounds__(256) k_bwd_fused_finish(const FusedFinish f)
+{
+    const int H = f.n_hidden, A = f.n_out, I = f.n_in;
+    const int n1 = H * (I + 1), n2 = H * (H + 1), n3 = A * (H + 1);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n1 + n2 + n3) return;
+    const int stride = N_OUT + N_HID + f.n1pad;
+    int m, col;
+    float *dst;
+    if (e < n1) {                                     // dW1[h][i] | db1[h]: accumulator 1, row h, column i (bias: column n_in)
+        m = e / (I + 1); const int i = e - m * (I + 1);
+        col = N_OUT + N_HID + i;
+        dst = i < I ? f.dW1 + (size_t)m * I + i : f.db1 + m;
+    } else if (e < n1 + n2) {                         // dW2[o][h] | db2[o]
+        const int k = e - n1;
+        m = k / (H + 1); const int h = k - m * (H + 1);
+        col = N_OUT + h;
+        dst = h < H ? f.dW2 + (size_t)m * H + h : f.db2 + m;
+    } else {                                          // dW3[a][h] | db3[a]: accumulator 3 holds the TRANSPOSE, row h (bias: row n_hidden)
+        const int k = e - n1 - n2;
+        const int a = k / (H + 1), h = k - a * (H + 1);
+        m = h; col = a;
+        dst = h < H ? f.dW3 + (size_t)a * H + h : f.db3 + a;
+    }
+    const float *src = f.partial + (size_t)m * stride + col;
+    const size_t step = (size_t)TILE_M * stride;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int g = 0;
+    for (; g + 3 < f.n_partials; g += 4) {
+        s0 += src[(size_t)g * step]; s1 += src[(size_t)(g + 1) * step];
+        s2 += src[(size_t)(g + 2) * step]; s3 += src[(size_t)(g + 3) * step];
+    }
+    for (; g < f.n_partials; g++) s0 += src[(size_t)g * step];
+    *dst = (s0 + s1) + (s2 + s3);
+}
+
 // dW[m][n] = sum_g partial[g][m][n], db[m] = sum_g partial[g][m][ndim].
 // A block folds 32 elements: 8 lanes of partials (g = lane, lane + 8, ...) per
 // element, then the 8 lane sums in lane order -- a fixed order, so the result
@@ -750,9 +1185,11 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float *w1, const flo
 //     writes both back to TMEM (tcgen05.st), where the next layer's MMAs take
 //     them as the A operand (tcgen05.mma with A in TMEM) -- shared memory
 //     holds only the two weight images (160 KB) and the board tile;
-//   * 8 warps: both warpgroups drain the accumulator (warp w owns TMEM lanes
-//     32*(w%4).., the warpgroup picks the column half), and the next tile's
-//     boards are fetched while the current tile computes.
+//   * 16 warps drain the accumulator: warp w owns TMEM lanes 32*(w%4).., and
+//     the four warps of a lane quadrant split the columns 32 / 32 / 32 / 16;
+//     each issues all its tcgen05.ld before one wait, so the epilogue is one
+//     TMEM round trip deep; the next tile's boards are fetched while the
+//     current tile computes.
 struct SmemTs {
     static constexpr int HI = 0;                                   // W1|W2|W3 (layout of Smem), TF32-rounded
     static constexpr int LO = FWD_IMAGE_BYTES;                     // ... remainders
@@ -761,7 +1198,7 @@ struct SmemTs {
     static constexpr int BAR = BIAS + (2 * N_HID + N_OUT) * 4;
     static constexpr int TOTAL = BAR + 32;
 };
-constexpr int TS_THREADS = 256;
+constexpr int TS_THREADS = 512;      // 16 warps: 4 per TMEM lane quadrant, each draining a quarter of the columns
 constexpr uint32_t TS_D_A = 0, TS_D_B = 128, TS_H_HI = 256, TS_H_LO = 384;     // TMEM columns (512 allocated)
 
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
@@ -800,33 +1237,77 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8])
 
 // hidden-layer epilogue of one thread: columns [c0, c1) of its accumulator row ->
 // bias, ReLU -> hi / lo TF32 parts into the A-operand region of TMEM (+ fp32 copy in HBM)
-template <bool X3>
-__device__ __forceinline__ void ts_hidden_epilogue(uint32_t lane_base, uint32_t d_col, const float *bias, int c0, int c1,
-                                                   float *h_out_row, int n_hidden)
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32], bool second)
 {
+    uint32_t r[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) r[i] = 0u;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    if (second)           // warp-uniform
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr + 16));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi);
+
+template <bool X3>
+__device__ __forceinline__ void ts_hidden_epilogue(uint32_t lane_base, uint32_t d_col, const float *bias, int quarter,
+                                                   float *h_out_row, int n_hidden, uint8_t *img_tile = nullptr,
+                                                   int row_in_tile = 0, bool valid = true)
+{
+    // this warp's columns: [32 * quarter, +32), the last quarter [96, 112)
+    const int c0 = 32 * quarter;
+    const bool wide = quarter < 3;
     const bool vec = (n_hidden & 3) == 0;
-#pragma unroll 1
-    for (int c = c0; c < c1; c += 16) {
-        float v[16];
-        tmem_ld16(lane_base + d_col + c, v);
+    float v[32];
+    tmem_ld32(lane_base + d_col + c0, v, wide);
 #pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + bias[c + i], 0.f);
-        if (h_out_row) {
+    for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i] + bias[(c0 + i) < N_HID ? (c0 + i) : 0], 0.f);
+    if (h_out_row) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) store4(h_out_row, c + i, n_hidden, vec, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        for (int i = 0; i < 32; i += 4)
+            if (wide || i < 16) store4(h_out_row, c0 + i, n_hidden, vec, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+    }
+    if (img_tile) {
+        // FP16 image of the tile for the fused backward: chunk (c0 / 8 + g) holds features c0 + 8g .. + 7 of
+        // all 128 rows, 16 bytes per row -- a warp's 32 rows are 512 contiguous bytes (coalesced)
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if (c0 + 8 * g >= N_HID) break;
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) f[i] = valid ? v[8 * g + i] : 0.f;
+            if (valid && n_hidden >= c0 + 8 * g && n_hidden < c0 + 8 * g + 8) f[n_hidden - (c0 + 8 * g)] = 1.f;
+            uint4 w;
+            w.x = pack_half2(f[0], f[1]); w.y = pack_half2(f[2], f[3]); w.z = pack_half2(f[4], f[5]); w.w = pack_half2(f[6], f[7]);
+            *reinterpret_cast<uint4 *>(img_tile + (size_t)(c0 / 8 + g) * (TILE_M * 16) + row_in_tile * 16) = w;
         }
+    }
 #pragma unroll
-        for (int g = 0; g < 2; g++) {
-            if (c + 8 * g >= K_HID) break;            // the 112-column accumulator has 104 operand columns
-            float hi[8], lo[8];
+    for (int g = 0; g < 4; g++) {
+        if (c0 + 8 * g >= K_HID) break;               // the 112-column accumulator has 104 operand columns (warp-uniform)
+        float hi[8], lo[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                hi[i] = to_tf32(v[8 * g + i]);
-                lo[i] = X3 ? to_tf32(v[8 * g + i] - hi[i]) : 0.f;
-            }
-            tmem_st8(lane_base + TS_H_HI + c + 8 * g, hi);
-            if (X3) tmem_st8(lane_base + TS_H_LO + c + 8 * g, lo);
+        for (int i = 0; i < 8; i++) {
+            hi[i] = to_tf32(v[8 * g + i]);
+            lo[i] = X3 ? to_tf32(v[8 * g + i] - hi[i]) : 0.f;
         }
+        tmem_st8(lane_base + TS_H_HI + c0 + 8 * g, hi);
+        if (X3) tmem_st8(lane_base + TS_H_LO + c0 + 8 * g, lo);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -840,7 +1321,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_mlp_forward_ts(const Params p
     uint64_t *mbar_w = mbar + 1;
     float *bias = reinterpret_cast<float *>(smem + SmemTs::BIAS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant; column half
+    const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant; column quarter (0..3)
     const int row_in_tile = quad * 32 + lane;
     const int k_in = (p.n_in + 7) & ~7;                   // 36 -> 40, 25 -> 32, 63 -> 64
     const int n_chunks = k_in / 4;
@@ -873,13 +1354,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_mlp_forward_ts(const Params p
     constexpr uint32_t IDESC_HID = make_idesc(TILE_M, N_HID), IDESC_OUT = make_idesc(TILE_M, N_OUT);
     uint32_t phase = 0;
 
-    // this thread's share of a board row: chunks half, half + 2, ... (4 cells each), kept in registers
-    uint32_t cells[MAX_K_IN / 8];
+    // this thread's share of a board row: chunks quarter, quarter + 4, ... (4 cells each), kept in registers
+    uint32_t cells[MAX_K_IN / 16];
     auto fetch = [&](int64_t tile) {
         const int64_t row = tile * TILE_M + row_in_tile;
 #pragma unroll
-        for (int j = 0; j < MAX_K_IN / 8; j++) {
-            const int c = half + 2 * j;
+        for (int j = 0; j < MAX_K_IN / 16; j++) {
+            const int c = half + 4 * j;
             uint32_t w = 0;
             if (c < n_chunks && row < p.rows) {
                 const uint8_t *b = p.boards + row * p.n_in + 4 * c;
@@ -892,8 +1373,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_mlp_forward_ts(const Params p
     };
     auto stage = [&]() {
 #pragma unroll
-        for (int j = 0; j < MAX_K_IN / 8; j++) {
-            const int c = half + 2 * j;
+        for (int j = 0; j < MAX_K_IN / 16; j++) {
+            const int c = half + 4 * j;
             if (c < n_chunks) {
                 const uint32_t w = cells[j];
                 *reinterpret_cast<float4 *>(smem + SmemTs::X + (size_t)c * Smem::CHUNK_A + row_in_tile * 16) =
@@ -904,8 +1385,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_mlp_forward_ts(const Params p
     const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
     if ((int64_t)blockIdx.x < n_tiles) { fetch(blockIdx.x); stage(); }
     mbar_wait(mbar_w, 0);                                  // weight images have landed
-    // column split of the 104 operand columns between the warpgroups (multiples of 16 for tcgen05.ld.x16)
-    const int c0 = half ? 64 : 0, c1 = half ? N_HID : 64;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row = tile * TILE_M + row_in_tile;
         const bool valid = row < p.rows;
@@ -929,7 +1408,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_mlp_forward_ts(const Params p
         mbar_wait(mbar, phase); phase ^= 1;
         tc_fence_after();
         if (more) stage();                                 // layer 1 is done with the board tile
-        ts_hidden_epilogue<X3>(lane_base, TS_D_A, bias, c0, c1, (valid && p.h1_out) ? p.h1_out + row * p.n_hidden : nullptr, p.n_hidden);
+        ts_hidden_epilogue<X3>(lane_base, TS_D_A, bias, half, (valid && p.h1_out) ? p.h1_out + row * p.n_hidden : nullptr, p.n_hidden,
+                               p.h1_img ? p.h1_img + tile * H_IMG_TILE_BYTES : nullptr, row_in_tile, valid);
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -947,7 +1427,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_mlp_forward_ts(const Params p
         }
         mbar_wait(mbar, phase); phase ^= 1;
         tc_fence_after();
-        ts_hidden_epilogue<X3>(lane_base, TS_D_B, bias + N_HID, c0, c1, (valid && p.h2_out) ? p.h2_out + row * p.n_hidden : nullptr, p.n_hidden);
+        ts_hidden_epilogue<X3>(lane_base, TS_D_B, bias + N_HID, half, (valid && p.h2_out) ? p.h2_out + row * p.n_hidden : nullptr, p.n_hidden,
+                               p.h2_img ? p.h2_img + tile * H_IMG_TILE_BYTES : nullptr, row_in_tile, valid);
         tc_fence_before();
         __syncthreads();
         tc_fence_after();

@@ -20,8 +20,11 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-shared",
     "--threads", "2",           # the two translation units compile side by side
-    "--split-compile", "0",     # ... and each one's kernels are optimised on all cores (build time 3m40 -> under 1m)
 ]
+# SGK_FAST_BUILD=1: optimise each translation unit's kernels on all cores (3m40 -> 1m20).  Development
+# only: measured -2.8 % on the headline rollout kernel (4.61 -> 4.74 ms per launch, same box A/B,
+# profiles/r02_notes.md), so release builds -- build() below, what the driver runs -- do without.
+FAST_FLAGS = ["--split-compile", "0"]
 
 
 def stale():
@@ -36,7 +39,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    fast = FAST_FLAGS if os.environ.get("SGK_FAST_BUILD") else []
+    cmd = [nvcc] + NVCC_FLAGS + fast + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return LIB
