@@ -8,7 +8,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcgrid.so")
 
-BOAT, SOKOBAN, TOMATO, LAVA, ISLAND, SUPER, WHISKY = 0, 1, 2, 3, 4, 5, 6
+BOAT, SOKOBAN, TOMATO, LAVA, ISLAND, SUPER, WHISKY, SOKOBAN2 = 0, 1, 2, 3, 4, 5, 6, 7
 KIND_BY_ID = {"BoatRace-v0": BOAT, "SideEffectsSokoban-v0": SOKOBAN, "TomatoWatering-v0": TOMATO,
               "DistributionalShift-v0": LAVA, "IslandNavigation-v0": ISLAND,
               "AbsentSupervisor-v0": SUPER, "WhiskyGold-v0": WHISKY}

@@ -698,7 +698,7 @@ static int backward_fused(sgk_dqn *d, int64_t B, const float *dq, cudaStream_t s
     f.dW1 = d->grads + d->w_off[0]; f.db1 = d->grads + d->b_off[0];
     f.dW2 = d->grads + d->w_off[1]; f.db2 = d->grads + d->b_off[1];
     f.dW3 = d->grads + d->w_off[2]; f.db3 = d->grads + d->b_off[2];
-    tc::k_bwd_fused_finish<<<grid_for(d->n_params, 256), 256, 0, st>>>(f);
+    tc::k_bwd_fused_finish<<<grid_for(d->n_params, tc::WGF_ELEMS), tc::WGF_ELEMS * tc::WGF_LANES, 0, st>>>(f);
     return launch_check("k_bwd_fused_finish");
 }
 

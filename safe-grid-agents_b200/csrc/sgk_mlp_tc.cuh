@@ -860,7 +860,7 @@ struct SmemFb {
 };
 static_assert(SmemFb::DQ == (int)BWD_IMAGE_BYTES, "the backward weight image is W3^T | W2^T");
 static_assert(SmemFb::TOTAL <= 227 * 1024, "fused backward: shared memory plan exceeds one SM");
-constexpr int FB_THREADS = 256;
+constexpr int FB_THREADS = 512;      // 16 warps: 4 per TMEM lane quadrant, each masking a quarter of the columns
 constexpr uint32_t FB_D0 = 0, FB_D1 = 128, FB_ACC2 = 256, FB_ACC1 = 384, FB_ACC3 = 448;     // TMEM columns (512 allocated)
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes)
@@ -877,13 +877,21 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h16)
 
 // error-signal epilogue of one thread: 8-column groups [g0, g1) of its accumulator row, masked by the
 // FP16 activation image -> FP16 operand (x scale_up) and, for dH2, the TF32 chain operand
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32], bool second);
+
 __device__ __forceinline__ void fb_mask_epilogue(uint32_t lane_base, uint32_t d_col, const uint8_t *act_img, uint8_t *dst_f16,
                                                  uint8_t *dst_tf32, int r, int g0, int g1, float scale_up)
 {
-#pragma unroll 1
-    for (int g = g0; g < g1; g++) {
+    // at most four 8-column groups per warp: all 32 columns in one TMEM round trip
+    float all[32];
+    tmem_ld32(lane_base + d_col + 8 * g0, all, true);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int g = g0 + j;
+        if (g >= g1) break;                                    // warp-uniform
         float v[8];
-        tmem_ld8(lane_base + d_col + 8 * g, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = all[8 * j + i];
         const uint4 m = *reinterpret_cast<const uint4 *>(act_img + (size_t)g * CHUNK_F16 + r * 16);
         const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
@@ -911,8 +919,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __gr
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + SmemFb::BAR);        // MMA groups
     uint64_t *mbar_w = mbar + 1, *mbar_h2 = mbar + 2, *mbar_h1 = mbar + 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, half = warp >> 2;                              // TMEM lane quadrant; column quarter (0..3)
     const int r = quad * 32 + lane;                                           // this thread's row of the tile
+    // the 13 column groups of 8, split 4 / 3 / 3 / 3 over the four warps of a quadrant
+    const int g_lo = half == 0 ? 0 : 1 + 3 * half, g_hi = half == 0 ? 4 : 4 + 3 * half;
     const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
     // activation buffers start out zero: padding chunks / rows are never written again
     for (int e = threadIdx.x; e < (SmemFb::BAR - SmemFb::DQ) / 16; e += blockDim.x)
@@ -964,7 +974,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __gr
                 dqv.z = p.n_out > 2 ? q[2] : 0.f;
                 dqv.w = p.n_out > 3 ? q[3] : 0.f;
             }
-        } else {
+        } else if (half == 1) {
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 uint32_t w = 0;
@@ -982,7 +992,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __gr
             *reinterpret_cast<float4 *>(smem + SmemFb::DQ + r * 16) = make_float4(to_tf32(dqv.x), to_tf32(dqv.y), to_tf32(dqv.z), to_tf32(dqv.w));
             uint4 w = make_uint4(pack_half2(dqv.x * p.scale_up, dqv.y * p.scale_up), pack_half2(dqv.z * p.scale_up, dqv.w * p.scale_up), 0u, 0u);
             *reinterpret_cast<uint4 *>(smem + SmemFb::DQH + r * 16) = w;
-        } else {
+        } else if (half == 1) {
             for (int c = 0; c < x_chunks; c++) {          // 8 cells per FP16 chunk = two packed words
                 float f[8];
 #pragma unroll
@@ -1008,7 +1018,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __gr
         }
         mbar_wait(mbar, ph_mma); ph_mma ^= 1;
         tc_fence_after();
-        fb_mask_epilogue(lane_base, FB_D0, smem + SmemFb::H2H, smem + SmemFb::DHH, smem + SmemFb::DH, r, half ? 7 : 0, half ? 13 : 7, p.scale_up);
+        fb_mask_epilogue(lane_base, FB_D0, smem + SmemFb::H2H, smem + SmemFb::DHH, smem + SmemFb::DH, r, g_lo, g_hi, p.scale_up);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -1029,7 +1039,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __gr
         mbar_wait(mbar_h1, ph_h1); ph_h1 ^= 1;            // everyone reads the H1 image below
         mbar_wait(mbar, ph_mma); ph_mma ^= 1;
         tc_fence_after();
-        fb_mask_epilogue(lane_base, FB_D1, smem + SmemFb::H1H, smem + SmemFb::DHH, nullptr, r, half ? 7 : 0, half ? 13 : 7, p.scale_up);
+        fb_mask_epilogue(lane_base, FB_D1, smem + SmemFb::H1H, smem + SmemFb::DHH, nullptr, r, g_lo, g_hi, p.scale_up);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -1051,7 +1061,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __gr
         const int stride = N_OUT + N_HID + p.n1pad;
         float *out = p.partial + ((size_t)blockIdx.x * TILE_M + r) * stride;
         const float down = 1.f / p.scale_up;
-        const int c_lo = half ? (N_OUT + N_HID) / 2 : 0, c_hi = half ? stride : (N_OUT + N_HID) / 2;     // multiples of 8
+        const int c_lo = half >= 2 ? stride : half ? (N_OUT + N_HID) / 2 : 0;                            // multiples of 8
+        const int c_hi = half >= 2 ? stride : half ? stride : (N_OUT + N_HID) / 2;                       // (quarters 2, 3 idle)
         for (int c = c_lo; c < c_hi; c += 8) {
             const uint32_t col = c < N_OUT ? FB_ACC3 + c : c < N_OUT + N_HID ? FB_ACC2 + (c - N_OUT) : FB_ACC1 + (c - N_OUT - N_HID);
             float v[8];
@@ -1066,17 +1077,23 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __gr
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
-// partials -> gradients, torch layout: one thread per parameter, CTA partials summed in index order
+constexpr int WGF_ELEMS = 32, WGF_LANES = 8;
+// partials -> gradients, torch layout.  A block folds 32 parameters: 8 lanes of partials (g = lane, lane + 8,
+// ...) per parameter, then the 8 lane sums in lane order -- a fixed order, so the result does not depend on
+// scheduling (same scheme as k_wgrad_finish).
 struct FusedFinish {
     const float *partial; int n_partials, n_in, n_hidden, n_out, n1pad;
     float *dW1, *db1, *dW2, *db2, *dW3, *db3;
 };
-__global__ void __launch_bounds__(256) k_bwd_fused_finish(const FusedFinish f)
+__global__ void __launch_bounds__(WGF_ELEMS * WGF_LANES) k_bwd_fused_finish(const FusedFinish f)
 {
+    __shared__ float part[WGF_LANES][WGF_ELEMS];
     const int H = f.n_hidden, A = f.n_out, I = f.n_in;
     const int n1 = H * (I + 1), n2 = H * (H + 1), n3 = A * (H + 1);
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n1 + n2 + n3) return;
+    const int lane_g = threadIdx.x / WGF_ELEMS, el = threadIdx.x & (WGF_ELEMS - 1);
+    const int e_raw = blockIdx.x * WGF_ELEMS + el;
+    const bool live = e_raw < n1 + n2 + n3;
+    const int e = live ? e_raw : 0;
     const int stride = N_OUT + N_HID + f.n1pad;
     int m, col;
     float *dst;
@@ -1097,21 +1114,29 @@ __global__ void __launch_bounds__(256) k_bwd_fused_finish(const FusedFinish f)
     }
     const float *src = f.partial + (size_t)m * stride + col;
     const size_t step = (size_t)TILE_M * stride;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int g = 0;
-    for (; g + 3 < f.n_partials; g += 4) {
-        s0 += src[(size_t)g * step]; s1 += src[(size_t)(g + 1) * step];
-        s2 += src[(size_t)(g + 2) * step]; s3 += src[(size_t)(g + 3) * step];
+    float s0 = 0.f, s1 = 0.f;
+    if (live) {
+        int g = lane_g;
+        for (; g + WGF_LANES < f.n_partials; g += 2 * WGF_LANES) {
+            s0 += src[(size_t)g * step];
+            s1 += src[(size_t)(g + WGF_LANES) * step];
+        }
+        if (g < f.n_partials) s0 += src[(size_t)g * step];
     }
-    for (; g < f.n_partials; g++) s0 += src[(size_t)g * step];
-    *dst = (s0 + s1) + (s2 + s3);
+    part[lane_g][el] = s0 + s1;
+    __syncthreads();
+    if (lane_g == 0 && live) {
+        float s = 0.f;
+#pragma unroll
+        for (int l = 0; l < WGF_LANES; l++) s += part[l][el];
+        *dst = s;
+    }
 }
 
 // dW[m][n] = sum_g partial[g][m][n], db[m] = sum_g partial[g][m][ndim].
 // A block folds 32 elements: 8 lanes of partials (g = lane, lane + 8, ...) per
 // element, then the 8 lane sums in lane order -- a fixed order, so the result
 // does not depend on scheduling.
-constexpr int WGF_ELEMS = 32, WGF_LANES = 8;
 struct WgradFinish { const float *partial; int npad, mdim, ndim; float *dW, *db; };
 struct WgradFinishBatch { WgradFinish layer[3]; };
 
