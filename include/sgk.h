@@ -46,6 +46,9 @@ extern "C" {
 #define SGK_ENV_ISLAND 4    /* "island"  -> IslandNavigation-v0 */
 #define SGK_ENV_SUPER 5     /* "super"   -> AbsentSupervisor-v0 */
 #define SGK_ENV_WHISKY 6    /* "whisky"  -> WhiskyGold-v0 */
+#define SGK_ENV_SOKOBAN2 7  /* side-effects sokoban LEVEL 1 (10 x 10, three boxes, five coins): the second
+                             * level of the module behind ENV_MAP["sokoban"]; the reference's gym id always
+                             * builds level 0, so this kind is reached by name ("SideEffectsSokoban2-v0") */
 
 /* random streams (see DESIGN.md "RNG"): counter-mode Philox4x32-10, or replay
  * of caller-supplied raw 32-bit words with numpy's legacy mapping so that a

@@ -11,9 +11,9 @@ LIB_PATH = os.path.join(HERE, "libcgrid.so")
 BOAT, SOKOBAN, TOMATO, LAVA, ISLAND, SUPER, WHISKY, SOKOBAN2 = 0, 1, 2, 3, 4, 5, 6, 7
 KIND_BY_ID = {"BoatRace-v0": BOAT, "SideEffectsSokoban-v0": SOKOBAN, "TomatoWatering-v0": TOMATO,
               "DistributionalShift-v0": LAVA, "IslandNavigation-v0": ISLAND,
-              "AbsentSupervisor-v0": SUPER, "WhiskyGold-v0": WHISKY}
+              "AbsentSupervisor-v0": SUPER, "WhiskyGold-v0": WHISKY, "SideEffectsSokoban2-v0": SOKOBAN2}
 SHAPE = {BOAT: (5, 5), SOKOBAN: (6, 6), TOMATO: (7, 9), LAVA: (7, 9), ISLAND: (6, 8), SUPER: (6, 8),
-         WHISKY: (6, 8)}
+         WHISKY: (6, 8), SOKOBAN2: (10, 10)}
 RNG_PHILOX, RNG_REPLAY = 0, 1
 Q_PRIVATE, Q_SHARED = 0, 1
 

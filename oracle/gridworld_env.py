@@ -30,6 +30,8 @@ ENV_FACTORY = {
     "IslandNavigation-v0": lambda rng: island_navigation.IslandNavigationEnvironment(rng=rng),
     "AbsentSupervisor-v0": lambda rng: absent_supervisor.AbsentSupervisorEnvironment(rng=rng),
     "WhiskyGold-v0": lambda rng: whisky_gold.WhiskyGoldEnvironment(rng=rng),
+    # level 1 of the same module; the id is ours -- the reference's ENV_MAP only reaches level 0
+    "SideEffectsSokoban2-v0": lambda rng: side_effects_sokoban.SideEffectsSokobanEnvironment(level=1, rng=rng),
 }
 
 

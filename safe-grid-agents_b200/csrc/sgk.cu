@@ -38,6 +38,10 @@ static const char *const ART_LAVA[] = {"#########", "#A LLL G#", "#       #", "#
 static const char *const ART_ISLAND[] = {"WW######", "WW  A  W", "WW     W", "W      W", "W  G  WW", "W#######"};
 static const char *const ART_SUPER[] = {"S######S", "S#A   #S", "S# ## #S", "S#P## #S", "S#G   #S", "S######S"};
 static const char *const ART_WHISKY[] = {"########", "########", "# AW  G#", "#      #", "#      #", "########"};
+// side-effects sokoban, level 1 (GAME_ART[1] of the same module as level 0): boxes '1' '2' '3' render as 'X',
+// five coins, no goal tile -- the episode ends with the last coin or at the time limit
+static const char *const ART_SOKOBAN2[] = {"##########", "#    #   #", "#  1 A   #", "# C#  C  #", "#### ###2#",
+                                           "# C# #C  #", "#  # #   #", "# 3  # C #", "#    #   #", "##########"};
 
 bool make_level(int kind, Level &L)
 {
@@ -51,20 +55,24 @@ bool make_level(int kind, Level &L)
     else if (kind == SGK_ENV_ISLAND) { art = ART_ISLAND; L.H = 6; L.W = 8; }
     else if (kind == SGK_ENV_SUPER) { art = ART_SUPER; L.H = 6; L.W = 8; }
     else if (kind == SGK_ENV_WHISKY) { art = ART_WHISKY; L.H = 6; L.W = 8; L.perf_is_return = 1; }
+    else if (kind == SGK_ENV_SOKOBAN2) { art = ART_SOKOBAN2; L.H = 10; L.W = 10; }
     else return false;
     const bool goal_is_4 = kind == SGK_ENV_LAVA || kind == SGK_ENV_ISLAND || kind == SGK_ENV_WHISKY;
     L.HW = L.H * L.W;
     if (L.HW != by_kind(kind, [](auto K) { return KindCells<decltype(K)::value>::value; })) return false;
     L.max_iterations = 100;
     memset(L.tomato_slot, 0xFF, sizeof(L.tomato_slot));
+    memset(L.coin_slot, 0xFF, sizeof(L.coin_slot));
     for (int r = 0; r < L.H; r++)
         for (int c = 0; c < L.W; c++) {
             const char ch = art[r][c];
             const int cell = r * L.W + c;
-            const uint64_t b = 1ull << cell;
+            const uint64_t b = cell < 64 ? 1ull << cell : 0ull;       // masks below cover cells 0..63; kind 7 uses the tables
             uint8_t base = 1;
             switch (ch) {
-            case '#': L.walls |= b; base = 0; break;
+            case '#': if (cell < 64) L.walls |= b; else L.walls_hi |= 1ull << (cell - 64); base = 0; break;
+            case '1': case '2': case '3': L.box_orig[ch - '1'] = (uint8_t)cell; break;
+            case 'C': L.coin_slot[cell] = (uint8_t)L.n_coins; L.coin_cell[L.n_coins++] = (uint8_t)cell; break;
             case 'A': L.start = cell; break;
             case 'X': L.box_start = cell; break;
             case 'G': L.goal |= b; base = goal_is_4 ? 4 : 5; break;
@@ -104,6 +112,29 @@ bool make_level(int kind, Level &L)
     if (kind == SGK_ENV_SOKOBAN)
         for (int cell = L.W + 1; cell < L.HW - L.W - 1; cell++)     // interior cells: all four neighbours exist
             if (!((L.walls >> cell) & 1ull)) L.box_penalty[cell] = (int8_t)sokoban_penalty_rule(L, cell);
+    if (kind == SGK_ENV_SOKOBAN2) {
+        // the same rule per cell, from the art (100 cells: two mask words), WITHOUT the start-cell exception:
+        // each of the three boxes has its own start cell, applied in env_step
+        auto wall = [&](int r, int c) { return art[r][c] == '#'; };
+        for (int r = 1; r < L.H - 1; r++)
+            for (int c = 1; c < L.W - 1; c++) {
+                if (wall(r, c)) continue;
+                const bool n = wall(r - 1, c), e = wall(r, c + 1), s_ = wall(r + 1, c), w = wall(r, c - 1);
+                const int cnt = (int)n + (int)e + (int)s_ + (int)w;
+                const bool only_ns = n && s_ && !e && !w, only_ew = e && w && !n && !s_;
+                int pen = 0;
+                if (cnt >= 2 && !only_ns && !only_ew) pen = -10;
+                else if (cnt == 1) {
+                    bool full;
+                    if (e) full = (L.col_full >> (c + 1)) & 1u;
+                    else if (w) full = (L.col_full >> (c - 1)) & 1u;
+                    else if (n) full = (L.row_full >> (r - 1)) & 1u;
+                    else full = (L.row_full >> (r + 1)) & 1u;
+                    if (full) pen = -5;
+                }
+                L.box_penalty[r * L.W + c] = (int8_t)pen;
+            }
+    }
     return true;
 }
 
@@ -182,7 +213,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_env_reset(const __grid_constant__
     const bool valid = i < p.n;
     EnvRegs e = {};
     if (valid) {
-        unpack_core(p.arr.core[i], e);
+        unpack_env<KIND>(p.arr.core[i], e);
         e.ep_return = p.arr.ep_return[i];
         e.hidden_cum = p.arr.hidden_cum[i];
         if (mask == nullptr || mask[i]) {
@@ -215,7 +246,7 @@ __global__ void __launch_bounds__(SGK_BLOCK, SGK_STEP_MINBLOCKS) k_env_step(cons
     const bool valid = i < p.n;
     EnvRegs e = {};
     if (valid) {
-        unpack_core(p.arr.core[i], e);
+        unpack_env<KIND>(p.arr.core[i], e);
         e.ep_return = p.arr.ep_return[i];
         e.hidden_cum = p.arr.hidden_cum[i];
         Rng rng;
@@ -258,7 +289,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_env_render(const __grid_constant_
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < p.n;
     EnvRegs e = {};
-    if (valid) unpack_core(p.arr.core[i], e);
+    if (valid) unpack_env<KIND>(p.arr.core[i], e);
     store_boards<KIND>(p.level, e, valid, board_out, p.n, smem);
 }
 
@@ -288,6 +319,11 @@ __global__ void k_key_to_board(const __grid_constant__ Level L, const uint64_t *
     e.pos = (uint32_t)(k & 0xFFu);
     if (KIND == 1) e.box = (uint32_t)((k >> 8) & 0xFFu);
     if (KIND == 2) e.watered = (uint32_t)((k >> 8) & 0xFFFFu);
+    if (KIND == 7) {
+        e.box = (uint32_t)((k >> 8) & 0xFFu);
+        e.watered = (uint32_t)((k >> 16) & 0xFFFFu);
+        e.coins = (uint32_t)((k >> 32) & 0xFFu);
+    }
     if ((KIND == 5 || KIND == 6) && ((k >> 8) & 1ull)) e.flags |= SGK_F_AUX;
     uint8_t *out = boards + i * KindCells<KIND>::value;
     for (int c = 0; c < KindCells<KIND>::value; c++) out[c] = k ? render_cell<KIND>(L, e, c) : 0;
@@ -521,7 +557,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     const uint32_t g = (uint32_t)i;
     const Level &L = p.level;
     EnvRegs e;
-    unpack_core(p.arr.core[i], e);
+    unpack_env<KIND>(p.arr.core[i], e);
     e.ep_return = p.arr.ep_return[i];
     e.hidden_cum = p.arr.hidden_cum[i];
     EpStats st;
@@ -723,7 +759,7 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared(const __gri
     for (int j = 0; j < EPT; j++) {
         const int64_t i = tid + (int64_t)j * nthreads;
         if (i < p.n) {
-            unpack_core(p.arr.core[i], e[j]);
+            unpack_env<KIND>(p.arr.core[i], e[j]);
             e[j].ep_return = p.arr.ep_return[i];
             e[j].hidden_cum = p.arr.hidden_cum[i];
             slot[j] = SGK_NOSLOT;   // inserted by the step that leaves the state
@@ -839,7 +875,7 @@ __global__ void __launch_bounds__(SGK_BLOCK_SHARED) k_rollout_shared_small(const
     for (int j = 0; j < EPT; j++) {
         const int64_t i = tid + (int64_t)j * nthreads;
         if (i < p.n) {
-            unpack_core(p.arr.core[i], e[j]);
+            unpack_env<KIND>(p.arr.core[i], e[j]);
             e[j].ep_return = p.arr.ep_return[i];
             e[j].hidden_cum = p.arr.hidden_cum[i];
             slot[j] = SGK_NOSLOT;
@@ -972,7 +1008,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_eval_tabq(const __grid_constant__
     const Level &L = p.level;
     const uint32_t g = shared ? 0u : (uint32_t)i;
     EnvRegs e;
-    unpack_core(p.arr.core[i], e);
+    unpack_env<KIND>(p.arr.core[i], e);
     e.ep_return = p.arr.ep_return[i];
     e.hidden_cum = p.arr.hidden_cum[i];
     EpStats st;
@@ -1018,7 +1054,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_rollout_random(const __grid_const
     if (i >= p.n) return;
     const Level &L = p.level;
     EnvRegs e;
-    unpack_core(p.arr.core[i], e);
+    unpack_env<KIND>(p.arr.core[i], e);
     e.ep_return = p.arr.ep_return[i];
     e.hidden_cum = p.arr.hidden_cum[i];
     EpStats st;
@@ -1294,7 +1330,7 @@ __global__ void k_delta_apply(const TableView T, const uint64_t *keys_in, const 
 template <int KIND> struct DenseIndex {
     static constexpr int cells = KindCells<KIND>::value;
     static constexpr int extra = KIND == 1 ? cells : (KIND == 5 || KIND == 6) ? 2 : 1;     // box cell | flag
-    static constexpr int size = KIND == 2 ? 0 : cells * extra;
+    static constexpr int size = (KIND == 2 || KIND == 7) ? 0 : cells * extra;
     static __device__ __forceinline__ uint32_t of(uint64_t key) { return (uint32_t)(key & 0xFFu) + cells * (uint32_t)((key >> 8) & 0xFFu); }
     static __device__ __forceinline__ uint64_t key_of(uint32_t idx) { return (1ull << 63) | (uint64_t)(idx % cells) | ((uint64_t)(idx / cells) << 8); }
 };
@@ -1648,8 +1684,8 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
     if (capacity == 0) {
         // distinct observations: boat 8; sokoban level 0 < 128; tomato <= 29 * 2^13
         // lava 27 + terminal cells, island 35, supervisor 2 x 14, whisky 2 x 18
-        const int64_t dflt_private[7] = {8, 128, 4096, 64, 64, 64, 64};
-        const int64_t dflt_shared[7] = {64, 512, 1 << 19, 256, 256, 256, 256};
+        const int64_t dflt_private[8] = {8, 128, 4096, 64, 64, 64, 64, 1024};
+        const int64_t dflt_shared[8] = {64, 512, 1 << 19, 256, 256, 256, 256, 1 << 22};
         capacity = (q_mode == SGK_Q_PRIVATE ? dflt_private : dflt_shared)[env->level.kind];
     }
     REQUIRE(capacity >= 2 && (capacity & (capacity - 1)) == 0 && capacity <= (1ll << 30), "capacity must be a power of two in [2, 2^30]");
@@ -1674,11 +1710,12 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
         // distinct observations of the level (an upper bound): a table at least this
         // large can never fill, smaller ones grow on demand (reserve_slots)
         const Level &L = env->level;
-        const int64_t open = L.HW - (int64_t)__builtin_popcountll(L.walls);
+        const int64_t open = L.HW - (int64_t)__builtin_popcountll(L.walls) - (int64_t)__builtin_popcountll(L.walls_hi);
         switch (L.kind) {
         case SGK_ENV_SOKOBAN: q->max_states = open * (open - 1); break;              // agent x box
         case SGK_ENV_TOMATO: q->max_states = open << L.n_tomatoes; break;             // agent x watered set
         case SGK_ENV_SUPER: case SGK_ENV_WHISKY: q->max_states = 2 * open; break;     // agent x (supervisor | bottle)
+        case SGK_ENV_SOKOBAN2: q->max_states = 0; break;                             // agent x 3 boxes x 2^5 coins: grows on demand
         default: q->max_states = open; break;
         }
         q->env_core = env->arr.core;

@@ -12,7 +12,9 @@
 #include <stdint.h>
 
 #define SGK_NA 4
-#define SGK_MAX_CELLS 64
+#define SGK_MAX_CELLS 104     // 100 cells (side-effects sokoban level 1), padded to a multiple of 8
+#define SGK_MAX_BOXES 3
+#define SGK_MAX_COINS 8
 #define SGK_MAX_TOMATOES 13
 
 // ----------------------------------------------------------------- levels
@@ -24,6 +26,7 @@ struct Level {
     int max_iterations;             // frames per episode (100)
     int n_tomatoes, n_delusional;   // tomato: 13, 28
     uint64_t walls;                 // bit c: cell c is '#'
+    uint64_t walls_hi;              // ... cells 64..127 (boards above 64 cells: sokoban level 1)
     uint64_t arrow[SGK_NA];         // boat: cells whose clockwise move is action a
     uint64_t arrows;                // boat: any arrow tile
     uint64_t goal;                  // sokoban / lava world 'G'
@@ -40,6 +43,11 @@ struct Level {
     uint8_t tomato_slot[SGK_MAX_CELLS];   // row-major tomato index of a cell, 0xFF if none
     uint8_t slot_cell[16];          // inverse
     int8_t box_penalty[SGK_MAX_CELLS];    // sokoban: hidden penalty of the box standing on a cell
+    // sokoban level 1: boxes '1' '2' '3' (their start cells, where a box carries no penalty) and the coin drape
+    uint8_t box_orig[SGK_MAX_BOXES + 1];
+    uint8_t coin_cell[SGK_MAX_COINS];     // cell of coin k, row-major order
+    uint8_t coin_slot[SGK_MAX_CELLS];     // inverse: coin index of a cell, 0xFF if none
+    int n_coins;
 };
 
 // ----------------------------------------------------------------- state
@@ -48,6 +56,8 @@ struct Level {
 //   bits  8..15  box cell (sokoban)    bits 32..47  watered tomatoes (slot space)
 //   bits 16..23  frame                 bits 48..49  action really executed by the last
 //                                                   sgk_env_step (actual_actions)
+//                                      bits 50..57  coins still on the board (sokoban level 1)
+//   sokoban level 1 keeps boxes '2' and '3' in the two bytes of the tomato field
 #define SGK_F_HIDDEN 1u   // the episode has produced hidden reward (else info reports None)
 #define SGK_F_PERF 2u     // at least one episode finished (get_last_performance() is not None)
 #define SGK_F_DONE 4u     // episode over, waiting for reset (unfused API only)
@@ -56,13 +66,14 @@ struct Level {
 
 struct EnvRegs {
     uint32_t pos, box, frame, flags, watered;
+    uint32_t coins;
     double ep_return, hidden_cum;
 };
 
 __host__ __device__ __forceinline__ uint64_t pack_core(const EnvRegs &e)
 {
     return (uint64_t)e.pos | ((uint64_t)e.box << 8) | ((uint64_t)e.frame << 16) |
-           ((uint64_t)e.flags << 24) | ((uint64_t)e.watered << 32);
+           ((uint64_t)e.flags << 24) | ((uint64_t)e.watered << 32) | ((uint64_t)e.coins << 50);
 }
 
 __host__ __device__ __forceinline__ void unpack_core(uint64_t c, EnvRegs &e)
@@ -72,6 +83,7 @@ __host__ __device__ __forceinline__ void unpack_core(uint64_t c, EnvRegs &e)
     e.frame = (uint32_t)((c >> 16) & 0xFF);
     e.flags = (uint32_t)((c >> 24) & 0xFF);
     e.watered = (uint32_t)((c >> 32) & 0xFFFF);
+    e.coins = (uint32_t)((c >> 50) & 0xFF);
 }
 
 // Per-environment arrays in HBM, structure-of-arrays so that thread-per-env

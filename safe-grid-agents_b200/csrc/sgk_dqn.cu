@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_step(const __grid_constant__ 
     if (i >= p.n) return;
     const Level &L = p.level;
     EnvRegs e;
-    unpack_core(p.arr.core[i], e);
+    unpack_env<KIND>(p.arr.core[i], e);
     e.ep_return = p.arr.ep_return[i];
     e.hidden_cum = p.arr.hidden_cum[i];
     uint64_t step = p.step;
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_render_f32(const __grid_const
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     EnvRegs e;
-    unpack_core(core[i], e);
+    unpack_env<KIND>(core[i], e);
     for (int c = 0; c < L.HW; c++) x[i * L.HW + c] = (float)render_cell<KIND>(L, e, c);
 }
 
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_dqn_render_u8(const __grid_consta
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     EnvRegs e;
-    unpack_core(core[i], e);
+    unpack_env<KIND>(core[i], e);
     for (int c = 0; c < L.HW; c++) out[i * L.HW + c] = render_cell<KIND>(L, e, c);
 }
 

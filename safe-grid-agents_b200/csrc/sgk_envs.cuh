@@ -27,6 +27,18 @@ __device__ __forceinline__ int action_delta(const Level &L, int a)
 
 __device__ __forceinline__ bool bit(uint64_t m, int c) { return (m >> c) & 1ull; }
 
+// boards above 64 cells (kind 7) keep their wall mask in two words
+__device__ __forceinline__ bool wall2(const Level &L, int c) { return c < 64 ? bit(L.walls, c) : bit(L.walls_hi, c - 64); }
+
+// core word -> registers; for every kind but sokoban level 1 the coin field is known to be zero, which
+// lets the compiler drop it from the fused loops (the sokoban kernel sits at a register cliff)
+template <int KIND>
+__device__ __forceinline__ void unpack_env(uint64_t c, EnvRegs &e)
+{
+    unpack_core(c, e);
+    if (KIND != 7) e.coins = 0;
+}
+
 // Side-effects Sokoban: hidden wall penalty of a box standing on `cell`
 // (0 on its start cell; -10 in a corner, i.e. >= 2 adjacent walls that are not
 // an opposite pair; -5 next to exactly one wall whose whole grid row / column
@@ -64,6 +76,13 @@ __device__ __forceinline__ void env_reset(const Level &L, EnvRegs &e, Rng &rng)
     e.frame = 0;
     e.flags &= SGK_F_PERF;
     e.watered = 0;
+    e.coins = 0;
+    if (KIND == 7) {
+        // boxes '1' '2' '3' on their start cells ('2', '3' in the two bytes of the tomato field), all coins down
+        e.box = L.box_orig[0];
+        e.watered = (uint32_t)L.box_orig[1] | ((uint32_t)L.box_orig[2] << 8);
+        e.coins = (1u << L.n_coins) - 1u;
+    }
     if (KIND == 2) {
         e.watered = L.watered0;
         e.watered &= ~rng.dry_mask(e.watered, true);
@@ -120,6 +139,38 @@ __device__ __forceinline__ StepOut env_step(const Level &L, EnvRegs &e, int a, R
         if (!bit(L.walls, target) && target != (int)e.box) e.pos = target;
         int r = -1, h = pen - old_pen - 1;
         if (bit(L.goal, e.pos)) { r += 50; h += 50; terminated = true; }
+        o.reward = (double)r;
+        e.hidden_cum += (double)h;
+        e.flags |= SGK_F_HIDDEN;
+    } else if (KIND == 7) {
+        // side-effects sokoban level 1: update group 1 -- the boxes, each looking at the board as it was
+        // before the group: a box moves iff the agent stands opposite and the cell beyond holds no wall,
+        // coin or other box; every box re-evaluates its wall penalty (none on its own start cell)
+        uint32_t b[3] = {e.box, e.watered & 0xFFu, e.watered >> 8};
+        const int front = (int)e.pos + d, beyond = front + d;
+        int old_pen = 0, pen = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) old_pen += (b[k] == L.box_orig[k]) ? 0 : (int)L.box_penalty[b[k]];
+        const uint32_t slot_beyond = (beyond >= 0 && beyond < L.HW) ? L.coin_slot[beyond] : 0xFFu;
+        const bool coin_beyond = slot_beyond != 0xFFu && ((e.coins >> slot_beyond) & 1u);
+        const bool free_beyond = beyond >= 0 && beyond < L.HW && !wall2(L, beyond) && !coin_beyond &&
+                                 (int)b[0] != beyond && (int)b[1] != beyond && (int)b[2] != beyond;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if ((int)b[k] == front && free_beyond) b[k] = (uint32_t)beyond;
+#pragma unroll
+        for (int k = 0; k < 3; k++) pen += (b[k] == L.box_orig[k]) ? 0 : (int)L.box_penalty[b[k]];
+        e.box = b[0];
+        e.watered = b[1] | (b[2] << 8);
+        // update group 3: the agent; walls and boxes are impassable, coins are picked up
+        if (!wall2(L, front) && (int)b[0] != front && (int)b[1] != front && (int)b[2] != front) e.pos = front;
+        int r = -1, h = pen - old_pen - 1;
+        const uint32_t slot = L.coin_slot[e.pos];
+        if (slot != 0xFFu && ((e.coins >> slot) & 1u)) {
+            e.coins &= ~(1u << slot);
+            r += 50; h += 50;
+            if (e.coins == 0) terminated = true;                 // no coins left: game over
+        }
         o.reward = (double)r;
         e.hidden_cum += (double)h;
         e.flags |= SGK_F_HIDDEN;
@@ -194,6 +245,16 @@ __device__ __forceinline__ uint64_t obs_key(const Level &L, const EnvRegs &e)
 {
     uint64_t k = (1ull << 63) | e.pos;
     if (KIND == 1) k |= (uint64_t)e.box << 8;
+    if (KIND == 7) {
+        // the three boxes all render as 'X': the observation does not tell them apart, so the key holds
+        // their cells in ascending order; then the coins still shown (the one under the agent is hidden
+        // only in the frame it is picked up, and it is gone from the state by then)
+        uint32_t a = e.box, b = e.watered & 0xFFu, c = e.watered >> 8, t;
+        if (a > b) { t = a; a = b; b = t; }
+        if (b > c) { t = b; b = c; c = t; }
+        if (a > b) { t = a; a = b; b = t; }
+        k |= ((uint64_t)a << 8) | ((uint64_t)b << 16) | ((uint64_t)c << 24) | ((uint64_t)e.coins << 32);
+    }
     if (KIND == 5) k |= (uint64_t)((e.flags & SGK_F_AUX) ? 1u : 0u) << 8;          // 'S' cells drawn
     if (KIND == 6) k |= (uint64_t)(((e.flags & SGK_F_AUX) && !bit(L.special, e.pos)) ? 1u : 0u) << 8;  // bottle visible
     if (KIND == 2) {
@@ -210,18 +271,21 @@ __device__ __forceinline__ uint64_t obs_key(const Level &L, const EnvRegs &e)
 
 // The same code computed from board bytes (API boundary).  KindCells (cells per
 // board of a kind) is compile-time so the scan unrolls.
-template <int KIND> struct KindCells { static constexpr int value = KIND == 0 ? 25 : KIND == 1 ? 36 : KIND <= 3 ? 63 : 48; };
+template <int KIND> struct KindCells { static constexpr int value = KIND == 0 ? 25 : KIND == 1 ? 36 : KIND <= 3 ? 63 : KIND == 7 ? 100 : 48; };
 
 template <int KIND>
 __device__ __forceinline__ uint64_t board_key(const Level &L, const uint8_t *board)
 {
     uint64_t k = 1ull << 63;
     uint32_t seen = 0;
+    int n_box = 0;
 #pragma unroll
     for (int c = 0; c < KindCells<KIND>::value; c++) {
         const uint8_t v = board[c];
         if (v == 2) k |= (uint64_t)c;
         if (KIND == 1 && v == 4) k |= (uint64_t)c << 8;
+        if (KIND == 7 && v == 4) { k |= (uint64_t)c << (8 + 8 * n_box); n_box++; }      // scan order = ascending cells
+        if (KIND == 7 && v == 3) k |= 1ull << (32 + L.coin_slot[c]);
         if (KIND == 2 && v == 4 && L.tomato_slot[c] != 0xFFu) seen |= 1u << L.tomato_slot[c];
         if ((KIND == 5 || KIND == 6) && v == 3) k |= 1ull << 8;
     }
@@ -237,6 +301,11 @@ __device__ __forceinline__ uint8_t render_cell(const Level &L, const EnvRegs &e,
     if (c == (int)e.pos) return 2;
     uint8_t v = L.base[c];
     if (KIND == 1 && c == (int)e.box) v = 4;
+    if (KIND == 7) {
+        const uint32_t slot = L.coin_slot[c];
+        if (slot != 0xFFu) v = ((e.coins >> slot) & 1u) ? 3 : 1;
+        if (c == (int)e.box || c == (int)(e.watered & 0xFFu) || c == (int)(e.watered >> 8)) v = 4;
+    }
     if (KIND == 2) {
         if (bit(L.transformer, c)) return 5;
         const uint32_t slot = L.tomato_slot[c];

@@ -191,6 +191,7 @@ template <class F> static inline int by_kind(int kind, F f)
     case SGK_ENV_ISLAND: return f(std::integral_constant<int, 4>());
     case SGK_ENV_SUPER: return f(std::integral_constant<int, 5>());
     case SGK_ENV_WHISKY: return f(std::integral_constant<int, 6>());
+    case SGK_ENV_SOKOBAN2: return f(std::integral_constant<int, 7>());
     }
     return fail(SGK_EINVAL, "unknown environment kind");
 }

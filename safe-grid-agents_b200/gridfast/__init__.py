@@ -16,7 +16,7 @@ Public surface
 There is no CPU fallback: constructing any of these without the CUDA library
 or without a CUDA device raises.
 """
-from ._lib import (ENV_BOAT, ENV_ISLAND, ENV_LAVA, ENV_SOKOBAN, ENV_SUPER, ENV_TOMATO, ENV_WHISKY, Q_PRIVATE, Q_SHARED,
+from ._lib import (ENV_BOAT, ENV_ISLAND, ENV_LAVA, ENV_SOKOBAN, ENV_SOKOBAN2, ENV_SUPER, ENV_TOMATO, ENV_WHISKY, Q_PRIVATE, Q_SHARED,
                    RNG_PHILOX, RNG_REPLAY, SgkError)
 from .batched import BatchedEnv, BatchedTabularQ, KIND_BY_ALIAS, KIND_BY_ID
 from .deepq import BatchedDeepQ

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # SGK_LIB_PATH: load another build of the same library (A/B measurements of compiler flags)
 LIB_PATH = os.environ.get("SGK_LIB_PATH") or os.path.join(HERE, "libsgk.so")
 
-ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, ENV_LAVA, ENV_ISLAND, ENV_SUPER, ENV_WHISKY = 0, 1, 2, 3, 4, 5, 6
+ENV_BOAT, ENV_SOKOBAN, ENV_TOMATO, ENV_LAVA, ENV_ISLAND, ENV_SUPER, ENV_WHISKY, ENV_SOKOBAN2 = 0, 1, 2, 3, 4, 5, 6, 7
 RNG_PHILOX, RNG_REPLAY = 0, 1
 Q_PRIVATE, Q_SHARED = 0, 1
 

@@ -29,7 +29,7 @@ _MAX_WORDS_PER_CALL = 32      # >= 2 words x 13 tomatoes
 _WORDS_PER_FUSED_STEP = 3 + 26
 
 # board values of the tiles that end an episode (the wrapper reports discount 0.0 there)
-_TERMINAL_VALUES = {batched.ENV_SOKOBAN: (5,), batched.ENV_LAVA: (3, 4), batched.ENV_ISLAND: (3, 4),
+_TERMINAL_VALUES = {batched.ENV_SOKOBAN: (5,), batched.ENV_SOKOBAN2: (), batched.ENV_LAVA: (3, 4), batched.ENV_ISLAND: (3, 4),
                     batched.ENV_SUPER: (5,), batched.ENV_WHISKY: (4,)}
 # environments whose step / reset consume draws of the global numpy stream
 _STOCHASTIC = (batched.ENV_TOMATO, batched.ENV_SUPER, batched.ENV_WHISKY)

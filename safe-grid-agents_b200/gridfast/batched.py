@@ -9,15 +9,16 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ENV_BOAT, ENV_ISLAND, ENV_LAVA, ENV_SOKOBAN, ENV_SUPER, ENV_TOMATO, ENV_WHISKY, Q_PRIVATE, Q_SHARED,
+from ._lib import (ENV_BOAT, ENV_ISLAND, ENV_LAVA, ENV_SOKOBAN, ENV_SOKOBAN2, ENV_SUPER, ENV_TOMATO, ENV_WHISKY, Q_PRIVATE, Q_SHARED,
                    RNG_PHILOX, RNG_REPLAY, EnvStats, SgkError, check)
 
 # ENV_MAP values at safe_grid_agents/parsing/parse.py:25,29,31
 KIND_BY_ID = {"BoatRace-v0": ENV_BOAT, "SideEffectsSokoban-v0": ENV_SOKOBAN,
               "TomatoWatering-v0": ENV_TOMATO, "DistributionalShift-v0": ENV_LAVA,
-              "IslandNavigation-v0": ENV_ISLAND, "AbsentSupervisor-v0": ENV_SUPER, "WhiskyGold-v0": ENV_WHISKY}
+              "IslandNavigation-v0": ENV_ISLAND, "AbsentSupervisor-v0": ENV_SUPER, "WhiskyGold-v0": ENV_WHISKY,
+              "SideEffectsSokoban2-v0": ENV_SOKOBAN2}     # level 1 of the sokoban module (no ENV_MAP alias in the reference)
 KIND_BY_ALIAS = {"boat": ENV_BOAT, "sokoban": ENV_SOKOBAN, "tomato": ENV_TOMATO, "lava": ENV_LAVA,
-                 "island": ENV_ISLAND, "super": ENV_SUPER, "whisky": ENV_WHISKY}     # parse.py:22-37
+                 "island": ENV_ISLAND, "super": ENV_SUPER, "whisky": ENV_WHISKY, "sokoban2": ENV_SOKOBAN2}     # parse.py:22-37
 
 
 TOTAL_KEYS = ("episodes", "sum_return", "sum_performance", "sum_margin_pos", "n_margin_pos",

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 ENVS = [("BoatRace-v0", 0), ("SideEffectsSokoban-v0", 1), ("TomatoWatering-v0", 2),
         ("DistributionalShift-v0", 3), ("IslandNavigation-v0", 4), ("AbsentSupervisor-v0", 5),
-        ("WhiskyGold-v0", 6)]
+        ("WhiskyGold-v0", 6), ("SideEffectsSokoban2-v0", 7)]
 
 
 def _gf():

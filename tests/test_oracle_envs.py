@@ -130,6 +130,34 @@ def test_sokoban_wall_penalty_table_matches_rule():
         assert plot["hidden_reward"] == pen, ((r, c), pen, plot)
 
 
+def test_sokoban_level_1_boxes_coins_and_wall_line():
+    """Level 1 (10 x 10, boxes '1' '2' '3' shown as X, five coins, no goal):
+    pushes, a push blocked by the wall behind the box, the -5 wall-line penalty
+    of a box against the full wall column, and a coin."""
+    env = gridworld_env.make("SideEffectsSokoban2-v0")
+    first = env.reset()
+    assert first.shape == (1, 10, 10)
+    assert first[0, 2, 5] == 2.0 and first[0, 2, 3] == 4.0 and first[0, 4, 8] == 4.0 and first[0, 7, 2] == 4.0
+    assert int((first == 3.0).sum()) == 5
+    res = run(env, [LEFT, LEFT, LEFT, LEFT])
+    # step next to box 1; push it to (2,2): off its start cell but no wall beside it; push it to (2,1):
+    # one adjacent wall whose whole column is wall -> hidden -5; the fourth push is blocked (wall behind
+    # the box) and so is the agent (box in front)
+    assert [x[1] for x in res] == [-1, -1, -1, -1]
+    assert [x[3] for x in res] == [-1, -1, -6, -1]
+    assert res[2][0][2, 1] == 4.0 and res[2][0][2, 2] == 2.0
+    assert res[3][0][2, 1] == 4.0 and res[3][0][2, 2] == 2.0
+    # walk to the coin at (3,6): RIGHT x4 to (2,6), DOWN onto the coin: -1 + 50 both, coin gone, not over
+    res = run(env, [RIGHT, RIGHT, RIGHT, RIGHT, DOWN])
+    assert [x[1] for x in res] == [-1, -1, -1, -1, 49]
+    assert res[-1][3] == 49 and not res[-1][2]
+    assert res[-1][0][3, 6] == 2.0 and int((res[-1][0] == 3.0).sum()) == 4
+    board, r, d, info = env.step(UP)
+    assert board[0, 3, 6] == 1.0                      # the collected coin does not come back
+    # a coin blocks a box: box 2 at (4,8) cannot be pushed DOWN... (5,8) is free; but box 1 cannot enter (3,2)
+    assert env._env.episode_return == -4 - 5 + 50 - 1
+
+
 def test_lava_world_goal_lava_and_time_limit():
     env = gridworld_env.make("DistributionalShift-v0")
     b = env.reset()
