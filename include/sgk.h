@@ -88,9 +88,10 @@ int64_t sgk_env_count(const sgk_env *env);
  * 1 word per discrete draw, tomato draws inside step/reset).  Rewinds every
  * environment's cursor to 0; does not reset the environments (the reference
  * seeds numpy before env.reset(), train.py:32,64 -- call sgk_env_reset next
- * to take the first reset frame's draws from the replayed stream).
+ * to take the first reset frame's draws from the replayed stream).  The rewind
+ * is enqueued on `stream`, the stream the next launches use.
  * words == NULL switches back to Philox. */
-int sgk_env_set_replay(sgk_env *env, const uint32_t *words, int64_t words_per_env);
+int sgk_env_set_replay(sgk_env *env, const uint32_t *words, int64_t words_per_env, void *stream);
 /* Words consumed so far per environment (device [n_envs] int64). */
 int sgk_env_replay_cursor(const sgk_env *env, int64_t *cursor_out, void *stream);
 

@@ -1413,7 +1413,8 @@ extern "C" int sgk_env_destroy(sgk_env *env)
     DeviceGuard g(env->device);
     EnvArrays &A = env->arr;
     void *ptrs[] = {A.core, A.ep_return, A.hidden_cum, A.last_return, A.last_perf, A.sum_return, A.sum_perf,
-                    A.sum_margin_pos, A.max_return, A.max_perf, A.max_margin, A.counts, A.trace_hash, A.replay_cursor, env->status, env->totals, env->partials};
+                    A.sum_margin_pos, A.max_return, A.max_perf, A.max_margin, A.counts, A.trace_hash, A.replay_cursor, env->status, env->totals, env->partials,
+                    env->stage_boards};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete env;
     return SGK_OK;
@@ -1473,14 +1474,14 @@ extern "C" int sgk_env_shape(const sgk_env *env, int *channels, int *height, int
 
 extern "C" int64_t sgk_env_count(const sgk_env *env) { return env ? env->n : 0; }
 
-extern "C" int sgk_env_set_replay(sgk_env *env, const uint32_t *words, int64_t words_per_env)
+extern "C" int sgk_env_set_replay(sgk_env *env, const uint32_t *words, int64_t words_per_env, void *stream)
 {
     REQUIRE(env != nullptr, "env is NULL");
     DeviceGuard g(env->device);
     if (words == nullptr) { env->rng_mode = SGK_RNG_PHILOX; env->replay_words = nullptr; env->words_per_env = 0; return SGK_OK; }
     REQUIRE(words_per_env > 0, "words_per_env must be positive");
     env->rng_mode = SGK_RNG_REPLAY; env->replay_words = words; env->words_per_env = words_per_env;
-    CU(cudaMemsetAsync(env->arr.replay_cursor, 0, (size_t)env->n * sizeof(long long), 0));
+    CU(cudaMemsetAsync(env->arr.replay_cursor, 0, (size_t)env->n * sizeof(long long), (cudaStream_t)stream));
     return SGK_OK;
 }
 
@@ -2440,22 +2441,20 @@ extern "C" int sgk_rollout_tabq_host(sgk_env *env, sgk_tabq *q, int64_t n_steps,
     REQUIRE(env != nullptr && q != nullptr, "env or q is NULL");
     DeviceGuard g(env->device);
     cudaStream_t st = (cudaStream_t)stream;
-    static thread_local uint8_t *d_boards = nullptr;
-    static thread_local size_t d_boards_cap = 0;
     if (core_in) CU(cudaMemcpyAsync(env->arr.core, core_in, (size_t)env->n * 8, cudaMemcpyHostToDevice, st));
     int rc = sgk_rollout_tabq(env, q, n_steps, t0, cheat, stream);
     if (rc != SGK_OK) return rc;
     if (boards_out) {
         const size_t bytes = (size_t)env->n * env->level.HW;
-        if (d_boards_cap < bytes) {
-            if (d_boards) cudaFree(d_boards);
-            d_boards = nullptr; d_boards_cap = 0;
-            CU(cudaMalloc(&d_boards, bytes));
-            d_boards_cap = bytes;
+        if (env->stage_cap < bytes) {
+            if (env->stage_boards) cudaFree(env->stage_boards);
+            env->stage_boards = nullptr; env->stage_cap = 0;
+            CU(cudaMalloc(&env->stage_boards, bytes));
+            env->stage_cap = bytes;
         }
-        rc = sgk_env_render(env, d_boards, stream);
+        rc = sgk_env_render(env, env->stage_boards, stream);
         if (rc != SGK_OK) return rc;
-        CU(cudaMemcpyAsync(boards_out, d_boards, bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(boards_out, env->stage_boards, bytes, cudaMemcpyDeviceToHost, st));
     }
     if (core_out) CU(cudaMemcpyAsync(core_out, env->arr.core, (size_t)env->n * 8, cudaMemcpyDeviceToHost, st));
     if (totals_out) {

@@ -48,6 +48,9 @@ struct sgk_env {
     int *status;        // device
     double *totals;     // device [SGK_N_TOTALS]
     double *partials;   // device [TOT_BLOCKS][SGK_N_TOTALS]
+    uint8_t *stage_boards;      // device staging of sgk_rollout_tabq_host's board read-back (owned, freed with the object)
+    size_t stage_cap;
+    int replay_rewind;          // sgk_env_set_replay was called: the next launch's stream zeroes the cursors first
 };
 
 

@@ -36,7 +36,7 @@ SYMBOLS = [
     ("sgk_env_destroy", _i32, [_vp]),
     ("sgk_env_shape", _i32, [_vp, _pi, _pi, _pi, _pi]),
     ("sgk_env_count", _i64, [_vp]),
-    ("sgk_env_set_replay", _i32, [_vp, _vp, _i64]),
+    ("sgk_env_set_replay", _i32, [_vp, _vp, _i64, _vp]),
     ("sgk_env_replay_cursor", _i32, [_vp, _vp, _vp]),
     ("sgk_env_reset", _i32, [_vp, _vp, _u64, _vp, _vp]),
     ("sgk_env_step", _i32, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),

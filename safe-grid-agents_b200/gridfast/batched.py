@@ -99,7 +99,7 @@ class BatchedEnv:
         w = torch.as_tensor(np.ascontiguousarray(words, dtype=np.uint32).view(np.int32)).to(self.device)
         w = w.reshape(self.n, -1).contiguous()
         self._replay = w
-        check(self.L.sgk_env_set_replay(self.h, _p(w), w.shape[1]))
+        check(self.L.sgk_env_set_replay(self.h, _p(w), w.shape[1], _stream()))
 
     def set_trace(self, enabled=True):
         check(self.L.sgk_env_set_trace(self.h, int(enabled)))

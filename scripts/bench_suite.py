@@ -131,7 +131,7 @@ def dqn(n, batch, T, use_tc, reps=3, label=None):
     sec = timed(lambda: agent.rollout(T), reps, warm=1)
     flop = T * (n * 28000.0 + batch * 4 * 28000.0)
     emit(measurement=label or "dqn_rollout", env="SideEffectsSokoban-v0", n_envs=n, learn_batch=batch, locksteps=T,
-         forward="tcgen05 tf32" if use_tc else "fp32 ffma", seconds_per_call=sec, env_steps_per_s=n * T / sec,
+         forward=agent.precision, seconds_per_call=sec, env_steps_per_s=n * T / sec,
          us_per_lockstep=1e6 * sec / T, samples_learned_per_s=batch * T / sec, model_TFLOPs=flop / sec / 1e12,
          loss_norm_clip=agent.last_scalars())
     del agent, env
@@ -145,11 +145,39 @@ def mlp_forward(rows, use_tc, reps=10):
     agent.set_tensor_cores(use_tc)
     boards = torch.randint(0, 6, (rows, env.hw), dtype=torch.uint8, device="cuda")
     sec = timed(lambda: agent.q_values(boards), reps)
-    emit(measurement="mlp_forward", rows=rows, forward="tcgen05 tf32" if use_tc else "fp32 ffma", seconds_per_call=sec,
+    emit(measurement="mlp_forward", rows=rows, forward=agent.precision, seconds_per_call=sec,
          rows_per_s=rows / sec, TFLOPs=rows * 28000.0 / sec / 1e12,
          frac_of_measured_bf16_tensor_peak=rows * 28000.0 / sec / 1e12 / 1648.6 if use_tc else None)
     del agent, env
     torch.cuda.empty_cache()
+
+
+def torch_context(rows=1 << 20, batch=262144, reps=10):
+    """Context for the deep-Q kernels: the same 36-100-100-4 network in plain
+    torch -- cuBLAS GEMMs with TF32 allowed, separate bias / ReLU kernels, autograd backward -- on the
+    same shapes.  Not part of the product path."""
+    import torch.nn as nn
+    for allow in (True, False):
+        torch.backends.cuda.matmul.allow_tf32 = allow
+        torch.backends.cudnn.allow_tf32 = allow
+        net = nn.Sequential(nn.Linear(36, 100), nn.ReLU(), nn.Linear(100, 100), nn.ReLU(), nn.Linear(100, 4)).cuda()
+        x = torch.randint(0, 6, (rows, 36), device="cuda").float()
+        with torch.no_grad():
+            sec = timed(lambda: net(x), reps)
+        emit(measurement="torch_mlp_forward", rows=rows, math="cuBLAS TF32" if allow else "cuBLAS fp32", seconds_per_call=sec,
+             rows_per_s=rows / sec, TFLOPs=rows * 28000.0 / sec / 1e12)
+        xb = torch.randint(0, 6, (batch, 36), device="cuda").float()
+        a = torch.randint(0, 4, (batch, 1), device="cuda")
+        y = torch.randn(batch, device="cuda")
+
+        def step():
+            net.zero_grad(set_to_none=True)
+            q = net(xb).gather(1, a).reshape(-1)
+            torch.nn.functional.mse_loss(q, y).backward()
+        sec = timed(step, reps)
+        emit(measurement="torch_mlp_forward_backward", batch=batch, math="cuBLAS TF32" if allow else "cuBLAS fp32",
+             seconds_per_call=sec, samples_per_s=batch / sec, TFLOPs=batch * 3 * 28000.0 / sec / 1e12)
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def main():
@@ -174,6 +202,8 @@ def main():
     if "large" in which:
         fused("BoatRace-v0", 1 << 24, 200, P, reps=3, label="large-N boat private 2^24 x 200")
         fused("SideEffectsSokoban-v0", 1 << 22, 200, P, reps=3, label="large-N sokoban private 2^22 x 200")
+    if "torch" in which:
+        torch_context()
     if "dqn" in which:
         for use_tc in (False, True):
             mlp_forward(1 << 20, use_tc)

@@ -5,9 +5,11 @@ import subprocess
 import sys
 
 rep, out, title = sys.argv[1], sys.argv[2], sys.argv[3]
+which = int(sys.argv[4]) if len(sys.argv) > 4 else 0        # index of the launch inside the report
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units, vals = rows[0], rows[1], rows[2 + which]
+title += "\nkernel: " + vals[hdr.index("Kernel Name")]
 keep = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct",
         "dram__throughput.avg.pct", "lts__t_bytes.sum", "lts__t_sector_hit_rate", "l1tex__t_sector_hit_rate", "l1tex__t_bytes.sum",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
