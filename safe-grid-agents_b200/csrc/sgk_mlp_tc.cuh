@@ -1,4 +1,5 @@
-// sgk_mlp_tc.cuh -- fused MLP forward on the 5th-generation tensor cores.
+// sgk_mlp_tc.cuh -- the deep-Q network on the 5th-generation tensor cores: fused forward
+// (k_mlp_forward_ts, at the end of this file), fused backward (k_mlp_backward_fused).
 //
 // The deep-Q network of the reference (value.py:148-158, n_layers = 2):
 //     Q(s) = W3 relu(W2 relu(W1 s + b1) + b2) + b3,   36 -> 100 -> 100 -> 4
@@ -58,6 +59,14 @@ __device__ __forceinline__ float to_tf32(float x)
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+}
+
+// The same rounding (nearest, ties away from zero) in two integer instructions, for finite inputs:
+// cvt.rna.tf32 expands to ~5 SASS instructions with its NaN handling, and the 3xTF32 epilogue needs two
+// conversions per accumulator element.
+__device__ __forceinline__ float to_tf32_fast(float x)
+{
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
@@ -210,161 +219,6 @@ __device__ __forceinline__ void store4(float *row, int col, int n, bool vec, flo
     if (col + 1 < n) row[col + 1] = v.y;
     if (col + 2 < n) row[col + 2] = v.z;
     if (col + 3 < n) row[col + 3] = v.w;
-}
-
-// epilogue of a hidden layer: this thread's accumulator row -> bias, ReLU ->
-// next layer's A operand in shared memory (+ optional fp32 copy in HBM)
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float *bias, uint8_t *h_smem, int row_in_tile,
-                                                float *h_out_row, int n_hidden)
-{
-#pragma unroll 1
-    for (int c8 = 0; c8 < K_HID / 8; c8++) {
-        float v[8];
-        tmem_ld8(tmem_row + c8 * 8, v);
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = fmaxf(v[i] + bias[c8 * 8 + i], 0.f);
-        if (h_out_row) {
-            const bool vec = (n_hidden & 3) == 0;
-            store4(h_out_row, c8 * 8, n_hidden, vec, make_float4(v[0], v[1], v[2], v[3]));
-            store4(h_out_row, c8 * 8 + 4, n_hidden, vec, make_float4(v[4], v[5], v[6], v[7]));
-        }
-        float4 lo = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
-        float4 hi = make_float4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
-        *reinterpret_cast<float4 *>(h_smem + (size_t)(2 * c8) * Smem::CHUNK_A + row_in_tile * 16) = lo;
-        *reinterpret_cast<float4 *>(h_smem + (size_t)(2 * c8 + 1) * Smem::CHUNK_A + row_in_tile * 16) = hi;
-    }
-}
-
-__global__ void __launch_bounds__(TILE_M, 1) k_mlp_forward_tc(const Params p)
-{
-    extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint32_t tmem_base_slot;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + Smem::BAR);
-    float *bias = reinterpret_cast<float *>(smem + Smem::BIAS);
-    const int warp = threadIdx.x >> 5;
-    const int k_in = (p.n_in + 7) & ~7;             // 36 -> 40, 25 -> 32, 63 -> 64
-
-    // ---- one-time setup: weights, biases, barrier, TMEM
-    uint64_t *mbar_w = mbar + 1;                    // completion of the weight image's bulk copy
-    if (p.w_image) {
-        // the three matrices arrive as ONE TMA bulk copy of their pre-packed image
-        if (threadIdx.x == 0) {
-            mbar_init(mbar_w, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            bulk_load(smem + Smem::W1, p.w_image, FWD_IMAGE_BYTES, mbar_w);
-        }
-    } else {
-        stage_weights(smem + Smem::W1, p.w1, p.n_hidden, p.n_in, N_HID, k_in);
-        stage_weights(smem + Smem::W2, p.w2, p.n_hidden, p.n_hidden, N_HID, K_HID);
-        stage_weights(smem + Smem::W3, p.w3, p.n_out, p.n_hidden, N_OUT, K_HID);
-    }
-    for (int i = threadIdx.x; i < 2 * N_HID + N_OUT; i += blockDim.x) {
-        float b = 0.f;
-        if (i < N_HID) b = i < p.n_hidden ? p.b1[i] : 0.f;
-        else if (i < 2 * N_HID) b = i - N_HID < p.n_hidden ? p.b2[i - N_HID] : 0.f;
-        else b = i - 2 * N_HID < p.n_out ? p.b3[i - 2 * N_HID] : 0.f;
-        bias[i] = b;
-    }
-    if (threadIdx.x == 0) {
-        mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (p.w_image) mbar_wait(mbar_w, 0);
-    const uint32_t tmem = tmem_base_slot;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 lanes
-    const uint32_t d1 = tmem, d2 = tmem + 128, d3 = tmem;
-    const uint32_t a_x = smem_u32(smem + Smem::X), a_h = smem_u32(smem + Smem::H);
-    const uint32_t b_w1 = smem_u32(smem + Smem::W1), b_w2 = smem_u32(smem + Smem::W2), b_w3 = smem_u32(smem + Smem::W3);
-    constexpr uint32_t IDESC_HID = make_idesc(TILE_M, N_HID), IDESC_OUT = make_idesc(TILE_M, N_OUT);
-    uint32_t phase = 0;
-
-    const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row = tile * TILE_M + threadIdx.x;
-        const bool valid = row < p.rows;
-        // ---- stage this thread's board as A operand of layer 1
-        for (int c = 0; c < k_in / 4; c++) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                const uint8_t *b = p.boards + row * p.n_in + 4 * c;
-                const int k = 4 * c;
-                v.x = k + 0 < p.n_in ? (float)b[0] : 0.f;
-                v.y = k + 1 < p.n_in ? (float)b[1] : 0.f;
-                v.z = k + 2 < p.n_in ? (float)b[2] : 0.f;
-                v.w = k + 3 < p.n_in ? (float)b[3] : 0.f;
-            }
-            *reinterpret_cast<float4 *>(smem + Smem::X + (size_t)c * Smem::CHUNK_A + threadIdx.x * 16) = v;
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        // ---- layer 1: D1[128 x 112] = X[128 x k_in] * W1^T
-        if (threadIdx.x == 0) {
-            for (int k = 0; k < k_in / 8; k++)
-                mma_tf32(d1, make_desc(a_x + k * 2 * Smem::CHUNK_A, Smem::CHUNK_A, 128),
-                         make_desc(b_w1 + k * 2 * Smem::CHUNK_H, Smem::CHUNK_H, 128), IDESC_HID, k > 0);
-            mma_commit(mbar);
-        }
-        mbar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        hidden_epilogue(tmem_row + 0, bias, smem + Smem::H, threadIdx.x,
-                        (valid && p.h1_out) ? p.h1_out + row * p.n_hidden : nullptr, p.n_hidden);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        // ---- layer 2: D2[128 x 112] = H1[128 x 104] * W2^T
-        if (threadIdx.x == 0) {
-            for (int k = 0; k < K_HID / 8; k++)
-                mma_tf32(d2, make_desc(a_h + k * 2 * Smem::CHUNK_A, Smem::CHUNK_A, 128),
-                         make_desc(b_w2 + k * 2 * Smem::CHUNK_H, Smem::CHUNK_H, 128), IDESC_HID, k > 0);
-            mma_commit(mbar);
-        }
-        mbar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        hidden_epilogue(tmem_row + 128, bias + N_HID, smem + Smem::H, threadIdx.x,
-                        (valid && p.h2_out) ? p.h2_out + row * p.n_hidden : nullptr, p.n_hidden);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        // ---- layer 3: D3[128 x 16] = H2[128 x 104] * W3^T
-        if (threadIdx.x == 0) {
-            for (int k = 0; k < K_HID / 8; k++)
-                mma_tf32(d3, make_desc(a_h + k * 2 * Smem::CHUNK_A, Smem::CHUNK_A, 128),
-                         make_desc(b_w3 + k * 2 * Smem::CHUNK_O, Smem::CHUNK_O, 128), IDESC_OUT, k > 0);
-            mma_commit(mbar);
-        }
-        mbar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        {
-            float v[8];
-            tmem_ld8(tmem_row + 0, v);
-            if (valid) {
-                const float *b3 = bias + 2 * N_HID;
-                if (p.n_out == 4) {
-                    *reinterpret_cast<float4 *>(p.q_out + row * 4) = make_float4(v[0] + b3[0], v[1] + b3[1], v[2] + b3[2], v[3] + b3[3]);
-                } else {
-                    for (int i = 0; i < p.n_out && i < 8; i++) p.q_out[row * p.n_out + i] = v[i] + b3[i];
-                }
-            }
-        }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-    }
-    if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
 // ===================================================================== backward
@@ -905,9 +759,9 @@ __device__ __forceinline__ void fb_mask_epilogue(uint32_t lane_base, uint32_t d_
         *reinterpret_cast<uint4 *>(dst_f16 + (size_t)g * CHUNK_F16 + r * 16) = w;
         if (dst_tf32) {
             *reinterpret_cast<float4 *>(dst_tf32 + (size_t)(2 * g) * Smem::CHUNK_A + r * 16) =
-                make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+                make_float4(to_tf32_fast(v[0]), to_tf32_fast(v[1]), to_tf32_fast(v[2]), to_tf32_fast(v[3]));
             *reinterpret_cast<float4 *>(dst_tf32 + (size_t)(2 * g + 1) * Smem::CHUNK_A + r * 16) =
-                make_float4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
+                make_float4(to_tf32_fast(v[4]), to_tf32_fast(v[5]), to_tf32_fast(v[6]), to_tf32_fast(v[7]));
         }
     }
 }
@@ -1300,8 +1154,14 @@ __device__ __forceinline__ void ts_hidden_epilogue(uint32_t lane_base, uint32_t 
     const bool vec = (n_hidden & 3) == 0;
     float v[32];
     tmem_ld32(lane_base + d_col + c0, v, wide);
+    // bias as four-wide shared-memory loads (the last quarter reads 16 floats past its 16 columns: still
+    // inside the bias block, and those lanes of v are never stored)
 #pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i] + bias[(c0 + i) < N_HID ? (c0 + i) : 0], 0.f);
+    for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(bias + c0 + i);
+        v[i] = fmaxf(v[i] + b4.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b4.y, 0.f);
+        v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
+    }
     if (h_out_row) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
@@ -1328,8 +1188,8 @@ __device__ __forceinline__ void ts_hidden_epilogue(uint32_t lane_base, uint32_t 
         float hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            hi[i] = to_tf32(v[8 * g + i]);
-            lo[i] = X3 ? to_tf32(v[8 * g + i] - hi[i]) : 0.f;
+            hi[i] = to_tf32_fast(v[8 * g + i]);
+            lo[i] = X3 ? to_tf32_fast(v[8 * g + i] - hi[i]) : 0.f;
         }
         tmem_st8(lane_base + TS_H_HI + c0 + 8 * g, hi);
         if (X3) tmem_st8(lane_base + TS_H_LO + c0 + 8 * g, lo);
