@@ -714,7 +714,7 @@ struct SmemFb {
 };
 static_assert(SmemFb::DQ == (int)BWD_IMAGE_BYTES, "the backward weight image is W3^T | W2^T");
 static_assert(SmemFb::TOTAL <= 227 * 1024, "fused backward: shared memory plan exceeds one SM");
-constexpr int FB_THREADS = 512;      // 16 warps: 4 per TMEM lane quadrant, each masking a quarter of the columns
+constexpr int FB_THREADS = 384;      // 12 warps: 3 per TMEM lane quadrant, each masking a third of the columns (16 warps spilled)
 constexpr uint32_t FB_D0 = 0, FB_D1 = 128, FB_ACC2 = 256, FB_ACC1 = 384, FB_ACC3 = 448;     // TMEM columns (512 allocated)
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes)
@@ -731,16 +731,16 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h16)
 
 // error-signal epilogue of one thread: 8-column groups [g0, g1) of its accumulator row, masked by the
 // FP16 activation image -> FP16 operand (x scale_up) and, for dH2, the TF32 chain operand
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32], bool second);
+__device__ __forceinline__ void tmem_ld8x5(uint32_t taddr, uint32_t stride, float (&v)[40], int n_loads);
 
 __device__ __forceinline__ void fb_mask_epilogue(uint32_t lane_base, uint32_t d_col, const uint8_t *act_img, uint8_t *dst_f16,
                                                  uint8_t *dst_tf32, int r, int g0, int g1, float scale_up)
 {
-    // at most four 8-column groups per warp: all 32 columns in one TMEM round trip
-    float all[32];
-    tmem_ld32(lane_base + d_col + 8 * g0, all, true);
+    // at most five 8-column groups per warp: all of them in one TMEM round trip
+    float all[40];
+    tmem_ld8x5(lane_base + d_col + 8 * g0, 8, all, g1 - g0);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 5; j++) {
         const int g = g0 + j;
         if (g >= g1) break;                                    // warp-uniform
         float v[8];
@@ -773,10 +773,10 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __gr
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + SmemFb::BAR);        // MMA groups
     uint64_t *mbar_w = mbar + 1, *mbar_h2 = mbar + 2, *mbar_h1 = mbar + 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int quad = warp & 3, half = warp >> 2;                              // TMEM lane quadrant; column quarter (0..3)
+    const int quad = warp & 3, half = warp >> 2;                              // TMEM lane quadrant; column third (0..2)
     const int r = quad * 32 + lane;                                           // this thread's row of the tile
-    // the 13 column groups of 8, split 4 / 3 / 3 / 3 over the four warps of a quadrant
-    const int g_lo = half == 0 ? 0 : 1 + 3 * half, g_hi = half == 0 ? 4 : 4 + 3 * half;
+    // the 13 column groups of 8, split 5 / 4 / 4 over the three warps of a quadrant
+    const int g_lo = half == 0 ? 0 : 1 + 4 * half, g_hi = half == 0 ? 5 : 5 + 4 * half;
     const int64_t n_tiles = (p.rows + TILE_M - 1) / TILE_M;
     // activation buffers start out zero: padding chunks / rows are never written again
     for (int e = threadIdx.x; e < (SmemFb::BAR - SmemFb::DQ) / 16; e += blockDim.x)
@@ -847,7 +847,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_mlp_backward_fused(const __gr
             uint4 w = make_uint4(pack_half2(dqv.x * p.scale_up, dqv.y * p.scale_up), pack_half2(dqv.z * p.scale_up, dqv.w * p.scale_up), 0u, 0u);
             *reinterpret_cast<uint4 *>(smem + SmemFb::DQH + r * 16) = w;
         } else if (half == 1) {
-            for (int c = 0; c < x_chunks; c++) {          // 8 cells per FP16 chunk = two packed words
+#pragma unroll
+            for (int c = 0; c < 8; c++) {                 // 8 cells per FP16 chunk = two packed words
+                if (c >= x_chunks) continue;
                 float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) f[i] = (float)((cells[2 * c + (i >> 2)] >> (8 * (i & 3))) & 0xFFu);
@@ -1068,7 +1070,12 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float *w1, const flo
 //     the four warps of a lane quadrant split the columns 32 / 32 / 32 / 16;
 //     each issues all its tcgen05.ld before one wait, so the epilogue is one
 //     TMEM round trip deep; the next tile's boards are fetched while the
-//     current tile computes.
+//     current tile computes.  (Tried and rejected: a 17th warp issuing the
+//     next layer's K steps as the epilogue delivers its 8-column groups, one
+//     mbarrier per group.  The per-group tcgen05.wait::st + arrive and the
+//     fewer epilogue warps that fit the register file made the epilogue, the
+//     long pole at 3.8 of 5.7 us per tile, slower than the hidden MMA time
+//     gained: 2.8e9 boards/s against 3.3e9.)
 struct SmemTs {
     static constexpr int HI = 0;                                   // W1|W2|W3 (layout of Smem), TF32-rounded
     static constexpr int LO = FWD_IMAGE_BYTES;                     // ... remainders
@@ -1112,6 +1119,33 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8])
                     "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
                     "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                  : "memory");
+}
+
+// up to five 8-column loads (`stride` columns apart) in flight, then one wait (a second, already
+// satisfied one carries the last eight registers: an asm statement takes at most 32 of them)
+__device__ __forceinline__ void tmem_ld8x5(uint32_t taddr, uint32_t stride, float (&v)[40], int n_loads)
+{
+    uint32_t r[40];
+#pragma unroll
+    for (int i = 0; i < 40; i++) r[i] = 0u;
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+        if (j < n_loads)          // warp-uniform
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[8 * j + 0]), "=r"(r[8 * j + 1]), "=r"(r[8 * j + 2]), "=r"(r[8 * j + 3]),
+                           "=r"(r[8 * j + 4]), "=r"(r[8 * j + 5]), "=r"(r[8 * j + 6]), "=r"(r[8 * j + 7])
+                         : "r"(taddr + stride * j));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35]), "+r"(r[36]), "+r"(r[37]), "+r"(r[38]), "+r"(r[39])
+                 :: "memory");
+#pragma unroll
+    for (int i = 0; i < 40; i++) v[i] = __uint_as_float(r[i]);
 }
 
 // hidden-layer epilogue of one thread: columns [c0, c1) of its accumulator row ->

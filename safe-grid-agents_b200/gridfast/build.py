@@ -27,22 +27,44 @@ NVCC_FLAGS = [
 FAST_FLAGS = ["--split-compile", "0"]
 
 
-def stale():
-    if not os.path.exists(LIB):
+OBJ_DIR = os.path.join(HERE, "_build")
+# what each translation unit includes (sgk.cu does not see the tensor-core header)
+DEPS = {"sgk.cu": [h for h in HEADERS if h != "sgk_mlp_tc.cuh"], "sgk_dqn.cu": HEADERS}
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
         return True
-    built = os.path.getmtime(LIB)
+    built = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > built for s in sources)
+
+
+def stale():
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > built for d in deps)
+    return _newer(LIB, deps)
 
 
 def build(force=False, verbose=False):
+    """One object per translation unit (compiled side by side, recompiled only when its own sources
+    changed), then one link.  No relocatable device code: the units share host symbols only."""
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     fast = FAST_FLAGS if os.environ.get("SGK_FAST_BUILD") else []
-    cmd = [nvcc] + NVCC_FLAGS + fast + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    tag = "fast" if fast else "release"
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f not in ("-shared", "--threads", "2")]
+    jobs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, "%s.%s.o" % (os.path.splitext(src)[0], tag))
+        objs.append(obj)
+        if force or _newer(obj, [os.path.join(CSRC, f) for f in [src] + DEPS[src]]):
+            cmd = [nvcc] + flags + fast + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+            jobs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, job in jobs:
+        if job.wait() != 0:
+            raise subprocess.CalledProcessError(job.returncode, cmd)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
     return LIB
 
 
