@@ -591,3 +591,85 @@ def test_full_size_tomato_65536_envs_ssrl_and_shared():
     sim.rollout(T)
     _cmp_stats(env, sim)
     _cmp_table(env, agent, sim, 0)
+
+
+# ------------------------------------------------------------------ round-2 entry points
+def test_dense_delta_sync_equals_the_record_sync():
+    """The one-all-reduce form of the replica sync (dense canonical index, sgk_tabq_delta_export_dense /
+    _apply_dense) must leave every replica with exactly the table the (key, delta) record form leaves."""
+    gf = _gf()
+    hp = dict(lr=0.5, epsilon_anneal=200)
+    results = {}
+    for mode in ("records", "dense"):
+        reps = []
+        for r in range(2):
+            env = gf.BatchedEnv("SideEffectsSokoban-v0", 512, seed=4, env_id0=512 * r)
+            reps.append((env, gf.BatchedTabularQ(env, gf.Q_SHARED, **hp)))
+        assert reps[0][1].dense_size() == 36 * 36
+        for rnd in range(3):
+            for _, a in reps:
+                a.rollout(60)
+            if mode == "records":
+                exported = [a.delta_export() for _, a in reps]
+                for _, a in reps:
+                    a.restore_base()
+                    for keys, delta in exported:
+                        a.delta_apply(keys, delta, 0.5)
+                    a.rebase()
+            else:
+                total = reps[0][1].delta_export_dense() + reps[1][1].delta_export_dense()     # what the all-reduce computes
+                for _, a in reps:
+                    a.delta_apply_dense(total, 0.5)
+            for _, a in reps:
+                a.check()
+        tables = []
+        for _, a in reps:
+            keys, rows = a.export(0)
+            order = np.argsort(keys)
+            tables.append((keys[order], rows[order]))
+        assert np.array_equal(tables[0][0], tables[1][0]) and np.array_equal(tables[0][1], tables[1][1])
+        results[mode] = tables[0]
+    assert np.array_equal(results["records"][0], results["dense"][0])
+    # the record form adds the two scaled deltas one after the other, the dense form scales their sum:
+    # identical up to one rounding of the sum
+    assert np.allclose(results["records"][1], results["dense"][1], rtol=1e-15, atol=1e-13)
+
+
+@pytest.mark.parametrize("env_id,kind", ENVS)
+def test_keys_decode_back_into_the_boards_they_stand_for(env_id, kind):
+    """sgk_key_to_board is the inverse of sgk_board_to_key on every observation a rollout produces (what
+    lets the adapters show the device table as the reference's dict keyed by board tuples)."""
+    gf = _gf()
+    env = gf.BatchedEnv(env_id, 2048, seed=3)
+    seen = [env.render()]
+    for _ in range(6):
+        env.rollout_random(17)
+        seen.append(env.render())
+    boards = torch.cat(seen)
+    keys = env.board_keys(boards)
+    assert torch.equal(env.keys_to_boards(keys), boards)
+    assert len(torch.unique(keys)) == len(torch.unique(boards, dim=0))        # lossless: one key per distinct board
+
+
+def test_explicit_growth_keeps_every_table_entry():
+    gf = _gf()
+    from oracle import cgrid
+    n, seed = 300, 12
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=200)
+    env = gf.BatchedEnv("TomatoWatering-v0", n, seed=seed)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, capacity=512, **hp)
+    agent.rollout(300)
+    fill = agent.max_fill()
+    before = [agent.export(i) for i in (0, 150, n - 1)]
+    agent.grow(2048)                      # slot-major 512 -> table-major 2048
+    assert agent.capacity == 2048 and agent.max_fill() == fill
+    for (k0, r0), i in zip(before, (0, 150, n - 1)):
+        k1, r1 = agent.export(i)
+        o0, o1 = np.argsort(k0), np.argsort(k1)
+        assert np.array_equal(k0[o0], k1[o1]) and np.array_equal(r0[o0], r1[o1])
+    agent.rollout(200)                    # and the run continues exactly as the oracle's
+    agent.check()
+    sim = cgrid.Sim(cgrid.TOMATO, n, seed=seed, **hp)
+    sim.rollout(500)
+    _cmp_stats(env, sim, with_hash=False)
+    _cmp_table(env, agent, sim, 150)
