@@ -717,18 +717,6 @@ static_assert(SmemFb::TOTAL <= 227 * 1024, "fused backward: shared memory plan e
 constexpr int FB_THREADS = 384;      // 12 warps: 3 per TMEM lane quadrant, each masking a third of the columns (16 warps spilled)
 constexpr uint32_t FB_D0 = 0, FB_D1 = 128, FB_ACC2 = 256, FB_ACC1 = 384, FB_ACC3 = 448;     // TMEM columns (512 allocated)
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *mbar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ float half_bits_to_float(uint32_t h16)
-{
-    float f;
-    asm("{\n\t.reg .b16 h;\n\tcvt.u16.u32 h, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(h16 & 0xFFFFu));
-    return f;
-}
-
 // error-signal epilogue of one thread: 8-column groups [g0, g1) of its accumulator row, masked by the
 // FP16 activation image -> FP16 operand (x scale_up) and, for dH2, the TF32 chain operand
 __device__ __forceinline__ void tmem_ld8x5(uint32_t taddr, uint32_t stride, float (&v)[40], int n_loads);
@@ -1093,23 +1081,6 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
         :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-// 16 accumulator columns of this thread's lane; the wait carries the registers
-// so that nothing consuming them can be scheduled ahead of it
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
-{
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8])
