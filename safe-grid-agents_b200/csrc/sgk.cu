@@ -545,7 +545,9 @@ __device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i
 // per SM -- at 6 the grid needs a second wave and the rollout loses a quarter
 // of its rate (measured 4.6e10 -> 3.3e10 env-steps/s when the kernel grew from
 // 72 to 77 registers).  7 x 128 threads => at most 72 registers.
-template <int KIND, class Rng, bool TRACE, bool SSRL, bool DENSE>
+// CHEAT: -1 = the launch argument decides at run time; 0 / 1 = compiled in (the dense product kernel,
+// where the selects between observed and hidden reward are a measurable share of the ALU pipe)
+template <int KIND, class Rng, bool TRACE, bool SSRL, bool DENSE, int CHEAT = -1>
 #ifndef SGK_BOAT_MINBLOCKS
 #define SGK_BOAT_MINBLOCKS 1
 #endif
@@ -556,6 +558,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     if (i >= p.n) return;
     const uint32_t g = (uint32_t)i;
     const Level &L = p.level;
+    const bool cheat = CHEAT < 0 ? p.cheat != 0 : CHEAT != 0;
     EnvRegs e;
     unpack_env<KIND>(p.arr.core[i], e);
     e.ep_return = p.arr.ep_return[i];
@@ -606,8 +609,8 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     double last_r = 0.0, last_h = 0.0;
     int last_actual = 0;
 
-    for (int64_t k = 0; k < p.n_steps; k++) {
-        rng.set_step(p.t0 + (uint64_t)k);
+    // one lock-step; returns true when the rollout is over (episodic: the last episode ended)
+    auto lock_step = [&](const int64_t k, const unsigned long long explore_below) -> bool {
         if (episodic && (e.flags & SGK_F_DONE)) {
             // lazy reset: the new episode starts with this step
             env_reset<KIND>(L, e, rng);
@@ -624,7 +627,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         }
         // act_explore (value.py:37-42)
         int a = greedy;
-        if (rng.agent_uniform() < __ldg(p.thr + k)) a = rng.agent_choice();
+        if (rng.agent_uniform() < explore_below) a = rng.agent_choice();
         if (DENSE) touched |= 1u << slot;
         else if (slot == SGK_NOSLOT) slot = find_private(p.T, g, key, &status);
         if (SSRL) {
@@ -633,7 +636,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         }
         // env.step
         const StepOut o = env_step<KIND>(L, e, a, rng);
-        double r = p.cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;   // learn.py:72-73
+        double r = cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;   // learn.py:72-73
         if (SSRL && slot != SGK_NOSLOT) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[entry(p.T, slot, g)]));
         // learn (value.py:44-52): the successor's row is read before the write
         const uint64_t nkey = obs_key<KIND>(L, e);
@@ -647,7 +650,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             nrow = row;
             if (nkey != key) nslot = find_row_private(p.T, g, nkey, nrow, &status);
         }
-        const int la = (KIND == 6 && p.cheat) ? o.actual : a;     // learn.py:74-78: the action really taken
+        const int la = (KIND == 6 && cheat) ? o.actual : a;     // learn.py:74-78: the action really taken
         int next_greedy = 0;
         if (DENSE) {
             // one compare chain yields max Q(s', .) for the TD target AND the next
@@ -679,10 +682,9 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
                 e.flags |= SGK_F_DONE;
                 greedy = DENSE ? next_greedy : argmax_first(row);
                 fresh = true;
-                if (--episodes_left == 0) break;
-                continue;
+                return --episodes_left == 0;
             }
-            rng.set_step(p.t0 + (uint64_t)k + 1);
+            rng.set_env_step(p.t0 + (uint64_t)k + 1);
             env_reset<KIND>(L, e, rng);
             key = obs_key<KIND>(L, e);
             slot = SGK_NOSLOT;
@@ -697,6 +699,52 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         }
         greedy = DENSE ? next_greedy : argmax_first(row);
         fresh = o.done;
+        return false;
+    };
+    if constexpr (DENSE && Rng::kCounterMode) {
+        // Dense tables are issue-bound: walk the steps in the
+        // pairs that share one agent Philox call.  The call of the NEXT pair is
+        // computed beside this pair's first step, so its rounds fill the issue
+        // slots the dependent Q-learning chain leaves empty, and the word
+        // selection by step parity folds at compile time.  (Splitting the call
+        // five rounds beside each step measured 2.7 % slower.)
+        // An odd first step and an even last step of the call go through
+        // the plain path, so the pair loop carries no per-step guards.
+        int64_t k = 0;
+        bool over = p.n_steps <= 0;
+        if (!over && (p.t0 & 1)) {
+            rng.set_step(p.t0);
+            over = lock_step(0, __ldg(p.thr));
+            k = 1;
+        }
+        // the pair's exploration thresholds are fetched one pair ahead too (the load was the
+        // single largest stall of the loop when issued in the step that compares against it)
+        const int64_t last = p.n_steps > 0 ? p.n_steps - 1 : 0;
+        uint32_t ahead[4];
+        rng.pair_words((p.t0 + (uint64_t)k) >> 1, ahead);
+        unsigned long long below0 = __ldg(p.thr + min(k, last)), below1 = __ldg(p.thr + min(k + 1, last));
+        for (; !over && k + 2 <= p.n_steps; k += 2) {
+            const uint64_t t = p.t0 + (uint64_t)k, pair = t >> 1;
+            const unsigned long long b0 = below0, b1 = below1;
+            below0 = __ldg(p.thr + min(k + 2, last));
+            below1 = __ldg(p.thr + min(k + 3, last));
+            rng.adopt_pair(pair, ahead);
+            rng.pair_words(pair + 1, ahead);
+            rng.step_in_pair(t, 0);
+            over = lock_step(k, b0);
+            if (over) break;
+            rng.step_in_pair(t + 1, 1);
+            over = lock_step(k + 1, b1);
+        }
+        if (!over && k < p.n_steps) {
+            rng.set_step(p.t0 + (uint64_t)k);
+            lock_step(k, __ldg(p.thr + k));
+        }
+    } else {
+        for (int64_t k = 0; k < p.n_steps; k++) {
+            rng.set_step(p.t0 + (uint64_t)k);
+            if (lock_step(k, __ldg(p.thr + k))) break;
+        }
     }
     if (DENSE) {
         if (!fresh) touched |= 1u << slot;                      // the last learn touched Q[s']
@@ -2263,6 +2311,11 @@ static int launch_rollout(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t
             constexpr bool TRACE_ = decltype(TR)::value, SSRL_ = decltype(SS)::value;
             const unsigned rgrid = grid_for(env->n, SGK_BLOCK_ROLLOUT);
             const size_t dense_smem = (size_t)q->cap * SGK_NA * sizeof(double) * SGK_BLOCK_ROLLOUT;    // 32 KB
+            if constexpr (CAN_DENSE && !TRACE_ && !SSRL_ && Rng::kCounterMode) {
+                // the product kernel of the headline configuration: hidden-reward mode compiled in
+                if (dense && a.cheat) { k_rollout_private<KIND, Rng, TRACE_, SSRL_, true, 1><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a); return; }
+                if (dense) { k_rollout_private<KIND, Rng, TRACE_, SSRL_, true, 0><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a); return; }
+            }
             if (dense) k_rollout_private<KIND, Rng, TRACE_, SSRL_, CAN_DENSE><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a);
             else k_rollout_private<KIND, Rng, TRACE_, SSRL_, false><<<rgrid, SGK_BLOCK_ROLLOUT, 0, st>>>(a);
         };

@@ -106,12 +106,20 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1;
-        c3 = (uint32_t)p0;
+#ifdef __CUDA_ARCH__
+        // high and low product separately: ptxas fuses the pair into ONE IMAD.WIDE.U32.  Written as a
+        // 64-bit product of the widened constant it also emits an add of a zero high word per multiply
+        // (20 ALU-pipe instructions per call; the fused rollout is bound by that pipe).
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+#else
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+        const uint32_t n0 = h1 ^ c1 ^ k0;
+        const uint32_t n2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
         c0 = n0;
         c2 = n2;
         k0 += 0x9E3779B9u;
@@ -164,9 +172,37 @@ struct PhiloxStream {
         p1 = (uint32_t)((pair >> 32) & 0xFFFFFF) << 8;
         half = (uint32_t)step & 1u;
     }
+    // the step of the ENVIRONMENT draws only (reset at the end of step t draws as step t + 1);
+    // the agent call in flight is left alone
+    __device__ __forceinline__ void set_env_step(uint64_t step)
+    {
+        s0 = (uint32_t)step;
+        s1 = (uint32_t)((step >> 32) & 0xFFFFFF) << 8;
+    }
     __device__ __forceinline__ void call(int c, uint32_t out[4]) const
     {
         philox4x32_10(e0, e1, s0, (uint32_t)c | s1, k0, k1, out);
+    }
+    // Pair-unrolled rollouts (k_rollout_private with dense tables): the agent
+    // call of step pair `pair` is computed one pair AHEAD (pair_words) so its
+    // ten rounds interleave with the two dependent act->step->learn chains, is
+    // handed over by adopt_pair, and step_in_pair fixes the word pair at
+    // compile time (H = step & 1).  Same counters, same words as refill().
+    __device__ __forceinline__ void pair_words(uint64_t pair, uint32_t out[4]) const
+    {
+        philox4x32_10(e0, e1, (uint32_t)pair, (uint32_t)SGK_CALL_AGENT | ((uint32_t)((pair >> 32) & 0xFFFFFF) << 8), k0, k1, out);
+    }
+    __device__ __forceinline__ void adopt_pair(uint64_t pair, const uint32_t in[4])
+    {
+        p0 = have_p0 = (uint32_t)pair;
+        p1 = have_p1 = (uint32_t)((pair >> 32) & 0xFFFFFF) << 8;
+        w[0] = in[0]; w[1] = in[1]; w[2] = in[2]; w[3] = in[3];
+    }
+    __device__ __forceinline__ void step_in_pair(uint64_t step, uint32_t h)
+    {
+        s0 = (uint32_t)step;
+        s1 = (uint32_t)((step >> 32) & 0xFFFFFF) << 8;
+        half = h;
     }
     // Agent draws: ONE Philox call serves two consecutive agent-steps (counter
     // word 2 = step >> 1): step parity selects the word pair (a, b); the 53-bit
@@ -244,6 +280,7 @@ struct ReplayStream {
     bool dry_stream;
     static constexpr bool kCounterMode = false;  // strictly sequential consumption
     __device__ __forceinline__ void set_step(uint64_t) {}
+    __device__ __forceinline__ void set_env_step(uint64_t) {}
     __device__ __forceinline__ uint32_t next()
     {
         if (cursor >= n_words) { dry_stream = true; return 0; }

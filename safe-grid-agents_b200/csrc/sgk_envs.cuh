@@ -20,9 +20,13 @@ struct StepOut {
 
 __device__ __forceinline__ int action_delta(const Level &L, int a)
 {
-    // UP, DOWN, LEFT, RIGHT in cell-index space
-    const int vertical = (a & 1) ? L.W : -L.W, horizontal = (a & 1) ? 1 : -1;
-    return (a & 2) ? horizontal : vertical;
+    // UP, DOWN, LEFT, RIGHT in cell-index space: -W, +W, -1, +1 as the four signed bytes of one
+    // (launch-uniform) word; PRMT picks byte a and replicates its sign -- one multiply-add for the
+    // selector and one permute instead of a select tree on the ALU pipe
+    const uint32_t deltas = ((uint32_t)(-L.W) & 0xFFu) | (((uint32_t)L.W & 0xFFu) << 8) | 0x01FF0000u;
+    uint32_t d;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(deltas), "r"((uint32_t)a * 0x1111u + 0x8880u));   // nibble bit 3: sign of the byte
+    return (int)d;
 }
 
 __device__ __forceinline__ bool bit(uint64_t m, int c) { return (m >> c) & 1ull; }

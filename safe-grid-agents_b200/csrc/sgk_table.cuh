@@ -148,32 +148,29 @@ __device__ __forceinline__ uint32_t find_row_private(const TableView &T, uint32_
 }
 
 // np.argmax: first maximum wins (value.py:35)
-__device__ __forceinline__ int argmax_first(const QRow &r)
-{
-    int b = 0; double m = r.v0;
-    if (r.v1 > m) { m = r.v1; b = 1; }
-    if (r.v2 > m) { m = r.v2; b = 2; }
-    if (r.v3 > m) { m = r.v3; b = 3; }
-    return b;
-}
-
-// ... and the maximum itself (what learn bootstraps from, value.py:48-50)
+// ... and the maximum itself (what learn bootstraps from, value.py:48-50).
+// Two-level tournament: the halves compare in parallel, so the dependent chain
+// is two compare+select levels instead of three; strict > at both levels keeps
+// "first maximum wins" (a tie between the halves goes to the lower one).
 __device__ __forceinline__ int argmax_first(const QRow &r, double &m)
 {
-    int b = 0; m = r.v0;
-    if (r.v1 > m) { m = r.v1; b = 1; }
-    if (r.v2 > m) { m = r.v2; b = 2; }
-    if (r.v3 > m) { m = r.v3; b = 3; }
-    return b;
+    const bool p01 = r.v1 > r.v0, p23 = r.v3 > r.v2;
+    const double m01 = p01 ? r.v1 : r.v0, m23 = p23 ? r.v3 : r.v2;
+    const bool hi = m23 > m01;
+    m = hi ? m23 : m01;
+    return hi ? (p23 ? 3 : 2) : (p01 ? 1 : 0);
+}
+
+__device__ __forceinline__ int argmax_first(const QRow &r)
+{
+    double m;
+    return argmax_first(r, m);
 }
 
 __device__ __forceinline__ double row_max(const QRow &r)
 {
-    double m = r.v0;
-    if (r.v1 > m) m = r.v1;
-    if (r.v2 > m) m = r.v2;
-    if (r.v3 > m) m = r.v3;
-    return m;
+    const double m01 = r.v1 > r.v0 ? r.v1 : r.v0, m23 = r.v3 > r.v2 ? r.v3 : r.v2;
+    return m23 > m01 ? m23 : m01;
 }
 
 // branch-free element access (selects, not register shuffles behind branches)

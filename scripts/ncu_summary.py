@@ -15,7 +15,7 @@ keep = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
         "launch__occupancy_limit", "sm__warps_active.avg.pct", "sm__throughput.avg.pct", "sm__inst_executed.avg.per_cycle_elapsed",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct", "smsp__thread_inst_executed_per_inst_executed.ratio",
-        "sm__pipe_tensor", "sm__inst_executed_pipe_tensor", "sm__pipe_fp64_cycles_active.avg.pct", "sm__cycles_elapsed.avg",
+        "sm__pipe_", "smsp__pipe_", "sm__inst_executed_pipe_", "smsp__inst_executed_pipe_", "sm__cycles_elapsed.avg",
         "smsp__average_warps_issue_stalled", "l1tex__data_bank_conflicts", "smsp__sass_average_data_bytes_per_sector",
         "l1tex__average_t_sectors_per_request", "sm__sass_inst_executed_op_shared", "launch__shared_mem_per_block")
 with open(out, "w") as f:
