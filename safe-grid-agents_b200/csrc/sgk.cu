@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(SGK_BLOCK) k_tabq_learn_shared_b(const __grid_
     *q = __dadd_rn(q_sa, __dmul_rn(p.lr, __dsub_rn(scr_target[i], q_sa)));
 }
 
+#define SGK_THR_PAD 4
 // explore thresholds for lock-steps t0 .. t0+n-1: explore iff u53 < thr[k].
 // epsilon_at(k) per value.py:23-28,54-58, in float64 with IEEE division.
 __global__ void k_eps_thresholds(unsigned long long *thr, int64_t n, uint64_t t0, double one_minus_eps, int64_t anneal, int zero_first)
@@ -453,13 +454,15 @@ __global__ void k_eps_thresholds(unsigned long long *thr, int64_t n, uint64_t t0
 int ensure_eps_thresholds(unsigned long long **thr, int64_t *thr_cap, int64_t n_steps, uint64_t t0, double epsilon,
                           int64_t anneal, int zero_first, cudaStream_t st)
 {
+    // SGK_THR_PAD entries past the last step: the pair-unrolled rollout fetches thresholds one pair ahead
+    // without clamping the index (the padding holds the thresholds of the following steps, unused)
     if (*thr_cap < n_steps) {
         if (*thr) cudaFree(*thr);
         *thr = nullptr; *thr_cap = 0;
-        CU(cudaMalloc(thr, (size_t)n_steps * 8));
+        CU(cudaMalloc(thr, (size_t)(n_steps + SGK_THR_PAD) * 8));
         *thr_cap = n_steps;
     }
-    k_eps_thresholds<<<grid_for(n_steps, 256), 256, 0, st>>>(*thr, n_steps, t0, 1 - epsilon, anneal, zero_first);
+    k_eps_thresholds<<<grid_for(n_steps + SGK_THR_PAD, 256), 256, 0, st>>>(*thr, n_steps + SGK_THR_PAD, t0, 1 - epsilon, anneal, zero_first);
     return launch_check("k_eps_thresholds");
 }
 
@@ -719,17 +722,24 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         }
         // the pair's exploration thresholds are fetched one pair ahead too (the load was the
         // single largest stall of the loop when issued in the step that compares against it)
-        const int64_t last = p.n_steps > 0 ? p.n_steps - 1 : 0;
+        // (the table is padded by SGK_THR_PAD entries, so k + 3 is always readable)
         uint32_t ahead[4];
-        rng.pair_words((p.t0 + (uint64_t)k) >> 1, ahead);
-        unsigned long long below0 = __ldg(p.thr + min(k, last)), below1 = __ldg(p.thr + min(k + 1, last));
+        const uint64_t pair0 = (p.t0 + (uint64_t)k) >> 1;
+        rng.pair_words(pair0, ahead);
+        // counter words of the NEXT pair, carried incrementally
+        uint32_t c2 = (uint32_t)(pair0 + 1), c3 = (uint32_t)SGK_CALL_AGENT | ((uint32_t)(((pair0 + 1) >> 32) & 0xFFFFFF) << 8);
+        const unsigned long long *below = p.thr + k;
+        unsigned long long below0 = __ldg(below), below1 = __ldg(below + 1);
         for (; !over && k + 2 <= p.n_steps; k += 2) {
-            const uint64_t t = p.t0 + (uint64_t)k, pair = t >> 1;
+            const uint64_t t = p.t0 + (uint64_t)k;
             const unsigned long long b0 = below0, b1 = below1;
-            below0 = __ldg(p.thr + min(k + 2, last));
-            below1 = __ldg(p.thr + min(k + 3, last));
-            rng.adopt_pair(pair, ahead);
-            rng.pair_words(pair + 1, ahead);
+            below += 2;
+            below0 = __ldg(below);
+            below1 = __ldg(below + 1);
+            rng.adopt_pair(ahead);
+            rng.pair_words_at(c2, c3, ahead);
+            c2 += 1;
+            if (c2 == 0) c3 += 0x100u;
             rng.step_in_pair(t, 0);
             over = lock_step(k, b0);
             if (over) break;

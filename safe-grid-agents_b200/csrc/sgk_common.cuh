@@ -192,10 +192,15 @@ struct PhiloxStream {
     {
         philox4x32_10(e0, e1, (uint32_t)pair, (uint32_t)SGK_CALL_AGENT | ((uint32_t)((pair >> 32) & 0xFFFFFF) << 8), k0, k1, out);
     }
-    __device__ __forceinline__ void adopt_pair(uint64_t pair, const uint32_t in[4])
+    // ... or from the two counter words themselves, which the pair loop carries incrementally
+    // (word 2 = pair low, word 3 = call | pair high << 8) instead of re-deriving them from a 64-bit step
+    __device__ __forceinline__ void pair_words_at(uint32_t c2, uint32_t c3, uint32_t out[4]) const
     {
-        p0 = have_p0 = (uint32_t)pair;
-        p1 = have_p1 = (uint32_t)((pair >> 32) & 0xFFFFFF) << 8;
+        philox4x32_10(e0, e1, c2, c3, k0, k1, out);
+    }
+    __device__ __forceinline__ void adopt_pair(const uint32_t in[4])
+    {
+        have_p0 = p0; have_p1 = p1;      // the cached call IS the current one: refill() folds away
         w[0] = in[0]; w[1] = in[1]; w[2] = in[2]; w[3] = in[3];
     }
     __device__ __forceinline__ void step_in_pair(uint64_t step, uint32_t h)
