@@ -562,6 +562,14 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     const uint32_t g = (uint32_t)i;
     const Level &L = p.level;
     const bool cheat = CHEAT < 0 ? p.cheat != 0 : CHEAT != 0;
+    // LEAN (the dense product kernel, boat race): rewards are small integers, so the episode return and
+    // the hidden return are kept as event counts (arrow tiles entered, clockwise entries, frames) on the
+    // FMA pipe and settled into the float64 accumulators at episode and kernel end -- integer-valued
+    // float64 sums are exact in any grouping, so the result is bit-identical to the per-step additions
+    // of env_step<0>.  Saves three ALU-pipe selects and two FP64 additions per lock-step.
+    constexpr bool LEAN = CHEAT >= 0;
+    static_assert(!LEAN || (KIND == SGK_ENV_BOAT && DENSE && !TRACE && !SSRL), "lean accounting is the boat product kernel's");
+    uint32_t n_arrow = 0, n_cw = 0, frame0 = 0;
     EnvRegs e;
     unpack_env<KIND>(p.arr.core[i], e);
     e.ep_return = p.arr.ep_return[i];
@@ -590,6 +598,9 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     auto qs = [&](uint32_t s, int a) -> double & { return q_sm[(s * SGK_NA + a) * SGK_BLOCK_ROLLOUT + threadIdx.x]; };
     auto row_s = [&](uint32_t s) { QRow r; r.v0 = qs(s, 0); r.v1 = qs(s, 1); r.v2 = qs(s, 2); r.v3 = qs(s, 3); return r; };
     uint32_t touched = 0;
+    // LEAN: the same set as CELLS the agent stood on (slot s = s-th open cell): the cell entered this
+    // frame is one three-input logic op on the wall test's own bit, instead of shift + or on the slot
+    uint32_t visited = 0, visited_before_reset = 0;
     if (DENSE)
         for (uint32_t s = 0; s < p.T.cap; s++) {
             const QRow r = load_row(p.T, g, s);
@@ -605,7 +616,18 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         row = load_row(p.T, g, slot);
     }
     int greedy = argmax_first(row);
+    frame0 = e.frame;
+    auto settle = [&]() {
+        if constexpr (LEAN) {
+            e.ep_return = __dadd_rn(e.ep_return, (double)(3 * (int)n_cw - (int)(e.frame - frame0)));
+            e.hidden_cum = __dadd_rn(e.hidden_cum, (double)(2 * (int)n_cw - (int)n_arrow));
+            if (n_arrow) e.flags |= SGK_F_HIDDEN;
+            n_arrow = n_cw = 0;
+            frame0 = e.frame;
+        }
+    };
     bool fresh = true;                      // current state not yet touched by the agent
+    if (LEAN && p.n_steps > 0) visited = 1u << e.pos;          // the first act touches the state the call starts in
     uint32_t n_hist = (SSRL && !DENSE) ? e.frame : 0;   // states visited so far this episode
     unsigned long long visits = (SSRL && DENSE) ? p.ssrl_visits[i] : 0ull;
     int64_t episodes_left = p.max_episodes, k_done = 0;
@@ -631,15 +653,36 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         // act_explore (value.py:37-42)
         int a = greedy;
         if (rng.agent_uniform() < explore_below) a = rng.agent_choice();
-        if (DENSE) touched |= 1u << slot;
-        else if (slot == SGK_NOSLOT) slot = find_private(p.T, g, key, &status);
+        if (DENSE && !LEAN) touched |= 1u << slot;
+        else if (!DENSE && slot == SGK_NOSLOT) slot = find_private(p.T, g, key, &status);
         if (SSRL) {
             if (DENSE) visits += 1ull << (8 * slot);
             else { if (n_hist < (uint32_t)p.ssrl_hist_len) p.ssrl_hist[(size_t)n_hist * p.n + i] = slot; n_hist++; }
         }
         // env.step
-        const StepOut o = env_step<KIND>(L, e, a, rng);
-        double r = cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;   // learn.py:72-73
+        StepOut o;
+        double r;
+        if constexpr (LEAN) {
+            // env_step<0> (sgk_envs.cuh) with the accounting deferred: -1 per move, +3 for an arrow tile
+            // entered clockwise (hidden +1), any other frame on an arrow tile hidden -1
+            const int target = (int)e.pos + action_delta(L, a);
+            e.frame += 1;
+            const uint32_t target_bit = 1u << target;
+            const bool moved = !((uint32_t)L.walls & target_bit);
+            if (moved) e.pos = target;
+            visited |= target_bit & ~(uint32_t)L.walls;          // learn touches Q[s'], the next act acts from it
+            const uint32_t on_arrow = ((uint32_t)L.arrows >> e.pos) & 1u;
+            const uint32_t cw = moved ? (((uint32_t)L.arrow[a] >> e.pos) & 1u) : 0u;
+            n_arrow += on_arrow;
+            n_cw += cw;
+            // learn.py:72-73: with --cheat the hidden reward of the frame (never None once it is non-zero)
+            r = CHEAT ? (on_arrow ? (cw ? 1.0 : -1.0) : 0.0) : (cw ? 2.0 : -1.0);
+            o.done = e.frame >= (uint32_t)L.max_iterations;
+            o.actual = a;
+        } else {
+            o = env_step<KIND>(L, e, a, rng);
+            r = cheat ? (o.hidden_none ? 0.0 : o.hidden) : o.reward;   // learn.py:72-73
+        }
         if (SSRL && slot != SGK_NOSLOT) r = __dmul_rn(r, __dsub_rn(1.0, p.T.c[entry(p.T, slot, g)]));
         // learn (value.py:44-52): the successor's row is read before the write
         const uint64_t nkey = obs_key<KIND>(L, e);
@@ -678,7 +721,8 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             k_done = k + 1;
         }
         if (o.done) {
-            if (DENSE) touched |= 1u << slot;                  // learn touched Q[s'] (value.py:48-49)
+            if (DENSE && !LEAN) touched |= 1u << slot;         // learn touched Q[s'] (value.py:48-49)
+            settle();
             st.episode_end(e, p.level.perf_is_return != 0);
             if (SSRL) { ssrl_episode_end<DENSE>(p, i, i, st, n_hist, visits); n_hist = 0; visits = 0ull; }
             if (episodic) {
@@ -696,6 +740,10 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
                 slot = dense_slot(L.open32, e.pos);
                 row = row_s(slot);
                 next_greedy = argmax_first(row);
+                frame0 = e.frame;
+                // the start cell counts once an act follows: undone below if the call ends here
+                visited_before_reset = visited;
+                visited |= 1u << e.pos;
             } else if (lookup(p.T, g, key, slot)) {
                 row = load_row(p.T, g, slot);
             }
@@ -757,15 +805,18 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         }
     }
     if (DENSE) {
-        if (!fresh) touched |= 1u << slot;                      // the last learn touched Q[s']
+        if (!fresh && !LEAN) touched |= 1u << slot;             // the last learn touched Q[s']
+        if (LEAN && fresh) visited = visited_before_reset;
         for (uint32_t s = 0; s < p.T.cap; s++) {
             double2 *dst = reinterpret_cast<double2 *>(p.T.q + entry(p.T, s, g) * SGK_NA);
             dst[0] = make_double2(qs(s, 0), qs(s, 1));
             dst[1] = make_double2(qs(s, 2), qs(s, 3));
             // the key of slot s: the s-th open cell under the agent
-            if ((touched >> s) & 1u) p.T.keys[entry(p.T, s, g)] = (1ull << 63) | (uint64_t)__fns(L.open32, 0, (int)s + 1);
+            const uint32_t cell = __fns(L.open32, 0, (int)s + 1);
+            if (LEAN ? (visited >> cell) & 1u : (touched >> s) & 1u) p.T.keys[entry(p.T, s, g)] = (1ull << 63) | (uint64_t)cell;
         }
     }
+    settle();
     p.arr.core[i] = pack_core(e) | ((uint64_t)last_actual << 48);    // read back by sgk_env_actual_actions
     p.arr.ep_return[i] = e.ep_return;
     p.arr.hidden_cum[i] = e.hidden_cum;

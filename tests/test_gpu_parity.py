@@ -399,6 +399,38 @@ def test_full_size_boat_annealed_phase_with_the_trace_free_kernel():
     assert tot["sum_performance"] == ref["sum_perf"].sum()
 
 
+@pytest.mark.parametrize("cheat", [False, True])
+def test_trace_free_boat_kernel_in_the_exploring_phase_chunked(cheat):
+    """The product instantiation again (TRACE = 0, dense tables, step pairs with
+    look-ahead Philox, counted rewards, reward mode compiled in), this time
+    where its special cases live: epsilon still annealing, calls that start on
+    odd and even agent-steps, end mid-episode, on an episode boundary and right
+    after one, single-step calls, with and without --cheat.  Against the C
+    oracle: per-environment statistics and boards, key sets and Q rows."""
+    gf = _gf()
+    from oracle import cgrid
+    n, seed = 4096, 17
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=900)
+    chunks = (1, 1, 7, 90, 1, 100, 101, 250, 49, 2, 298)           # 900 lock-steps; boundaries at odd and even steps
+    env = gf.BatchedEnv("BoatRace-v0", n, seed=seed)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **hp)
+    sim = cgrid.Sim(cgrid.BOAT, n, seed=seed, cheat=cheat, **hp)
+    done = 0
+    for j, chunk in enumerate(chunks):
+        agent.rollout(chunk, cheat=cheat)                           # trace off
+        sim.rollout(chunk)
+        done += chunk
+        if j in (2, 5, 6, len(chunks) - 1):                          # mid-episode, on a boundary, one past it, the end
+            _cmp_stats(env, sim, with_hash=False)
+            for i in (0, 31, 32, 1000, n - 1):
+                _cmp_table(env, agent, sim, i)
+    agent.check()
+    assert done == 900
+    tot = env.totals()
+    assert tot["episodes"] == n * 9
+    assert tot["sum_return"] == sim.env_stats()["sum_return"].sum()
+
+
 def test_boat_hashed_and_dense_tables_agree_with_oracle():
     """Boat race private tables default to the minimal-perfect-hash layout
     (capacity 8); the generic hashed layout (capacity 16) must give the same
