@@ -371,6 +371,18 @@ def run_ours(args, out):
                          "warp_instructions_per_env_step": inst * 32 / (n * T),
                          "peak_source": "4 issue slots x 148 SMs x SM clock sampled under load (%.0f MHz)" % (f_sm / 1e6),
                          "instruction_count_source": issue.get("source")})
+            alu = issue.get("alu_pipe_warp_instructions_by_launch")
+            if alu:
+                # the unit that actually binds: the integer/logic ALU pipe takes one warp-instruction
+                # every 2 cycles per scheduler (B300_MICROARCH.md "Pipe rates": rt_SMSP = 2), and most
+                # of the lock-step (selects, shifts, compares, Philox xors) runs on it
+                a_timed = alu[W:W + K] if len(alu) >= W + K else alu
+                a_inst = sum(a_timed) / len(a_timed)
+                alu_peak = 0.5 * 4 * 148 * f_sm / 1e9
+                roof["alu_pipe"] = {"achieved": a_inst / per_launch_s / 1e9, "peak": alu_peak, "unit": "Gwarp-inst/s",
+                                    "frac": a_inst / per_launch_s / 1e9 / alu_peak,
+                                    "warp_instructions_per_env_step": a_inst * 32 / (n * T),
+                                    "peak_source": "1 ALU-pipe warp-instruction per 2 cycles x 4 schedulers x 148 SMs x SM clock"}
         else:
             roof.update({"bound": "hbm", "achieved": contract, "peak": peak, "unit": "GB/s", "frac": contract / peak,
                          "peak_source": peak_src})

@@ -99,6 +99,12 @@ bool make_level(int kind, Level &L)
             if (ch != '#' && ch != 'O') L.n_delusional++;
         }
     if (L.HW <= 32) L.open32 = ~(uint32_t)L.walls & (uint32_t)((1ull << L.HW) - 1);
+    memset(L.cell_rank, 0xFF, sizeof(L.cell_rank));
+    for (int cell = 0; cell < L.HW; cell++)
+        if (art[cell / L.W][cell % L.W] != '#') {
+            L.cell_rank[cell] = (uint8_t)L.n_open;
+            L.open_cell[L.n_open++] = (uint8_t)cell;
+        }
     for (int r = 0; r < L.H; r++) {
         bool full = true;
         for (int c = 0; c < L.W; c++) full = full && art[r][c] == '#';
@@ -144,6 +150,8 @@ struct sgk_tabq {
     int64_t n_tables, cap, n_envs;
     int log_cap;
     uint32_t dense_open;       // boat race, private tables: minimal perfect hash
+    uint32_t perfect_n;        // sokoban level 0, private tables: perfect index (n_open, 0 = hashed)
+    uint8_t *perfect_rank;     // device copy of Level::cell_rank
     int table_major;           // hashed private tables: [table][slot] instead of [slot][table]
     unsigned long long *keys;
     double *q;
@@ -189,6 +197,7 @@ static TableView view_of(const sgk_tabq *q)
     T.slot_stride = q->table_major ? 1u : (uint32_t)q->n_tables;
     T.table_stride = q->table_major ? (uint32_t)q->cap : 1u;
     T.dense_open = q->dense_open;
+    T.perfect_n = q->perfect_n; T.perfect_rank = q->perfect_rank;
     return T;
 }
 
@@ -550,7 +559,9 @@ __device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i
 // 72 to 77 registers).  7 x 128 threads => at most 72 registers.
 // CHEAT: -1 = the launch argument decides at run time; 0 / 1 = compiled in (the dense product kernel,
 // where the selects between observed and hidden reward are a measurable share of the ALU pipe)
-template <int KIND, class Rng, bool TRACE, bool SSRL, bool DENSE, int CHEAT = -1>
+// TABLE: 0 = hashed tables in HBM; 1 = dense tables held in shared memory (boat race); 2 = perfect-index
+// tables in HBM (sokoban level 0: slot computed from the state, no key reads, no probing)
+template <int KIND, class Rng, bool TRACE, bool SSRL, int TABLE, int CHEAT = -1>
 #ifndef SGK_BOAT_MINBLOCKS
 #define SGK_BOAT_MINBLOCKS 1
 #endif
@@ -562,6 +573,8 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     const uint32_t g = (uint32_t)i;
     const Level &L = p.level;
     const bool cheat = CHEAT < 0 ? p.cheat != 0 : CHEAT != 0;
+    constexpr bool DENSE = TABLE == 1, PERFECT = TABLE == 2;
+    static_assert(!PERFECT || KIND == SGK_ENV_SOKOBAN, "the perfect index is sokoban level 0's");
     // LEAN (the dense product kernel, boat race): rewards are small integers, so the episode return and
     // the hidden return are kept as event counts (arrow tiles entered, clockwise entries, frames) on the
     // FMA pipe and settled into the float64 accumulators at episode and kernel end -- integer-valued
@@ -601,6 +614,13 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     // LEAN: the same set as CELLS the agent stood on (slot s = s-th open cell): the cell entered this
     // frame is one three-input logic op on the wall test's own bit, instead of shift + or on the slot
     uint32_t visited = 0, visited_before_reset = 0;
+    // PERFECT: which slots the agent touched, (cap / 32) words per thread in shared memory (column
+    // threadIdx.x); their keys are written once, when the kernel ends
+    uint32_t *touched_sm = reinterpret_cast<uint32_t *>(q_sm);
+    auto touch = [&](uint32_t s) { touched_sm[(s >> 5) * SGK_BLOCK_ROLLOUT + threadIdx.x] |= 1u << (s & 31u); };
+    auto perfect_of = [&]() { return (uint32_t)L.cell_rank[e.pos] * (uint32_t)L.n_open + (uint32_t)L.cell_rank[e.box]; };
+    if (PERFECT)
+        for (uint32_t w = 0; w < (p.T.cap + 31u) / 32u; w++) touched_sm[w * SGK_BLOCK_ROLLOUT + threadIdx.x] = 0u;
     if (DENSE)
         for (uint32_t s = 0; s < p.T.cap; s++) {
             const QRow r = load_row(p.T, g, s);
@@ -612,6 +632,9 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
     if (DENSE) {
         slot = dense_slot(L.open32, e.pos);
         row = row_s(slot);
+    } else if (PERFECT) {
+        slot = perfect_of();
+        row = load_row(p.T, g, slot);        // never written = the zero row of an unseen state
     } else if (lookup(p.T, g, key, slot)) {
         row = load_row(p.T, g, slot);
     }
@@ -645,6 +668,9 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             if (DENSE) {
                 slot = dense_slot(L.open32, e.pos);
                 row = row_s(slot);
+            } else if (PERFECT) {
+                slot = perfect_of();
+                row = load_row(p.T, g, slot);
             } else if (lookup(p.T, g, key, slot)) {
                 row = load_row(p.T, g, slot);
             }
@@ -654,6 +680,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         int a = greedy;
         if (rng.agent_uniform() < explore_below) a = rng.agent_choice();
         if (DENSE && !LEAN) touched |= 1u << slot;
+        else if (PERFECT) touch(slot);
         else if (!DENSE && slot == SGK_NOSLOT) slot = find_private(p.T, g, key, &status);
         if (SSRL) {
             if (DENSE) visits += 1ull << (8 * slot);
@@ -691,6 +718,10 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         if (DENSE) {
             nslot = dense_slot(L.open32, e.pos);
             nrow = row_s(nslot);
+        } else if (PERFECT) {
+            nslot = perfect_of();
+            nrow = row;
+            if (nslot != slot) nrow = load_row(p.T, g, nslot);
         } else {
             nslot = slot;
             nrow = row;
@@ -722,6 +753,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
         }
         if (o.done) {
             if (DENSE && !LEAN) touched |= 1u << slot;         // learn touched Q[s'] (value.py:48-49)
+            if (PERFECT) touch(slot);
             settle();
             st.episode_end(e, p.level.perf_is_return != 0);
             if (SSRL) { ssrl_episode_end<DENSE>(p, i, i, st, n_hist, visits); n_hist = 0; visits = 0ull; }
@@ -744,6 +776,9 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
                 // the start cell counts once an act follows: undone below if the call ends here
                 visited_before_reset = visited;
                 visited |= 1u << e.pos;
+            } else if (PERFECT) {
+                slot = perfect_of();
+                row = load_row(p.T, g, slot);
             } else if (lookup(p.T, g, key, slot)) {
                 row = load_row(p.T, g, slot);
             }
@@ -815,6 +850,15 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             const uint32_t cell = __fns(L.open32, 0, (int)s + 1);
             if (LEAN ? (visited >> cell) & 1u : (touched >> s) & 1u) p.T.keys[entry(p.T, s, g)] = (1ull << 63) | (uint64_t)cell;
         }
+    }
+    if (PERFECT) {
+        if (!fresh) touch(slot);                                // the last learn touched Q[s']
+        for (uint32_t w = 0; w < (p.T.cap + 31u) / 32u; w++)
+            for (uint32_t bits = touched_sm[w * SGK_BLOCK_ROLLOUT + threadIdx.x]; bits; bits &= bits - 1u) {
+                const uint32_t s = w * 32u + (uint32_t)__ffs((int)bits) - 1u;
+                const uint32_t agent_cell = L.open_cell[s / (uint32_t)L.n_open], box_cell = L.open_cell[s % (uint32_t)L.n_open];
+                p.T.keys[entry(p.T, s, g)] = (1ull << 63) | (uint64_t)agent_cell | ((uint64_t)box_cell << 8);
+            }
     }
     settle();
     p.arr.core[i] = pack_core(e) | ((uint64_t)last_actual << 48);    // read back by sgk_env_actual_actions
@@ -1779,7 +1823,7 @@ extern "C" int sgk_tabq_destroy(sgk_tabq *q)
     DeviceGuard g(q->device);
     void *ptrs[] = {q->keys, q->q, q->c, q->winner, q->status, q->thr, q->scr_slot, q->scr_target,
                     q->ssrl_hist, q->ssrl_budget, q->ssrl_counts, q->base_keys, q->base_q, q->pub_target,
-                    q->ssrl_visits, q->fill_scratch};
+                    q->ssrl_visits, q->fill_scratch, q->perfect_rank};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete q;
     return SGK_OK;
@@ -1816,6 +1860,12 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
     q->lr = 0.5; q->discount = 0.99; q->epsilon = 0.01; q->anneal = 100000;
     q->auto_grow = 1;
     q->dense_open = dense ? env->level.open32 : 0u;
+    // sokoban level 0, default capacity: rank(agent) * n_open + rank(box) is a perfect index into the
+    // 128 slots (121 used); any other capacity keeps the hashed layout (and is what the tests compare with)
+    const bool perfect = env->level.kind == SGK_ENV_SOKOBAN && q_mode == SGK_Q_PRIVATE &&
+                         (int64_t)env->level.n_open * env->level.n_open <= capacity &&
+                         2 * (int64_t)env->level.n_open * env->level.n_open > capacity;
+    q->perfect_n = perfect ? (uint32_t)env->level.n_open : 0u;
     {
         // distinct observations of the level (an upper bound): a table at least this
         // large can never fill, smaller ones grow on demand (reserve_slots)
@@ -1841,6 +1891,9 @@ extern "C" int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity,
     if (ok && q_mode == SGK_Q_SHARED)
         ok = cudaMalloc(&q->winner, 2 * slots * 8 * SGK_NA) == cudaSuccess && cudaMemset(q->winner, 0, 2 * slots * 8 * SGK_NA) == cudaSuccess &&
              cudaMalloc(&q->pub_target, 2 * (size_t)env->n * 8) == cudaSuccess;
+    if (ok && q->perfect_n)
+        ok = cudaMalloc(&q->perfect_rank, sizeof(env->level.cell_rank)) == cudaSuccess &&
+             cudaMemcpy(q->perfect_rank, env->level.cell_rank, sizeof(env->level.cell_rank), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         sgk_tabq_destroy(q);
         return fail(SGK_ECUDA, "cudaMalloc failed for the Q table (" + std::to_string(slots * 40 >> 20) + " MiB)");
@@ -2113,7 +2166,7 @@ static int table_max_fill(sgk_tabq *q, cudaStream_t st, int64_t *out)
 
 static int grow_tables(sgk_tabq *q, int64_t new_cap, cudaStream_t st)
 {
-    REQUIRE(q->q_mode == SGK_Q_PRIVATE && !q->dense_open, "only hashed private tables grow");
+    REQUIRE(q->q_mode == SGK_Q_PRIVATE && !q->dense_open && !q->perfect_n, "only hashed private tables grow");
     REQUIRE(new_cap > q->cap && (new_cap & (new_cap - 1)) == 0, "new capacity must be a larger power of two");
     if ((uint64_t)new_cap * (uint64_t)q->n_tables >= (1ull << 32))
         return fail(SGK_EFULL, "a Q table is full and cannot grow: capacity x tables would reach 2^32 slots");
@@ -2165,7 +2218,7 @@ static int grow_tables(sgk_tabq *q, int64_t new_cap, cudaStream_t st)
 static int reserve_slots(sgk_tabq *q, int64_t want, int64_t at_least, cudaStream_t st, int64_t *granted)
 {
     *granted = want;
-    if (q->q_mode != SGK_Q_PRIVATE || q->dense_open || !q->auto_grow) return SGK_OK;
+    if (q->q_mode != SGK_Q_PRIVATE || q->dense_open || q->perfect_n || !q->auto_grow) return SGK_OK;
     auto limit = [&]() { return q->cap > 512 ? q->cap - q->cap / 4 : q->cap; };
     if (q->max_states > 0 && q->max_states <= limit()) return SGK_OK;     // can hold every observation there is
     if (limit() - q->fill_ub >= want) { q->fill_ub += want; return SGK_OK; }
@@ -2374,11 +2427,18 @@ static int launch_rollout(sgk_env *env, sgk_tabq *q, int64_t n_steps, uint64_t t
             const size_t dense_smem = (size_t)q->cap * SGK_NA * sizeof(double) * SGK_BLOCK_ROLLOUT;    // 32 KB
             if constexpr (CAN_DENSE && !TRACE_ && !SSRL_ && Rng::kCounterMode) {
                 // the product kernel of the headline configuration: hidden-reward mode compiled in
-                if (dense && a.cheat) { k_rollout_private<KIND, Rng, TRACE_, SSRL_, true, 1><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a); return; }
-                if (dense) { k_rollout_private<KIND, Rng, TRACE_, SSRL_, true, 0><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a); return; }
+                if (dense && a.cheat) { k_rollout_private<KIND, Rng, TRACE_, SSRL_, 1, 1><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a); return; }
+                if (dense) { k_rollout_private<KIND, Rng, TRACE_, SSRL_, 1, 0><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a); return; }
             }
-            if (dense) k_rollout_private<KIND, Rng, TRACE_, SSRL_, CAN_DENSE><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a);
-            else k_rollout_private<KIND, Rng, TRACE_, SSRL_, false><<<rgrid, SGK_BLOCK_ROLLOUT, 0, st>>>(a);
+            if constexpr (KIND == SGK_ENV_SOKOBAN) {
+                if (q->perfect_n) {
+                    const size_t touched_smem = (size_t)((q->cap + 31) / 32) * 4 * SGK_BLOCK_ROLLOUT;
+                    k_rollout_private<KIND, Rng, TRACE_, SSRL_, 2><<<rgrid, SGK_BLOCK_ROLLOUT, touched_smem, st>>>(a);
+                    return;
+                }
+            }
+            if (dense) k_rollout_private<KIND, Rng, TRACE_, SSRL_, CAN_DENSE ? 1 : 0><<<rgrid, SGK_BLOCK_ROLLOUT, dense_smem, st>>>(a);
+            else k_rollout_private<KIND, Rng, TRACE_, SSRL_, 0><<<rgrid, SGK_BLOCK_ROLLOUT, 0, st>>>(a);
         };
         if (ssrl) {
             if (replay) go(type_tag<ReplayStream>(), std::true_type(), std::true_type());

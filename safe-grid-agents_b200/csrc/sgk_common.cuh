@@ -48,6 +48,11 @@ struct Level {
     uint8_t coin_cell[SGK_MAX_COINS];     // cell of coin k, row-major order
     uint8_t coin_slot[SGK_MAX_CELLS];     // inverse: coin index of a cell, 0xFF if none
     int n_coins;
+    // rank of a cell among the non-wall cells (0xFF for walls) and its inverse: sokoban level 0 addresses
+    // its private tables by rank(agent) * n_open + rank(box), a perfect index (sgk_table.cuh)
+    uint8_t cell_rank[SGK_MAX_CELLS];
+    uint8_t open_cell[SGK_MAX_CELLS];
+    int n_open;
 };
 
 // ----------------------------------------------------------------- state

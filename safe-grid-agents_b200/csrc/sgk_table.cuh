@@ -33,6 +33,8 @@ struct TableView {
     uint32_t slot_stride, table_stride;   // entry index = slot * slot_stride + table * table_stride
     uint32_t cap, log_cap;
     uint32_t dense_open;          // != 0: minimal perfect hash (boat race), see dense_slot
+    uint32_t perfect_n;           // != 0: perfect index rank(agent) * perfect_n + rank(box) (sokoban level 0)
+    const uint8_t *perfect_rank;  // ... the rank of a cell among the non-wall cells, 0xFF for a wall
 };
 
 // Multiplicative hash of the two key halves, 32-bit arithmetic only.
@@ -49,6 +51,16 @@ __device__ __forceinline__ uint32_t dense_slot(uint32_t open32, uint32_t pos)
     return __popc(open32 & ((1u << pos) - 1u));
 }
 
+// Sokoban level 0: the observation is (agent cell, box cell), both non-wall: 11 x 11 = 121 of the 128
+// slots, no probing and no key compare -- a row that was never written reads as the zero row of an
+// unseen state, so lookups need not read the key at all; keys are written on touch, so the key set
+// still equals the reference dict's.  A board that puts the agent or the box on a wall has no slot.
+__device__ __forceinline__ uint32_t perfect_slot(const TableView &T, uint64_t key)
+{
+    const uint32_t a = T.perfect_rank[(uint32_t)key & 0xFFu], b = T.perfect_rank[(uint32_t)(key >> 8) & 0xFFu];
+    return (a == 0xFFu || b == 0xFFu) ? SGK_NOSLOT : a * T.perfect_n + b;
+}
+
 __device__ __forceinline__ size_t entry(const TableView &T, uint32_t slot, uint32_t g)
 {
     return (size_t)(slot * T.slot_stride + g * T.table_stride);
@@ -60,6 +72,12 @@ __device__ __forceinline__ uint32_t find_private(const TableView &T, uint32_t g,
     if (T.dense_open) {
         const uint32_t s = dense_slot(T.dense_open, (uint32_t)key & 0xFFu);
         T.keys[entry(T, s, g)] = key;
+        return s;
+    }
+    if (T.perfect_n) {
+        const uint32_t s = perfect_slot(T, key);
+        if (s == SGK_NOSLOT) *status = SGK_ST_FULL;
+        else T.keys[entry(T, s, g)] = key;
         return s;
     }
     uint32_t s = home_slot(key, T.log_cap);
@@ -99,6 +117,10 @@ __device__ __forceinline__ bool lookup(const TableView &T, uint32_t g, uint64_t 
     if (T.dense_open) {
         slot = dense_slot(T.dense_open, (uint32_t)key & 0xFFu);
         return T.keys[entry(T, slot, g)] == key;
+    }
+    if (T.perfect_n) {
+        slot = perfect_slot(T, key);
+        return slot != SGK_NOSLOT && T.keys[entry(T, slot, g)] == key;
     }
     uint32_t s = home_slot(key, T.log_cap);
     for (uint32_t i = 0; i < T.cap; i++) {

@@ -2,7 +2,8 @@
 """ncu launch list of bench.py's k_rollout_private launches -> profiles/rollout_issue.json
 and profiles/rollout_traffic.json.
 
-    ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+    ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\
+sm__inst_executed_pipe_alu.sum,sm__inst_executed_pipe_fma.sum \
         --clock-control none -k regex:k_rollout_private --csv --log-file gpurun_out/issue.csv \
         python bench.py --main-only --steps 20 --warmup 3
     python scripts/ncu_issue.py gpurun_out/issue.csv r02
@@ -29,6 +30,10 @@ issue = {"kernel": "k_rollout_private<boat,philox>",
                    "--steps 20 --warmup 3 (launch i of the list = bench launch i: 3 warm-up, 20 timed, 2 + 20 host-buffer)" % tag,
          "warp_instructions_by_launch": inst,
          "ncu_ms_by_launch": [l["gpu__time_duration.sum"] / 1e6 for l in launches]}
+for pipe in ("alu", "fma"):                                  # warp-instructions through each half-rate pipe
+    name = "sm__inst_executed_pipe_%s.sum" % pipe
+    if all(name in l for l in launches):
+        issue["%s_pipe_warp_instructions_by_launch" % pipe] = [l[name] for l in launches]
 json.dump(issue, open(os.path.join(ROOT, "profiles", "rollout_issue.json"), "w"), indent=1)
 timed = launches[3:23] if len(launches) >= 23 else launches
 rd = sum(l["dram__bytes_read.sum"] for l in timed) / len(timed)

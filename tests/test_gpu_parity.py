@@ -454,6 +454,34 @@ def test_boat_hashed_and_dense_tables_agree_with_oracle():
             _cmp_table(env, agent, sim, i)
 
 
+@pytest.mark.parametrize("cheat", [False, True])
+def test_sokoban_hashed_and_perfect_index_tables_agree_with_oracle(cheat):
+    """Sokoban level 0 private tables default to the perfect index
+    rank(agent) * 11 + rank(box) (capacity 128, no key reads, no probing); the
+    generic hashed layout (capacity 256) must give the same trajectories, Q
+    rows and key sets -- with the trace kernels and with the trace-free ones,
+    in calls that end mid-episode, on an episode end and after single steps."""
+    gf = _gf()
+    from oracle import cgrid
+    n, seed = 3000, 8
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=500)
+    chunks = (1, 7, 93, 1, 250, 148)
+    sim = cgrid.Sim(cgrid.SOKOBAN, n, seed=seed, cheat=cheat, **hp)
+    sim.rollout(sum(chunks))
+    for capacity in (128, 256):
+        for trace in (True, False):
+            env = gf.BatchedEnv("SideEffectsSokoban-v0", n, seed=seed)
+            env.set_trace(trace)
+            agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, capacity=capacity, **hp)
+            assert agent.capacity == capacity
+            for chunk in chunks:
+                agent.rollout(chunk, cheat=cheat)
+            agent.check()
+            _cmp_stats(env, sim, with_hash=trace)
+            for i in (0, 3, 31, 32, 1700, n - 1):
+                _cmp_table(env, agent, sim, i)
+
+
 def test_replica_sync_of_two_shared_tables_on_one_gpu():
     """sgk_tabq_delta_export / restore_base / delta_apply / rebase: two
     replicas trained on different environment shards end bit-identical and
