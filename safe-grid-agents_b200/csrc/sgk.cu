@@ -738,6 +738,17 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             const double upd = td_update(qs(slot, la), r, p.discount, p.lr, best);
             qs(slot, la) = upd;
             if (nslot == slot) { nrow = row_s(nslot); next_greedy = argmax_first(nrow); }
+        } else if (PERFECT) {
+            // the same single chain on tables in HBM: Q(s, a) is read back by index (the row was
+            // loaded a step ago: an L1 hit off the critical path) instead of a select tree over the
+            // register copy, and the register copy of the successor row is patched only when the
+            // update hit it
+            double best;
+            next_greedy = argmax_first(nrow, best);
+            double *q_sa = p.T.q + entry(p.T, slot, g) * SGK_NA + la;
+            const double upd = td_update(*q_sa, r, p.discount, p.lr, best);
+            *q_sa = upd;
+            if (nslot == slot) { row_set_if(nrow, true, la, upd); next_greedy = argmax_first(nrow); }
         } else {
             const double upd = td_update(row_get(row, la), r, p.discount, p.lr, row_max(nrow));
             store_q(p.T, g, slot, la, upd);
@@ -759,7 +770,7 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             if (SSRL) { ssrl_episode_end<DENSE>(p, i, i, st, n_hist, visits); n_hist = 0; visits = 0ull; }
             if (episodic) {
                 e.flags |= SGK_F_DONE;
-                greedy = DENSE ? next_greedy : argmax_first(row);
+                greedy = (DENSE || PERFECT) ? next_greedy : argmax_first(row);
                 fresh = true;
                 return --episodes_left == 0;
             }
@@ -779,15 +790,16 @@ k_rollout_private(const __grid_constant__ RolloutArgs p)
             } else if (PERFECT) {
                 slot = perfect_of();
                 row = load_row(p.T, g, slot);
+                next_greedy = argmax_first(row);
             } else if (lookup(p.T, g, key, slot)) {
                 row = load_row(p.T, g, slot);
             }
         }
-        greedy = DENSE ? next_greedy : argmax_first(row);
+        greedy = (DENSE || PERFECT) ? next_greedy : argmax_first(row);
         fresh = o.done;
         return false;
     };
-    if constexpr (DENSE && Rng::kCounterMode) {
+    if constexpr ((DENSE || PERFECT) && Rng::kCounterMode) {
         // Dense tables are issue-bound: walk the steps in the
         // pairs that share one agent Philox call.  The call of the NEXT pair is
         // computed beside this pair's first step, so its rounds fill the issue
