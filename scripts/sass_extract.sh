@@ -6,7 +6,7 @@ out=${1:-profiles/r02_sass_summary.txt}
 {
 echo "cuobjdump -sass $so -- per-kernel counts of tensor-core / TMEM / TMA instructions ($(date -u +%F))"
 echo "nvcc $(nvcc --version | grep release | sed 's/.*release //')"
-for k in k_mlp_forward_ts k_mlp_backward_fused k_wgrad_mn k_mlp_backward_data_tc k_wgrad_tc "k_rollout_privateILi0E12PhiloxStreamLb0ELb0ELb1E"; do
+for k in k_mlp_forward_ts k_mlp_backward_fused k_wgrad_mn k_mlp_backward_data_tc k_wgrad_tc "k_rollout_privateILi0E12PhiloxStreamLb0ELb0ELi1ELi0E" "k_rollout_privateILi1E12PhiloxStreamLb0ELb0ELi2E"; do
   for fn in $(cuobjdump -sass $so 2>/dev/null | grep "Function :" | grep "$k" | awk '{print $3}' | sort -u); do
     echo; echo "== $(echo $fn | c++filt)"
     cuobjdump -sass -fun "$fn" $so 2>/dev/null | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's/^\s+\/\*[0-9a-f]+\*\/\s+//' | awk '{print $1}' | sed 's/;$//' > /tmp/sass_ops.txt
