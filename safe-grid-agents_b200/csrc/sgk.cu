@@ -561,10 +561,10 @@ __device__ __forceinline__ void ssrl_episode_end(const RolloutArgs &p, int64_t i
 // where the selects between observed and hidden reward are a measurable share of the ALU pipe)
 // TABLE: 0 = hashed tables in HBM; 1 = dense tables held in shared memory (boat race); 2 = perfect-index
 // tables in HBM (sokoban level 0: slot computed from the state, no key reads, no probing)
-template <int KIND, class Rng, bool TRACE, bool SSRL, int TABLE, int CHEAT = -1>
 #ifndef SGK_BOAT_MINBLOCKS
 #define SGK_BOAT_MINBLOCKS 1
 #endif
+template <int KIND, class Rng, bool TRACE, bool SSRL, int TABLE, int CHEAT = -1>
 __global__ void __launch_bounds__(SGK_BLOCK_ROLLOUT, (KIND == 1 && !SSRL) ? 7 : (KIND == 0 && !SSRL) ? SGK_BOAT_MINBLOCKS : 1)
 k_rollout_private(const __grid_constant__ RolloutArgs p)
 {
