@@ -169,7 +169,11 @@ int sgk_env_totals(const sgk_env *env, double *totals_out, void *stream);
  * (common/agents/value.py:31): an open-addressing table of float64 rows keyed
  * by a lossless 64-bit packing of the board.  `q_mode` selects private
  * (n_tables == env count) or shared (one table); `capacity` is slots per
- * table (power of two; 0 = per-kind default). */
+ * table (power of two; 0 = per-kind default).  Private tables of two levels
+ * are not hashed at their default capacity: boat race (8) is addressed by the
+ * rank of the agent's cell among the open cells, side-effects sokoban level 0
+ * (128) by rank(agent) * 11 + rank(box) -- same rows, same key set, no
+ * probing; any other capacity selects the generic hashed layout. */
 int sgk_tabq_create(const sgk_env *env, int q_mode, int64_t capacity, sgk_tabq **out);
 int sgk_tabq_destroy(sgk_tabq *q);
 int64_t sgk_tabq_capacity(const sgk_tabq *q);
