@@ -50,7 +50,16 @@ def _kind(kind):
     return int(kind)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream():
+    """torch's current stream as a C pointer.  The two raw accessors skip the
+    Python-side device bookkeeping of torch.cuda.current_stream() (15 us per
+    call, several calls per episode on the single-environment drop-in path)."""
+    if _raw_stream is not None and _raw_device is not None:
+        return ctypes.c_void_p(_raw_stream(_raw_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
