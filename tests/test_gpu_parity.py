@@ -337,6 +337,31 @@ def test_table_full_and_replay_dry_are_reported():
         agent.check()
 
 
+def test_perfect_index_table_rejects_a_board_it_has_no_slot_for():
+    """Sokoban's default private tables are addressed by the ranks of the agent
+    and box cells among the non-wall cells.  A board that is not an observation
+    of the level (here: the box painted onto a wall cell) has no slot: the
+    unfused call must not touch any row and the next synchronising call must
+    fail loudly -- never alias another state's row."""
+    gf = _gf()
+    env = gf.BatchedEnv("SideEffectsSokoban-v0", 4, seed=2)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE)
+    boards = env.reset().to(torch.uint8).reshape(4, -1).clone()
+    good = agent.act(boards, step=5)
+    agent.check()
+    before = [agent.export(i) for i in range(4)]
+    bad = boards.clone()
+    bad[bad == 4] = 1              # lift the box ...
+    bad[:, 0] = 4                  # ... onto the corner wall
+    agent.act(bad, step=6)
+    with pytest.raises(gf.SgkError):
+        agent.check()
+    for i in range(4):             # the legitimate rows and keys are untouched
+        keys, rows = agent.export(i)[:2]
+        assert np.array_equal(keys, before[i][0]) and np.array_equal(rows, before[i][1])
+    assert good.shape[0] == 4
+
+
 # ------------------------------------------------------------------ full size
 def test_full_size_boat_65536_envs_bit_exact():
     """BASELINE config 2 at full width: 65,536 lock-step boat races, private Q,
