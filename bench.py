@@ -291,7 +291,12 @@ def run_ours(args, out):
             kend[k].record()
             env.totals_device(stats[k])
             ends[k].record()
-        starts[K].record()                    # sync interval ends: one collective over all K rows
+        # sync interval ends: one collective over all K rows.  The ranks are re-aligned first
+        # (untimed): each rank's clock is the sum of its own steps, so what it waited for the
+        # others' UNTIMED gaps (L2 flushes, launch jitter of eight Python processes) is not
+        # work of the path; the slowest rank's steps still set the result (max over ranks).
+        barrier()
+        starts[K].record()
         all_reduce_totals(stats)
         ends[K].record()
         barrier()
@@ -393,7 +398,9 @@ def run_ours(args, out):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": n, "locksteps_per_call": T,
                        "q_mode": "private", "rng": "philox4x32-10", "l2": "flushed between timed iterations (256 MiB memset)",
-                       "episodes_finished": episodes_finished},
+                       "episodes_finished": episodes_finished,
+                       "multi_gpu_timing": "per rank: sum of its K device-timed steps + the closing statistics collective, "
+                                           "entered after an untimed barrier; value uses the max over ranks"},
             "roofline": roof,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "l2": "flushed before every step", "timed": "host wall clock around each sgk_rollout_tabq_host call"},
