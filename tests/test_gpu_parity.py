@@ -337,6 +337,28 @@ def test_table_full_and_replay_dry_are_reported():
         agent.check()
 
 
+@pytest.mark.parametrize("env_id,kind", [("BoatRace-v0", 0), ("SideEffectsSokoban-v0", 1)])
+@pytest.mark.parametrize("n", [1, 33, 129])
+def test_trace_free_product_kernels_at_ragged_sizes(env_id, kind, n):
+    """The two specialised product kernels (boat: dense tables + counted rewards,
+    sokoban: perfect-index tables) with environment counts that leave a warp
+    and a block partly empty, odd call lengths and an odd first step."""
+    gf = _gf()
+    from oracle import cgrid
+    seed = 5 + n
+    hp = dict(lr=0.5, discount=0.99, epsilon=0.01, epsilon_anneal=300)
+    env = gf.BatchedEnv(env_id, n, seed=seed)
+    agent = gf.BatchedTabularQ(env, gf.Q_PRIVATE, **hp)
+    sim = cgrid.Sim(kind, n, seed=seed, **hp)
+    for chunk in (3, 200, 1, 97):
+        agent.rollout(chunk)
+        sim.rollout(chunk)
+    agent.check()
+    _cmp_stats(env, sim, with_hash=False)
+    for i in sorted({0, n // 2, n - 1}):
+        _cmp_table(env, agent, sim, i)
+
+
 def test_perfect_index_table_rejects_a_board_it_has_no_slot_for():
     """Sokoban's default private tables are addressed by the ranks of the agent
     and box cells among the non-wall cells.  A board that is not an observation
