@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 ]
 # SGK_FAST_BUILD=1: optimise each translation unit's kernels on all cores (3m40 -> 1m20).  Development
 # only: measured -2.8 % on the headline rollout kernel (4.61 -> 4.74 ms per launch, same box A/B,
-# profiles/r02_notes.md), so release builds -- build() below, what the driver runs -- do without.
+# DESIGN.md section 4), so release builds -- build() below, what the driver runs -- do without.
 FAST_FLAGS = ["--split-compile", "0"]
 
 
